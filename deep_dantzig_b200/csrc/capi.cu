@@ -1,0 +1,368 @@
+// C ABI (include/ddb200.h): context management, kernel-plan selection, launch plumbing, host-buffer flavours.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/ddb200.h"
+#include "common.cuh"
+
+namespace ddb {
+size_t generic_smem_bytes(int m, int n, bool smem_tab);
+cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, int block, cudaStream_t st);
+cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, int n, double density, double* A,
+                            double* b, double* c, double* x0, int sm_count, cudaStream_t st, int* launches);
+bool regtile_supported(int m, int n);
+cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
+size_t regtile_scratch_bytes(int m, int n, int sm_count);
+}  // namespace ddb
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) return fail(DDB_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+namespace {
+constexpr int kCounters = 64;
+constexpr int kSlots = 2;   // double buffering of the host-buffer flavours
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    DevBuf A, b, c, mask, status, x, obj, labels, nact, piv, ties, viol;
+};
+}  // namespace
+
+struct ddb_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    int64_t smem_optin = 0;
+    unsigned long long* counters = nullptr;
+    int next_counter = 0;
+    DevBuf scratch;            // global tableau slabs / register-tile scratch
+    cudaEvent_t scratch_free = nullptr;
+    bool scratch_in_use = false;
+    DevBuf genA, genb, genc;   // fused generate->solve chunk buffers
+    Slot slots[kSlots];
+    int forced_plan = -1;
+    int64_t launches = 0;
+};
+
+static int ensure(DevBuf& buf, size_t bytes) {
+    if (bytes <= buf.cap) return DDB_OK;
+    if (buf.p) cudaFree(buf.p);
+    buf.p = nullptr;
+    buf.cap = 0;
+    cudaError_t e = cudaMalloc(&buf.p, bytes);
+    if (e != cudaSuccess) return fail(DDB_ENOMEM, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    buf.cap = bytes;
+    return DDB_OK;
+}
+
+extern "C" int ddb_abi_version(void) { return DDB_ABI_VERSION; }
+extern "C" const char* ddb_last_error(void) { return g_err; }
+
+extern "C" int ddb_create(int device, ddb_ctx** out) {
+    if (!out) return fail(DDB_EINVAL, "ddb_create: out is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(DDB_ECUDA, "ddb_create: no CUDA device (%s); this library has no CPU path",
+                    cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(DDB_EINVAL, "ddb_create: device %d out of range", device);
+    CUDA_TRY(cudaSetDevice(device));
+    ddb_ctx* ctx = new (std::nothrow) ddb_ctx();
+    if (!ctx) return fail(DDB_ENOMEM, "ddb_create: out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->cc_major = prop.major;
+    ctx->cc_minor = prop.minor;
+    ctx->smem_optin = (int64_t)prop.sharedMemPerBlockOptin;
+    if (prop.major != 10)
+        return fail(DDB_EUNSUPPORTED, "ddb_create: device is sm_%d%d; this library is built for sm_100a only",
+                    prop.major, prop.minor);
+    CUDA_TRY(cudaMalloc(&ctx->counters, kCounters * sizeof(unsigned long long)));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
+    for (int i = 0; i < kSlots; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming));
+    }
+    *out = ctx;
+    return DDB_OK;
+}
+
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+}
+
+extern "C" int ddb_destroy(ddb_ctx* ctx) {
+    if (!ctx) return DDB_OK;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kSlots; ++i) {
+        Slot& s = ctx->slots[i];
+        DevBuf* all[] = {&s.A, &s.b, &s.c, &s.mask, &s.status, &s.x, &s.obj, &s.labels, &s.nact, &s.piv, &s.ties, &s.viol};
+        for (DevBuf* d : all) release(*d);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    release(ctx->scratch);
+    release(ctx->genA);
+    release(ctx->genb);
+    release(ctx->genc);
+    if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
+    if (ctx->counters) cudaFree(ctx->counters);
+    delete ctx;
+    return DDB_OK;
+}
+
+extern "C" int ddb_device_info(ddb_ctx* ctx, int* sm_count, int* cc_major, int* cc_minor, int64_t* smem_optin) {
+    if (!ctx) return fail(DDB_EINVAL, "ddb_device_info: ctx is NULL");
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (cc_major) *cc_major = ctx->cc_major;
+    if (cc_minor) *cc_minor = ctx->cc_minor;
+    if (smem_optin) *smem_optin = ctx->smem_optin;
+    return DDB_OK;
+}
+
+extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static int auto_plan(const ddb_ctx* ctx, int m, int n) {
+    if (ddb::regtile_supported(m, n)) return 0;
+    if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
+    return 2;
+}
+
+extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
+    if (!ctx) return fail(DDB_EINVAL, "ddb_solve_plan: ctx is NULL");
+    if (m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_plan: m=%d n=%d", m, n);
+    if (n > 512) return fail(DDB_EUNSUPPORTED, "ddb_solve_plan: n=%d > 512 is not supported yet", n);
+    int plan = ctx->forced_plan >= 0 ? ctx->forced_plan : auto_plan(ctx, m, n);
+    if (plan == 0 && !ddb::regtile_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "register-tiled kernel does not cover m=%d n=%d", m, n);
+    if (plan == 1 && (int64_t)ddb::generic_smem_bytes(m, n, true) > ctx->smem_optin)
+        return fail(DDB_EUNSUPPORTED, "shared-memory tableau does not fit for m=%d n=%d", m, n);
+    return plan;
+}
+
+extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
+    if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
+    if (plan < -1 || plan > 2) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
+    ctx->forced_plan = plan;
+    return DDB_OK;
+}
+
+extern "C" int ddb_generate_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                double density, double* A, double* b, double* c, double* x0, void* stream) {
+    if (!ctx || !A || !b || !c) return fail(DDB_EINVAL, "ddb_generate_dev: NULL argument");
+    if (B < 0 || m < 1 || n < 1 || !(density > 0.0 && density <= 1.0))
+        return fail(DDB_EINVAL, "ddb_generate_dev: B=%lld m=%d n=%d density=%g", (long long)B, m, n, density);
+    if (B == 0) return DDB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    int launches = 0;
+    CUDA_TRY(ddb::launch_generate(key, first_instance, B, m, n, density, A, b, c, x0, ctx->sm_count,
+                                  (cudaStream_t)stream, &launches));
+    ctx->launches += launches;
+    return DDB_OK;
+}
+
+static int pick_block(int m, int n) {
+    const long long e = (long long)m * n;
+    if (e <= 2048) return 128;
+    if (e <= 8192) return 256;
+    if (e <= 16384) return 512;
+    return 1024;
+}
+
+extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b,
+                                   const double* c, double threshold, const uint8_t* row_mask, int32_t* status,
+                                   double* x, double* obj, uint8_t* labels, int32_t* n_active, int32_t* pivots,
+                                   int32_t* ties, int32_t* violations, void* stream) {
+    if (!ctx || !A || !b || !c || !status || !labels) return fail(DDB_EINVAL, "ddb_solve_label_dev: NULL argument");
+    if (B < 0 || m < 1 || n < 1 || !(threshold >= 0.0))
+        return fail(DDB_EINVAL, "ddb_solve_label_dev: B=%lld m=%d n=%d threshold=%g", (long long)B, m, n, threshold);
+    if (B == 0) return DDB_OK;
+    const int plan = ddb_solve_plan(ctx, m, n);
+    if (plan < 0) return plan;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+
+    ddb::SolveArgs a;
+    a.m = m; a.n = n; a.B = B;
+    a.A = A; a.b = b; a.c = c; a.row_mask = row_mask; a.thr = threshold;
+    a.status = status; a.x = x; a.obj = obj; a.labels = labels; a.n_active = n_active;
+    a.pivots = pivots; a.ties = ties; a.violations = violations;
+    a.max_iter = 50 * (m + n);
+    a.gtab = nullptr;
+    a.counter = ctx->counters + ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
+    CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+
+    if (plan == 0) {
+        const size_t need = ddb::regtile_scratch_bytes(m, n, ctx->sm_count);
+        if (need) {
+            if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
+            if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
+            int rc = ensure(ctx->scratch, need);
+            if (rc) return rc;
+            a.gtab = (double*)ctx->scratch.p;
+        }
+        CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
+        if (need) {
+            CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
+            ctx->scratch_in_use = true;
+        }
+        ctx->launches += 1;
+        return DDB_OK;
+    }
+
+    const bool smem_tab = (plan == 1);
+    const int block = pick_block(m, n);
+    const size_t smem = ddb::generic_smem_bytes(m, n, smem_tab);
+    // persistent grid: as many CTAs as are co-resident (bounded by shared memory and threads), never more than B
+    int per_sm = (int)((size_t)ctx->smem_optin / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int by_threads = 2048 / block;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 16) per_sm = 16;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > B) grid = B;
+    if (!smem_tab) {
+        const size_t need = (size_t)grid * m * n * sizeof(double);
+        if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
+        if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
+        int rc = ensure(ctx->scratch, need);
+        if (rc) return rc;
+        a.gtab = (double*)ctx->scratch.p;
+    }
+    CUDA_TRY(ddb::launch_simplex_generic(a, smem_tab, (int)grid, block, st));
+    if (!smem_tab) {
+        CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
+        ctx->scratch_in_use = true;
+    }
+    ctx->launches += 1;
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer flavour: chunked, two slots in flight (H2D of chunk k+1 overlaps the solve of chunk k)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ddb_solve_label_host(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b,
+                                    const double* c, double threshold, const uint8_t* row_mask, int32_t* status,
+                                    double* x, double* obj, uint8_t* labels, int32_t* n_active, int32_t* pivots,
+                                    int32_t* ties, int32_t* violations) {
+    if (!ctx || !A || !b || !c || !status || !labels) return fail(DDB_EINVAL, "ddb_solve_label_host: NULL argument");
+    if (B < 0 || m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_label_host: B=%lld m=%d n=%d", (long long)B, m, n);
+    if (B == 0) return DDB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
+    int64_t chunk = (int64_t)((size_t)(256u << 20) / per_lp);
+    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > B) chunk = B;
+    int rc = DDB_OK;
+    int k = 0;
+    for (int64_t off = 0; off < B; off += chunk, ++k) {
+        const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
+        Slot& s = ctx->slots[k % kSlots];
+        CUDA_TRY(cudaEventSynchronize(s.done));   // previous use of this slot has drained
+        if ((rc = ensure(s.A, (size_t)nb * m * n * 8))) return rc;
+        if ((rc = ensure(s.b, (size_t)nb * m * 8))) return rc;
+        if ((rc = ensure(s.c, (size_t)nb * n * 8))) return rc;
+        if ((rc = ensure(s.status, (size_t)nb * 4))) return rc;
+        if ((rc = ensure(s.labels, (size_t)nb * m))) return rc;
+        if (row_mask && (rc = ensure(s.mask, (size_t)nb * m))) return rc;
+        if (x && (rc = ensure(s.x, (size_t)nb * n * 8))) return rc;
+        if (obj && (rc = ensure(s.obj, (size_t)nb * 8))) return rc;
+        if (n_active && (rc = ensure(s.nact, (size_t)nb * 4))) return rc;
+        if (pivots && (rc = ensure(s.piv, (size_t)nb * 16))) return rc;
+        if (ties && (rc = ensure(s.ties, (size_t)nb * 4))) return rc;
+        if (violations && (rc = ensure(s.viol, (size_t)nb * 4))) return rc;
+        cudaStream_t st = s.stream;
+        CUDA_TRY(cudaMemcpyAsync(s.A.p, A + (size_t)off * m * n, (size_t)nb * m * n * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.b.p, b + (size_t)off * m, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.c.p, c + (size_t)off * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, st));
+        if (row_mask)
+            CUDA_TRY(cudaMemcpyAsync(s.mask.p, row_mask + (size_t)off * m, (size_t)nb * m, cudaMemcpyHostToDevice, st));
+        rc = ddb_solve_label_dev(ctx, nb, m, n, (const double*)s.A.p, (const double*)s.b.p, (const double*)s.c.p,
+                                 threshold, row_mask ? (const uint8_t*)s.mask.p : nullptr, (int32_t*)s.status.p,
+                                 x ? (double*)s.x.p : nullptr, obj ? (double*)s.obj.p : nullptr, (uint8_t*)s.labels.p,
+                                 n_active ? (int32_t*)s.nact.p : nullptr, pivots ? (int32_t*)s.piv.p : nullptr,
+                                 ties ? (int32_t*)s.ties.p : nullptr, violations ? (int32_t*)s.viol.p : nullptr, st);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(status + off, s.status.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(labels + (size_t)off * m, s.labels.p, (size_t)nb * m, cudaMemcpyDeviceToHost, st));
+        if (x) CUDA_TRY(cudaMemcpyAsync(x + (size_t)off * n, s.x.p, (size_t)nb * n * 8, cudaMemcpyDeviceToHost, st));
+        if (obj) CUDA_TRY(cudaMemcpyAsync(obj + off, s.obj.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
+        if (n_active) CUDA_TRY(cudaMemcpyAsync(n_active + off, s.nact.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (pivots) CUDA_TRY(cudaMemcpyAsync(pivots + (size_t)off * 4, s.piv.p, (size_t)nb * 16, cudaMemcpyDeviceToHost, st));
+        if (ties) CUDA_TRY(cudaMemcpyAsync(ties + off, s.ties.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        if (violations)
+            CUDA_TRY(cudaMemcpyAsync(violations + off, s.viol.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaEventRecord(s.done, st));
+    }
+    for (int i = 0; i < kSlots; ++i) CUDA_TRY(cudaEventSynchronize(ctx->slots[i].done));
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// fused generate -> solve -> label on device-resident outputs
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                            double density, double threshold, int32_t* status, double* x, double* obj,
+                                            uint8_t* labels, int32_t* n_active, int32_t* pivots, int32_t* ties,
+                                            double* A_out, double* b_out, double* c_out, void* stream) {
+    if (!ctx || !status || !labels) return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: NULL argument");
+    if (B < 0 || m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: B=%lld m=%d n=%d", (long long)B, m, n);
+    if (B == 0) return DDB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
+    // chunk sized so the generated instances are still in the 126 MB L2 when the solver reads them
+    int64_t chunk = (int64_t)((size_t)(64u << 20) / per_lp);
+    const int64_t min_chunk = (int64_t)ctx->sm_count * 4;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > B) chunk = B;
+    const bool keep = A_out && b_out && c_out;
+    int rc;
+    if (!keep) {
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // scratch reuse across calls
+        if ((rc = ensure(ctx->genA, (size_t)chunk * m * n * 8))) return rc;
+        if ((rc = ensure(ctx->genb, (size_t)chunk * m * 8))) return rc;
+        if ((rc = ensure(ctx->genc, (size_t)chunk * n * 8))) return rc;
+    }
+    for (int64_t off = 0; off < B; off += chunk) {
+        const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
+        double* Ap = keep ? A_out + (size_t)off * m * n : (double*)ctx->genA.p;
+        double* bp = keep ? b_out + (size_t)off * m : (double*)ctx->genb.p;
+        double* cp = keep ? c_out + (size_t)off * n : (double*)ctx->genc.p;
+        rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, stream);
+        if (rc) return rc;
+        rc = ddb_solve_label_dev(ctx, nb, m, n, Ap, bp, cp, threshold, nullptr, status + off,
+                                 x ? x + (size_t)off * n : nullptr, obj ? obj + off : nullptr,
+                                 labels + (size_t)off * m, n_active ? n_active + off : nullptr,
+                                 pivots ? pivots + (size_t)off * 4 : nullptr, ties ? ties + off : nullptr, nullptr,
+                                 stream);
+        if (rc) return rc;
+    }
+    return DDB_OK;
+}

@@ -1,0 +1,115 @@
+// Shared declarations for the ddb200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ddb {
+
+// Tolerances of the device simplex (absolute; instance data is O(1), see DESIGN.md "Numerics").
+constexpr double kTolPivot = 1e-9;   // smallest |entry| accepted as a ratio-test pivot
+constexpr double kTolFeas  = 1e-9;   // primal / dual feasibility tolerance
+constexpr double kTolCrash = 1e-7;   // smallest |entry| accepted as a crash pivot
+
+// Row states of the condensed tableau.
+enum : uint8_t { ROW_LIVE = 0, ROW_CRASHED = 1, ROW_EXCLUDED = 2 };
+
+// Status codes == Gurobi's (reference src/data/gurobi_lp.py:447-461).
+enum : int { ST_OPTIMAL = 2, ST_INFEASIBLE = 3, ST_UNBOUNDED = 5, ST_ITERATION_LIMIT = 7, ST_NUMERIC = 12 };
+
+struct SolveArgs {
+    int m, n;
+    long long B;
+    const double* A;
+    const double* b;
+    const double* c;
+    const uint8_t* row_mask;   // nullable
+    double thr;
+    int* status;
+    double* x;                 // nullable
+    double* obj;               // nullable
+    uint8_t* labels;
+    int* n_active;             // nullable
+    int* pivots;               // nullable, [B,4]
+    int* ties;                 // nullable
+    int* violations;           // nullable
+    unsigned long long* counter;   // work queue
+    double* gtab;              // per-CTA global tableau slabs (plan 2) or per-CTA scratch (plan 0)
+    int max_iter;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP) helpers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// warp argmin helpers with Bland (lowest variable index) tie-breaking
+// ---------------------------------------------------------------------------------------------------------
+struct Cand {
+    double val;   // key to minimise
+    int var;      // tie-break: lowest variable index wins
+    int idx;      // payload (row or column position)
+};
+__device__ __forceinline__ bool cand_better(double v1, int var1, double v2, int var2) {
+    return (v1 < v2) || (v1 == v2 && var1 < var2);
+}
+__device__ __forceinline__ Cand warp_argmin(Cand c) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double ov = __shfl_xor_sync(0xffffffffu, c.val, off);
+        int ovar = __shfl_xor_sync(0xffffffffu, c.var, off);
+        int oidx = __shfl_xor_sync(0xffffffffu, c.idx, off);
+        if (cand_better(ov, ovar, c.val, c.var)) {
+            c.val = ov;
+            c.var = ovar;
+            c.idx = oidx;
+        }
+    }
+    return c;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+constexpr double kInf = 1e300;
+constexpr int kBigVar = 0x7fffffff;
+
+}  // namespace ddb

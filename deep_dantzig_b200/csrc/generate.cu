@@ -1,0 +1,135 @@
+// Counter-based instance generator (throughput mode).
+//
+// Replaces the serial per-seed loop of the reference (src/data/randomlp_dataset.py:58-63) and the generator part
+// of create_lp_problem (:76-86):  A = randn(m,n); b = A.randn(n) + |randn(m)|; c = |randn(n)|.
+// The reference's stream is numpy's legacy MT19937 + polar Gaussian, which a counter-based generator cannot
+// reproduce bit for bit; parity mode therefore uploads numpy-generated instances, and this generator is pinned
+// by Philox4x32-10 known-answer tests on the integer level (oracle/philox.py, tests/test_philox.py).
+//
+// Instance i is a pure function of (key, i): Philox4x32-10, key = (key_lo, key_hi),
+// counter = (pair index, stream id, i_lo, i_hi).  One Philox block -> two 53-bit uniforms -> one Box-Muller
+// pair -> normals for elements 2*pair and 2*pair+1 of that stream.
+#include "common.cuh"
+
+namespace ddb {
+
+enum : uint32_t { STREAM_A = 0, STREAM_X0 = 1, STREAM_EPS = 2, STREAM_C = 3, STREAM_MASK = 4 };
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// (0,1] uniform from two 32-bit words: 27 + 26 = 53 bits, plus one so that log() is finite.
+__device__ __forceinline__ double u53_open0(uint32_t hi, uint32_t lo) {
+    const unsigned long long v = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
+    return (double)(v + 1ull) * 0x1.0p-53;
+}
+// [0,1) uniform.
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
+    const unsigned long long v = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
+    return (double)v * 0x1.0p-53;
+}
+
+__device__ __forceinline__ void normal_pair(uint64_t key, uint64_t inst, uint32_t stream, uint32_t pair, double& z0,
+                                            double& z1) {
+    uint32_t o[4];
+    philox4x32_10(pair, stream, (uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
+    const double u1 = u53_open0(o[0], o[1]);
+    const double u2 = u53(o[2], o[3]);
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// A: one thread per element pair, grid-stride, coalesced 16-byte stores when the pair is aligned.
+__global__ void __launch_bounds__(256) generate_A_kernel(uint64_t key, long long first, long long B, int m, int n,
+                                                         double density, double* __restrict__ A) {
+    const long long per = (long long)m * n;
+    const long long pairs_per = (per + 1) / 2;
+    const long long total = B * pairs_per;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total;
+         t += (long long)gridDim.x * blockDim.x) {
+        const long long k = t / pairs_per;
+        const uint32_t pair = (uint32_t)(t - k * pairs_per);
+        const uint64_t inst = (uint64_t)(first + k);
+        double z0, z1;
+        normal_pair(key, inst, STREAM_A, pair, z0, z1);
+        if (density < 1.0) {
+            uint32_t o[4];
+            philox4x32_10(pair, STREAM_MASK, (uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)key,
+                          (uint32_t)(key >> 32), o);
+            if (u53(o[0], o[1]) >= density) z0 = 0.0;
+            if (u53(o[2], o[3]) >= density) z1 = 0.0;
+        }
+        double* dst = A + k * per;
+        const long long e = 2ll * pair;
+        dst[e] = z0;
+        if (e + 1 < per) dst[e + 1] = z1;
+    }
+}
+
+// b, c, x0: one CTA per instance (A is read back, normally from L2).
+__global__ void __launch_bounds__(256) generate_bc_kernel(uint64_t key, long long first, long long B, int m, int n,
+                                                          const double* __restrict__ A, double* __restrict__ b,
+                                                          double* __restrict__ c, double* __restrict__ x0out) {
+    extern __shared__ double x0s[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    for (long long k = blockIdx.x; k < B; k += gridDim.x) {
+        const uint64_t inst = (uint64_t)(first + k);
+        for (int pr = tid; pr < (n + 1) / 2; pr += blockDim.x) {
+            double z0, z1;
+            normal_pair(key, inst, STREAM_X0, (uint32_t)pr, z0, z1);
+            x0s[2 * pr] = z0;
+            if (2 * pr + 1 < n) x0s[2 * pr + 1] = z1;
+            normal_pair(key, inst, STREAM_C, (uint32_t)pr, z0, z1);
+            c[k * n + 2 * pr] = fabs(z0);
+            if (2 * pr + 1 < n) c[k * n + 2 * pr + 1] = fabs(z1);
+        }
+        __syncthreads();
+        if (x0out)
+            for (int j = tid; j < n; j += blockDim.x) x0out[k * n + j] = x0s[j];
+        const double* Ak = A + k * (long long)m * n;
+        for (int i = warp; i < m; i += nw) {
+            double acc = 0.0;
+            for (int j = lane; j < n; j += 32) acc = fma(Ak[(long long)i * n + j], x0s[j], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) {
+                double z0, z1;
+                normal_pair(key, inst, STREAM_EPS, (uint32_t)(i >> 1), z0, z1);
+                b[k * m + i] = acc + fabs((i & 1) ? z1 : z0);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, int n, double density, double* A,
+                            double* b, double* c, double* x0, int sm_count, cudaStream_t st, int* launches) {
+    const long long pairs = B * (((long long)m * n + 1) / 2);
+    long long blocks = (pairs + 255) / 256;
+    const long long cap = (long long)sm_count * 32;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    generate_A_kernel<<<(int)blocks, 256, 0, st>>>(key, first, B, m, n, density, A);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    long long g2 = B < (long long)sm_count * 8 ? B : (long long)sm_count * 8;
+    if (g2 < 1) g2 = 1;
+    generate_bc_kernel<<<(int)g2, 256, (size_t)(n + 1) * sizeof(double), st>>>(key, first, B, m, n, A, b, c, x0);
+    *launches += 2;
+    return cudaGetLastError();
+}
+
+}  // namespace ddb

@@ -1,0 +1,507 @@
+// Generic batched fp64 simplex: one LP per thread block, condensed tableau in shared memory (plan 1, staged
+// by 1-D bulk TMA) or in a per-CTA global-memory slab that lives in L2/HBM (plan 2, for shapes whose tableau
+// exceeds 227 KB).  Persistent CTAs pull instance indices from an atomic work queue because the work per LP
+// is bimodal (about half the instances at m = 2n are unbounded and exit early).
+//
+// Replaces, for a whole batch: LinProg model build + optimize + get_statuscode + get_active_constraints
+// (reference src/data/gurobi_lp.py:11-29, 370-465) and the label assembly of create_lp_problem
+// (reference src/data/randomlp_dataset.py:88-106).  The reference delegates the solve to Gurobi; the
+// algorithm below is ours, parity is on results.
+//
+// Dictionary kept per LP (primal orientation, condensed):
+//     sigma_i = s_i - sum_j P[i][j] nu_j        row i: constraint whose slack sigma_i is basic
+//     z       = z0  + sum_j g[j]  nu_j          nu_j: free x_j before the crash, then an active slack
+// Stages: (1) static-order crash: n Gauss-Jordan pivots that make every free x_j basic, rows taken in the
+// order of the cosine score a_i.c/|a_i| (rows most opposed to c first), column = largest |entry|;
+// (2) phase 1: dual-simplex-type pivots with artificial costs ghat = 1 until s >= 0;
+// (3) phase 2: Dantzig primal simplex until g >= 0; ties everywhere broken by lowest variable index (Bland);
+// (4) x from the rows frozen at the end of the crash, slack = b - A x recomputed from the caller's A,
+//     labels = |slack| <= threshold exactly as gurobi_lp.py:435-443.
+#include "common.cuh"
+
+namespace ddb {
+
+struct Sel {
+    double p;      // pivot element
+    double gk;     // g[k] before the pivot
+    double ghk;    // ghat[k] before the pivot
+    int r, k;
+    int flag;      // 0 = pivot, 1 = stage finished, 2 = infeasible / unbounded, 3 = skip row (crash)
+};
+
+struct Layout {
+    size_t tab, s, g, gh, colbuf, xbuf, sig, rowvar, colvar, colvar0, where, order, rowfree, rowstate, red, sel, bar, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+__host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
+    Layout L;
+    size_t off = 0;
+    L.tab = off;      off += smem_tab ? align_up((size_t)m * n * 8, 16) : 0;
+    L.s = off;        off += align_up((size_t)m * 8, 16);
+    L.g = off;        off += align_up((size_t)n * 8, 16);
+    L.gh = off;       off += align_up((size_t)n * 8, 16);
+    L.colbuf = off;   off += align_up((size_t)m * 8, 16);
+    L.xbuf = off;     off += align_up((size_t)n * 8, 16);
+    L.sig = off;      off += align_up((size_t)n * 8, 16);
+    L.rowvar = off;   off += align_up((size_t)m * 4, 16);
+    L.colvar = off;   off += align_up((size_t)n * 4, 16);
+    L.colvar0 = off;  off += align_up((size_t)n * 4, 16);
+    L.where = off;    off += align_up((size_t)m * 4, 16);
+    L.order = off;    off += align_up((size_t)m * 4, 16);
+    L.rowfree = off;  off += align_up((size_t)m * 4, 16);
+    L.rowstate = off; off += align_up((size_t)m, 16);
+    L.red = off;      off += 3 * 32 * 4;
+    L.sel = off;      off += align_up(sizeof(Sel), 16);
+    L.bar = off;      off += 16;
+    L.total = off;
+    return L;
+}
+
+size_t generic_smem_bytes(int m, int n, bool smem_tab) { return make_layout(m, n, smem_tab).total; }
+
+template <bool kSmemTab, int CPL>
+__global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int m = a.m, n = a.n;
+    const Layout L = make_layout(m, n, kSmemTab);
+    double* P = kSmemTab ? reinterpret_cast<double*>(smem_raw + L.tab)
+                         : a.gtab + (size_t)blockIdx.x * ((size_t)m * n);
+    double* s = reinterpret_cast<double*>(smem_raw + L.s);
+    double* g = reinterpret_cast<double*>(smem_raw + L.g);
+    double* gh = reinterpret_cast<double*>(smem_raw + L.gh);
+    double* colbuf = reinterpret_cast<double*>(smem_raw + L.colbuf);
+    double* xbuf = reinterpret_cast<double*>(smem_raw + L.xbuf);
+    double* sig = reinterpret_cast<double*>(smem_raw + L.sig);
+    int* rowvar = reinterpret_cast<int*>(smem_raw + L.rowvar);
+    int* colvar = reinterpret_cast<int*>(smem_raw + L.colvar);
+    int* colvar0 = reinterpret_cast<int*>(smem_raw + L.colvar0);
+    int* where = reinterpret_cast<int*>(smem_raw + L.where);
+    int* order = reinterpret_cast<int*>(smem_raw + L.order);
+    int* rowfree = reinterpret_cast<int*>(smem_raw + L.rowfree);
+    uint8_t* rowstate = smem_raw + L.rowstate;
+    Sel* sel = reinterpret_cast<Sel*>(smem_raw + L.sel);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    __shared__ long long cur_lp;
+
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    uint32_t bar_parity = 0;
+
+    if (kSmemTab) {
+        if (tid == 0) {
+            mbar_init(bar, 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+
+    // One pivot on (r, k).  Every thread calls it with the same arguments (read from *sel after a barrier).
+    auto do_pivot = [&](int r, int k, double p, bool crash_mode) {
+        const double rp = 1.0 / p;
+        // B: normalise the pivot row, pull the pivot column out into colbuf and zero it in place
+        for (int j = tid; j < n; j += nt) P[(size_t)r * n + j] = (j == k) ? rp : P[(size_t)r * n + j] * rp;
+        for (int i = tid; i < m; i += nt) {
+            double f = 0.0;
+            const uint8_t st = rowstate[i];
+            if (i != r && (st == ROW_LIVE || (crash_mode && st == ROW_CRASHED))) {
+                f = P[(size_t)i * n + k];
+                P[(size_t)i * n + k] = 0.0;
+            }
+            colbuf[i] = f;
+        }
+        if (tid == 0) {
+            s[r] *= rp;
+            sel->gk = g[k];
+            sel->ghk = gh[k];
+            g[k] = 0.0;
+            gh[k] = 0.0;
+        }
+        __syncthreads();
+        // C: rank-1 update of every other row, of s, g and ghat
+        double pr[CPL];
+#pragma unroll
+        for (int q = 0; q < CPL; ++q) {
+            const int j = lane + 32 * q;
+            pr[q] = (j < n) ? P[(size_t)r * n + j] : 0.0;
+        }
+        const double sr = s[r];
+        for (int i = warp; i < m; i += nw) {
+            const double f = colbuf[i];
+            if (f != 0.0) {
+                double* Pi = P + (size_t)i * n;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
+                }
+                if (lane == 0) s[i] = fma(-f, sr, s[i]);
+            }
+        }
+        {
+            const double gk = sel->gk, ghk = sel->ghk;
+            for (int j = tid; j < n; j += nt) {
+                const double prj = P[(size_t)r * n + j];
+                g[j] = fma(-gk, prj, g[j]);
+                gh[j] = fma(-ghk, prj, gh[j]);
+            }
+        }
+        __syncthreads();
+    };
+
+    for (;;) {
+        if (tid == 0) cur_lp = (long long)atomicAdd(a.counter, 1ull);
+        __syncthreads();
+        const long long lp = cur_lp;
+        if (lp >= a.B) break;
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;
+
+        // ---- stage the instance ------------------------------------------------------------------------
+        bool used_tma = false;
+        if (kSmemTab) {
+            const size_t bytesA = (size_t)m * n * 8;
+            const bool aligned = (bytesA % 16 == 0) && ((reinterpret_cast<uintptr_t>(Ag) & 15) == 0);
+            if (aligned) {
+                used_tma = true;
+                if (tid == 0) {
+                    fence_proxy_async();   // order earlier generic-proxy accesses of the tableau before the async writes
+                    mbar_expect_tx(bar, (uint32_t)bytesA);
+                    const uint32_t chunk = 32768;
+                    for (size_t off = 0; off < bytesA; off += chunk) {
+                        const uint32_t nb = (uint32_t)((bytesA - off < chunk) ? (bytesA - off) : chunk);
+                        tma_load_1d(reinterpret_cast<unsigned char*>(P) + off,
+                                    reinterpret_cast<const unsigned char*>(Ag) + off, nb, bar);
+                    }
+                }
+            }
+        }
+        if (!used_tma) {
+            for (size_t e = tid; e < (size_t)m * n; e += nt) P[e] = Ag[e];
+        }
+        for (int i = tid; i < m; i += nt) {
+            s[i] = bg[i];
+            rowvar[i] = i;
+            where[i] = i;   // >= 0: basic in that row; < 0: nonbasic in column -(w+1)
+            rowfree[i] = -1;
+            rowstate[i] = (mask && mask[i] == 0) ? ROW_EXCLUDED : ROW_LIVE;
+        }
+        for (int j = tid; j < n; j += nt) {
+            g[j] = cg[j];
+            gh[j] = 1.0;
+            colvar[j] = -1;
+        }
+        if (used_tma) {
+            mbar_wait(bar, bar_parity);
+            bar_parity ^= 1;
+        }
+        __syncthreads();
+
+        // ---- crash order: rank rows by a_i.c / |a_i| (ascending), excluded rows last -----------------------
+        for (int i = warp; i < m; i += nw) {
+            double dot = 0.0, nn = 0.0;
+            for (int j = lane; j < n; j += 32) {
+                const double v = P[(size_t)i * n + j];
+                dot = fma(v, g[j], dot);
+                nn = fma(v, v, nn);
+            }
+            dot = warp_sum(dot);
+            nn = warp_sum(nn);
+            if (lane == 0) colbuf[i] = (rowstate[i] == ROW_EXCLUDED) ? kInf : (nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5);
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += nt) {
+            const double v = colbuf[i];
+            int rank = 0;
+            for (int i2 = 0; i2 < m; ++i2) {
+                const double v2 = colbuf[i2];
+                rank += (v2 < v) || (v2 == v && i2 < i);
+            }
+            order[rank] = i;
+        }
+        __syncthreads();
+
+        int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
+        int status = ST_OPTIMAL;
+
+        // ---- stage 1: crash --------------------------------------------------------------------------------
+        for (int oi = 0; oi < m && npiv_crash < n; ++oi) {
+            const int r = order[oi];
+            if (rowstate[r] == ROW_EXCLUDED) break;   // uniform: shared memory read after a barrier
+            if (warp == 0) {
+                Cand cd{kInf, kBigVar, -1};
+                for (int j = lane; j < n; j += 32) {
+                    if (colvar[j] < 0) {
+                        const double v = -fabs(P[(size_t)r * n + j]);
+                        if (cand_better(v, j, cd.val, cd.var)) cd = Cand{v, j, j};
+                    }
+                }
+                cd = warp_argmin(cd);
+                if (lane == 0) {
+                    sel->r = r;
+                    sel->k = cd.idx;
+                    if (cd.idx < 0 || -cd.val < kTolCrash) {
+                        sel->flag = 3;
+                    } else {
+                        sel->flag = 0;
+                        sel->p = P[(size_t)r * n + cd.idx];
+                    }
+                }
+            }
+            __syncthreads();
+            const int flag = sel->flag, k = sel->k;
+            const double p = sel->p;
+            __syncthreads();   // everyone has read *sel before anyone rewrites it
+            if (flag == 3) continue;
+            do_pivot(r, k, p, true);
+            if (tid == 0) {
+                rowstate[r] = ROW_CRASHED;
+                rowfree[r] = k;
+                colvar[k] = r;
+                where[r] = -(k + 1);
+            }
+            ++npiv_crash;
+            __syncthreads();
+        }
+        for (int j = tid; j < n; j += nt) {
+            colvar0[j] = colvar[j];
+            gh[j] = 1.0;
+        }
+        __syncthreads();
+
+        // ---- stage 2: phase 1 (row-first pivots until s >= 0) ------------------------------------------------
+        for (;;) {
+            if (warp == 0) {
+                Cand cr{kInf, kBigVar, -1};
+                for (int i = lane; i < m; i += 32) {
+                    if (rowstate[i] == ROW_LIVE) {
+                        const double v = s[i];
+                        if (cand_better(v, rowvar[i], cr.val, cr.var)) cr = Cand{v, rowvar[i], i};
+                    }
+                }
+                cr = warp_argmin(cr);
+                int flag = 0, kk = -1;
+                if (cr.idx < 0 || cr.val >= -kTolFeas) {
+                    flag = 1;
+                } else {
+                    const int r = cr.idx;
+                    Cand ck{kInf, kBigVar, -1};
+                    for (int j = lane; j < n; j += 32) {
+                        const double e = P[(size_t)r * n + j];
+                        if (colvar[j] >= 0 && e < -kTolPivot) {
+                            const double ratio = fmax(gh[j], 0.0) / (-e);
+                            if (cand_better(ratio, colvar[j], ck.val, ck.var)) ck = Cand{ratio, colvar[j], j};
+                        }
+                    }
+                    ck = warp_argmin(ck);
+                    kk = ck.idx;
+                    if (kk < 0) flag = 2;
+                }
+                if (lane == 0) {
+                    sel->flag = flag;
+                    sel->r = cr.idx;
+                    sel->k = kk;
+                    if (flag == 0) sel->p = P[(size_t)cr.idx * n + kk];
+                }
+            }
+            __syncthreads();
+            const int flag = sel->flag, r = sel->r, k = sel->k;
+            const double p = sel->p;
+            __syncthreads();
+            if (flag == 1) break;
+            if (flag == 2) { status = ST_INFEASIBLE; break; }
+            if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+            do_pivot(r, k, p, false);
+            if (tid == 0) {
+                const int vr = rowvar[r], vk = colvar[k];
+                rowvar[r] = vk;
+                colvar[k] = vr;
+                where[vk] = r;
+                where[vr] = -(k + 1);
+            }
+            ++npiv_p1;
+            __syncthreads();
+        }
+
+        // ---- stage 3: phase 2 (column-first Dantzig pivots until g >= 0) -----------------------------------
+        while (status == ST_OPTIMAL) {
+            if (warp == 0) {
+                Cand ck{kInf, kBigVar, -1};
+                int free_unbounded = 0;
+                for (int j = lane; j < n; j += 32) {
+                    if (colvar[j] >= 0) {
+                        const double v = g[j];
+                        if (cand_better(v, colvar[j], ck.val, ck.var)) ck = Cand{v, colvar[j], j};
+                    } else if (fabs(g[j]) > kTolFeas) {
+                        free_unbounded = 1;   // a free direction with non-zero cost that no row constrains
+                    }
+                }
+                ck = warp_argmin(ck);
+                free_unbounded = __any_sync(0xffffffffu, free_unbounded);
+                int flag = 0, rr = -1;
+                if (free_unbounded) {
+                    flag = 2;
+                } else if (ck.idx < 0 || ck.val >= -kTolFeas) {
+                    flag = 1;
+                } else {
+                    const int k = ck.idx;
+                    Cand cr{kInf, kBigVar, -1};
+                    for (int i = lane; i < m; i += 32) {
+                        if (rowstate[i] == ROW_LIVE) {
+                            const double e = P[(size_t)i * n + k];
+                            if (e > kTolPivot) {
+                                const double ratio = fmax(s[i], 0.0) / e;
+                                if (cand_better(ratio, rowvar[i], cr.val, cr.var)) cr = Cand{ratio, rowvar[i], i};
+                            }
+                        }
+                    }
+                    cr = warp_argmin(cr);
+                    rr = cr.idx;
+                    if (rr < 0) flag = 2;
+                }
+                if (lane == 0) {
+                    sel->flag = flag;
+                    sel->r = rr;
+                    sel->k = ck.idx;
+                    if (flag == 0) sel->p = P[(size_t)rr * n + ck.idx];
+                }
+            }
+            __syncthreads();
+            const int flag = sel->flag, r = sel->r, k = sel->k;
+            const double p = sel->p;
+            __syncthreads();
+            if (flag == 1) break;
+            if (flag == 2) { status = ST_UNBOUNDED; break; }
+            if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+            do_pivot(r, k, p, false);
+            if (tid == 0) {
+                const int vr = rowvar[r], vk = colvar[k];
+                rowvar[r] = vk;
+                colvar[k] = vr;
+                where[vk] = r;
+                where[vr] = -(k + 1);
+            }
+            ++npiv_p2;
+            __syncthreads();
+        }
+
+        // ---- stage 4: x, objective, slacks, labels ---------------------------------------------------------
+        uint8_t* lab = a.labels + (size_t)lp * m;
+        int nact = 0, nties = 0, nviol = 0;
+        if (status == ST_OPTIMAL) {
+            for (int j = tid; j < n; j += nt) {
+                const int q = colvar0[j];
+                double v = 0.0;
+                if (q >= 0) {
+                    const int w = where[q];
+                    if (w >= 0) v = s[w];   // that constraint left the active set: its current slack
+                }
+                sig[j] = v;
+                xbuf[j] = 0.0;
+            }
+            __syncthreads();
+            for (int i = warp; i < m; i += nw) {
+                if (rowstate[i] == ROW_CRASHED) {
+                    double acc = 0.0;
+                    for (int j = lane; j < n; j += 32) acc = fma(P[(size_t)i * n + j], sig[j], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) xbuf[rowfree[i]] = s[i] - acc;
+                }
+            }
+            __syncthreads();
+            if (warp == 0) {
+                double acc = 0.0;
+                for (int j = lane; j < n; j += 32) acc = fma(cg[j], xbuf[j], acc);
+                acc = warp_sum(acc);
+                if (lane == 0 && a.obj) a.obj[lp] = acc;
+            }
+            if (a.x)
+                for (int j = tid; j < n; j += nt) a.x[(size_t)lp * n + j] = xbuf[j];
+            // slack from the caller's A (not the tableau), as the reference does from the solver's x
+            for (int i = warp; i < m; i += nw) {
+                double acc = 0.0;
+                for (int j = lane; j < n; j += 32) acc = fma(Ag[(size_t)i * n + j], xbuf[j], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    const double slack = bg[i] - acc;
+                    const double as = fabs(slack);
+                    const int active = as <= a.thr;
+                    lab[i] = (uint8_t)active;
+                    nact += active;
+                    int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
+                    if (rowstate[i] != ROW_EXCLUDED) tie |= (active != (where[i] < 0));
+                    nties += tie;
+                    nviol += (slack < -a.thr * 10.0);
+                }
+            }
+        } else {
+            for (int i = tid; i < m; i += nt) lab[i] = 0;
+            if (a.x)
+                for (int j = tid; j < n; j += nt) a.x[(size_t)lp * n + j] = 0.0;
+            if (tid == 0 && a.obj) a.obj[lp] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        // block-wide sums of the three counters (lane 0 of each warp holds partials)
+        __syncthreads();
+        int* red = reinterpret_cast<int*>(smem_raw + L.red);
+        if (lane == 0) {
+            red[warp * 3 + 0] = nact;
+            red[warp * 3 + 1] = nties;
+            red[warp * 3 + 2] = nviol;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t0 = 0, t1 = 0, t2 = 0;
+            for (int w = 0; w < nw; ++w) {
+                t0 += red[w * 3 + 0];
+                t1 += red[w * 3 + 1];
+                t2 += red[w * 3 + 2];
+            }
+            a.status[lp] = status;
+            if (a.n_active) a.n_active[lp] = t0;
+            if (a.ties) a.ties[lp] = t1;
+            if (a.violations) a.violations[lp] = t2;
+            if (a.pivots) {
+                int* pv = a.pivots + (size_t)lp * 4;
+                pv[0] = npiv_crash;
+                pv[1] = npiv_p1;
+                pv[2] = npiv_p2;
+                pv[3] = npiv_crash + npiv_p1 + npiv_p2;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launcher
+// ---------------------------------------------------------------------------------------------------------
+template <bool kSmemTab, int CPL>
+static cudaError_t launch_one(const SolveArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
+    auto kern = simplex_generic_kernel<kSmemTab, CPL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, block, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, int block, cudaStream_t st) {
+    const size_t smem = generic_smem_bytes(a.m, a.n, smem_tab);
+    const int cpl = (a.n + 31) / 32;
+#define DDB_DISPATCH(T)                                                        \
+    do {                                                                       \
+        if (cpl <= 1) return launch_one<T, 1>(a, grid, block, smem, st);       \
+        if (cpl <= 2) return launch_one<T, 2>(a, grid, block, smem, st);       \
+        if (cpl <= 4) return launch_one<T, 4>(a, grid, block, smem, st);       \
+        if (cpl <= 8) return launch_one<T, 8>(a, grid, block, smem, st);       \
+        if (cpl <= 16) return launch_one<T, 16>(a, grid, block, smem, st);     \
+        return cudaErrorInvalidValue;                                          \
+    } while (0)
+    if (smem_tab) DDB_DISPATCH(true);
+    DDB_DISPATCH(false);
+#undef DDB_DISPATCH
+}
+
+}  // namespace ddb

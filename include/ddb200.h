@@ -1,0 +1,122 @@
+/*
+ * ddb200.h -- C ABI of the B200-native generate -> solve -> label hot path of rodrgo/deep_dantzig.
+ *
+ * The reference has no FFI; its boundary for this path is a Python class surface.
+ * Each entry point below replaces the per-instance Python/Gurobi code cited beside it with one batched call.
+ * Plain pointers and sizes only.  `*_dev` entry points take DEVICE pointers and a CUDA stream handle
+ * (cudaStream_t passed as void*, NULL = default stream) and are asynchronous on that stream; `*_host`
+ * entry points take HOST pointers, do the host<->device copies themselves and return when results are in
+ * the caller's buffers.
+ *
+ * Every function returns 0 on success and a negative DDB_E* code on failure; ddb_last_error() gives the
+ * message for the calling thread.  Per-instance solver outcomes are reported in `status[]` using the Gurobi
+ * code table the reference switches on (src/data/gurobi_lp.py:447-461).
+ */
+#ifndef DDB200_H
+#define DDB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDB_ABI_VERSION 1
+
+/* return codes */
+#define DDB_OK            0
+#define DDB_EINVAL       -1   /* bad argument (NULL pointer, m < 1, ...)                      */
+#define DDB_ECUDA        -2   /* CUDA runtime / launch error, see ddb_last_error()            */
+#define DDB_EUNSUPPORTED -3   /* shape not supported by any kernel (see ddb_last_error())     */
+#define DDB_ENOMEM       -4
+
+/* per-instance status codes == Gurobi's (src/data/gurobi_lp.py:447-461) */
+#define DDB_ST_LOADED           1
+#define DDB_ST_OPTIMAL          2
+#define DDB_ST_INFEASIBLE       3
+#define DDB_ST_INF_OR_UNBD      4
+#define DDB_ST_UNBOUNDED        5
+#define DDB_ST_ITERATION_LIMIT  7
+#define DDB_ST_NUMERIC         12
+
+/* The reference's active-constraint threshold (src/data/gurobi_lp.py:437). */
+#define DDB_DEFAULT_THRESHOLD 1e-7
+
+typedef struct ddb_ctx ddb_ctx;
+
+int         ddb_abi_version(void);
+const char *ddb_last_error(void);
+
+/* One context per (process, device): owns the work-queue counter, kernel scratch and pinned staging buffers. */
+int ddb_create(int device, ddb_ctx **out);
+int ddb_destroy(ddb_ctx *ctx);
+/* sm_count, compute capability, opt-in shared memory per block (bytes) of the context's device. */
+int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_optin);
+
+/* Which kernel family ddb_solve_label_* will use for an (m, n) shape: 0 = register-tiled (tableau in the
+ * register file), 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau; <0 = error. */
+int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
+/* Force a kernel family for testing (-1 = automatic). */
+int ddb_set_solve_plan(ddb_ctx *ctx, int plan);
+
+/*
+ * (1) GENERATE -- replaces the serial loop RandomLPDataset._generate_problems + the generator part of
+ * create_lp_problem (src/data/randomlp_dataset.py:58-63, 76-86) in throughput mode.
+ * Instance i = first_instance + k (k in [0,B)) is a pure function of (key, i): Philox4x32-10 with
+ * key = (key_lo, key_hi), counter = (element, stream, i_lo, i_hi); Box-Muller normals.
+ *   A[k,:,:] ~ N(0,1) (row-major m x n, each entry kept with probability `density`, else 0 -- density 1.0
+ *   is the reference's distribution), x0 ~ N(0,I_n), b = A x0 + |N(0,I_m)|, c = |N(0,I_n)|.
+ * x0 may be NULL.
+ */
+int ddb_generate_dev(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                     double density, double *A, double *b, double *c, double *x0, void *stream);
+
+/*
+ * (2) SOLVE + LABEL -- replaces LinProg(A,b,c,'min',['<']*m) + optimize() + get_statuscode() +
+ * get_active_constraints() (src/data/gurobi_lp.py:11-29, 428-465) and the label assembly of
+ * create_lp_problem (src/data/randomlp_dataset.py:88-106) for a batch of B LPs
+ *     min c'x  s.t.  A x <= b,  x free.
+ * Inputs  : A[B,m,n], b[B,m], c[B,n] fp64 row-major; threshold (the reference uses 1e-7);
+ *           row_mask[B,m] (nullable): rows with mask 0 are left out of the LP that is solved (the
+ *           "reduced LP" of BASELINE.json config 4); labels / violations are still evaluated on all m rows.
+ * Outputs : status[B]; x[B,n], obj[B] (defined when status == 2); labels[B,m] = 1 where
+ *           |b - A x| <= threshold, all 0 when status != 2 (randomlp_dataset.py:96-102);
+ *           n_active[B]; pivots[B,4] = {crash, phase-1, phase-2, total} pivot counts;
+ *           ties[B] = rows whose |slack| lies in [threshold/10, threshold*10] plus rows whose label disagrees
+ *           with final-basis membership; violations[B] (nullable) = rows with slack < -threshold*10 at the
+ *           returned x (non-zero only for reduced LPs).
+ * Any output pointer except status and labels may be NULL.
+ */
+int ddb_solve_label_dev(ddb_ctx *ctx, int64_t B, int m, int n,
+                        const double *A, const double *b, const double *c,
+                        double threshold, const uint8_t *row_mask,
+                        int32_t *status, double *x, double *obj, uint8_t *labels,
+                        int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations,
+                        void *stream);
+
+/* Same contract, HOST buffers; H2D / D2H copies are done inside (chunked, pinned, double-buffered). */
+int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
+                         const double *A, const double *b, const double *c,
+                         double threshold, const uint8_t *row_mask,
+                         int32_t *status, double *x, double *obj, uint8_t *labels,
+                         int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations);
+
+/*
+ * (3) FUSED GENERATE -> SOLVE -> LABEL: same outputs as (2) for instances first_instance..+B of stream `key`
+ * without the caller materialising A, b, c (they are produced chunk by chunk into context scratch).
+ * A_out/b_out/c_out (nullable, device) receive the instances when the caller asks for them.
+ */
+int ddb_generate_solve_label_dev(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                 double density, double threshold,
+                                 int32_t *status, double *x, double *obj, uint8_t *labels,
+                                 int32_t *n_active, int32_t *pivots, int32_t *ties,
+                                 double *A_out, double *b_out, double *c_out, void *stream);
+
+/* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
+int64_t ddb_launch_count(ddb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDB200_H */

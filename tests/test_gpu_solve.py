@@ -1,0 +1,291 @@
+"""GPU parity tests of the generate -> solve -> label path: CUDA (through the C ABI) vs the CPU oracle.
+
+Bars (BASELINE.json north_star): status predicate equal on every instance; active-set labels bit-exact on
+non-degenerate instances; objective and x within 1e-9 relative; ties counted and reported, not hidden."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import randomlp as oracle
+from oracle import philox
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-9          # north_star: objectives and primal values within 1e-9 relative in fp64
+
+
+def _numpy_batch(m, n, seeds):
+    A = np.empty((len(seeds), m, n)); b = np.empty((len(seeds), m)); c = np.empty((len(seeds), n))
+    for i, s in enumerate(seeds):
+        A[i], b[i], c[i] = oracle.generate_instance(m, n, s)
+    return A, b, c
+
+
+def _dev(*arrs):
+    return [torch.from_numpy(np.ascontiguousarray(a)).cuda() for a in arrs]
+
+
+def _check_against_oracle(res, ref, A, b, c, rel_tol=REL_TOL):
+    st = np.asarray(res['status']); lab = np.asarray(res['labels'])
+    ok_ref = ref['status'] == 2
+    assert ((st == 2) == ok_ref).all(), 'status predicate differs on %s' % np.flatnonzero((st == 2) != ok_ref)[:10]
+    assert set(np.unique(st[~ok_ref])) <= {5}, 'non-optimal instances of this generator are unbounded'
+    assert (lab[~ok_ref] == 0).all()
+    mism = np.flatnonzero((lab[ok_ref] != ref['labels'][ok_ref]).any(axis=1))
+    ties = np.asarray(res['ties'])[ok_ref]
+    # label mismatches are only tolerated where the kernel itself reported a tie
+    assert all(ties[i] > 0 for i in mism), 'active-set mismatch on non-degenerate instances: %s' % mism[:10]
+    assert len(mism) == 0, 'tie instances present: %s' % mism
+    if ok_ref.any():
+        obj = np.asarray(res['obj'])[ok_ref]; x = np.asarray(res['x'])[ok_ref]
+        rel_o = np.abs(obj - ref['obj'][ok_ref]) / np.abs(ref['obj'][ok_ref])
+        rel_x = np.abs(x - ref['x'][ok_ref]).max(axis=1) / np.abs(ref['x'][ok_ref]).max(axis=1)
+        assert rel_o.max() <= rel_tol, rel_o.max()
+        assert rel_x.max() <= rel_tol, rel_x.max()
+        assert (np.asarray(res['n_active'])[ok_ref] == A.shape[2]).all()
+    return int(ok_ref.sum())
+
+
+def _to_np(res):
+    return {k: v.cpu().numpy() for k, v in res.items() if torch.is_tensor(v)}
+
+
+def test_known_answer_vectors(cuda_device, golden_dir):
+    from deep_dantzig_b200 import solver
+    with open(os.path.join(golden_dir, 'randomlp_kat.json')) as f:
+        kat = json.load(f)
+    for it in kat['instances']:
+        A, b, c = oracle.generate_instance(it['m'], it['n'], it['seed'])
+        r = _to_np(solver.solve_label(*_dev(A[None], b[None], c[None])))
+        assert (r['status'][0] == 2) == (it['status'] == 2), it
+        assert list(np.flatnonzero(r['labels'][0])) == it['active'], it
+        if it['status'] == 2:
+            assert abs(r['obj'][0] - it['objval']) <= REL_TOL * abs(it['objval'])
+        else:
+            assert r['status'][0] == 5
+
+
+def test_config1_golden_fixture(cuda_device, golden_dir):
+    """BASELINE.json configs[0]: (50,20), seed 3231 -- against the committed fixture, through the HOST-buffer ABI."""
+    from deep_dantzig_b200 import solver
+    g = np.load(os.path.join(golden_dir, 'randomlp_config1.npz'))
+    A, b, c = _numpy_batch(50, 20, list(g['seeds']))
+    r = solver.solve_label_host(A, b, c)
+    want = np.stack([np.unpackbits(p)[:50] for p in g['labels_packed']])
+    assert ((r['status'] == 2) == (g['status'] == 2)).all()
+    assert (r['labels'] == want).all()
+    ok = g['status'] == 2
+    assert (np.abs(r['obj'][ok] - g['obj'][ok]) <= REL_TOL * np.abs(g['obj'][ok])).all()
+    assert (r['ties'] == 0).all()
+
+
+@pytest.mark.parametrize('m,n,N', [(10, 5, 400), (50, 20, 400), (200, 100, 160), (30, 20, 100), (120, 100, 40),
+                                   (33, 17, 100), (64, 32, 100), (300, 100, 24)])
+def test_parity_vs_oracle(cuda_device, m, n, N):
+    from deep_dantzig_b200 import solver
+    seeds = [685 * i for i in range(N)]
+    A, b, c = _numpy_batch(m, n, seeds)
+    r = _to_np(solver.solve_label(*_dev(A, b, c)))
+    ref = oracle.solve_batch(A, b, c)
+    nopt = _check_against_oracle(r, ref, A, b, c)
+    assert (r['pivots'][:, 3] == r['pivots'][:, :3].sum(axis=1)).all()
+    assert (r['pivots'][:, 0] == n).all()
+    assert (r['violations'] == 0).all()
+    assert 0 < nopt <= N
+
+
+def test_parity_large_global_tableau(cuda_device):
+    """BASELINE.json configs[3] shape (500,250): tableau does not fit in shared memory -> L2/HBM-streamed plan."""
+    from deep_dantzig_b200 import solver, _lib
+    assert _lib.context(0).solve_plan(500, 250) == 2
+    A, b, c = _numpy_batch(500, 250, [0, 1, 2, 3, 4, 5])
+    r = _to_np(solver.solve_label(*_dev(A, b, c)))
+    ref = oracle.solve_batch(A, b, c)
+    _check_against_oracle(r, ref, A, b, c)
+
+
+def test_plans_agree_bit_for_bit(cuda_device):
+    """shared-memory and global-memory tableau kernels run the same arithmetic."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    A, b, c = _numpy_batch(60, 24, list(range(200)))
+    dA, db, dc = _dev(A, b, c)
+    try:
+        ctx.set_solve_plan(1)
+        r1 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(2)
+        r2 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    for k in ('status', 'labels', 'pivots', 'n_active'):
+        assert (r1[k] == r2[k]).all(), k
+    ok = r1['status'] == 2
+    assert (r1['x'][ok] == r2['x'][ok]).all() and (r1['obj'][ok] == r2['obj'][ok]).all()
+
+
+def test_host_and_device_flavours_agree(cuda_device):
+    from deep_dantzig_b200 import solver
+    A, b, c = _numpy_batch(50, 20, list(range(3000)))            # > one host chunk boundary is exercised below
+    rh = solver.solve_label_host(A, b, c)
+    rd = _to_np(solver.solve_label(*_dev(A, b, c)))
+    for k in ('status', 'labels', 'pivots', 'n_active', 'ties'):
+        assert (rh[k] == rd[k]).all(), k
+    ok = rh['status'] == 2
+    assert (rh['x'][ok] == rd['x'][ok]).all()
+
+
+def test_edge_cases(cuda_device):
+    from deep_dantzig_b200 import solver, _lib
+    # empty batch
+    r = solver.solve_label_host(np.zeros((0, 5, 3)), np.zeros((0, 5)), np.zeros((0, 3)))
+    assert r['status'].shape == (0,)
+    # fewer rows than columns: no vertex, generic instance is unbounded
+    A, b, c = _numpy_batch(3, 5, [0, 1])
+    r = solver.solve_label_host(A, b, c)
+    ref = oracle.solve_batch(A, b, c)
+    assert ((r['status'] == 2) == (ref['status'] == 2)).all() and (r['labels'] == 0).all()
+    # a bounded box: min -x-y s.t. x<=1, y<=1, -x-y<=1  -> x=(1,1), rows 0,1 active
+    A = np.array([[[1.0, 0], [0, 1.0], [-1, -1]]]); b = np.array([[1.0, 1, 1]]); c = np.array([[-1.0, -1]])
+    r = solver.solve_label_host(A, b, c)
+    assert r['status'][0] == 2 and list(r['labels'][0]) == [1, 1, 0]
+    assert r['x'][0] == pytest.approx([1.0, 1.0]) and r['obj'][0] == pytest.approx(-2.0)
+    # infeasible: x <= -1 and -x <= -1 (x >= 1)
+    A = np.array([[[1.0], [-1.0]]]); b = np.array([[-1.0, -1.0]]); c = np.array([[1.0]])
+    r = solver.solve_label_host(A, b, c)
+    assert r['status'][0] == 3 and (r['labels'] == 0).all()
+    # degenerate vertex (three lines through one point in 2-D): still optimal, tie reported through n_active > n
+    A = np.array([[[1.0, 0], [0, 1.0], [1.0, 1.0], [-1.0, 0], [0, -1.0]]]); b = np.array([[1.0, 1, 2, 5, 5]]); c = np.array([[-1.0, -1]])
+    r = solver.solve_label_host(A, b, c)
+    assert r['status'][0] == 2 and list(r['labels'][0]) == [1, 1, 1, 0, 0] and r['n_active'][0] == 3 and r['ties'][0] >= 1
+    # bad arguments fail loudly
+    with pytest.raises(ValueError):
+        solver.solve_label_host(np.zeros((2, 4, 2)), np.zeros((2, 3)), np.zeros((2, 2)))
+    with pytest.raises(_lib.DdbError):
+        _lib.context(0).solve_plan(10, 600)
+
+
+def test_reduced_lp_row_mask(cuda_device):
+    """Rows left out by a mask that keeps every active row do not change the optimum (config-4 reduced solve)."""
+    from deep_dantzig_b200 import solver
+    A, b, c = _numpy_batch(50, 20, list(range(64)))
+    full = solver.solve_label_host(A, b, c)
+    rng = np.random.RandomState(0)
+    mask = np.maximum(full['labels'], (rng.rand(64, 50) < 0.3).astype(np.uint8))
+    ok = full['status'] == 2
+    red = solver.solve_label_host(A[ok], b[ok], c[ok], row_mask=mask[ok])
+    assert (red['status'] == 2).all() and (red['labels'] == full['labels'][ok]).all()
+    assert (red['violations'] == 0).all()
+    assert np.abs(red['obj'] - full['obj'][ok]).max() <= 1e-9 * np.abs(full['obj'][ok]).max()
+    assert red['pivots'][:, 3].mean() < full['pivots'][ok, 3].mean()
+    # dropping an active row is detected: the reduced optimum violates it (or the reduced LP is unbounded)
+    bad = mask[ok].copy()
+    first_active = full['labels'][ok].argmax(axis=1)
+    bad[np.arange(bad.shape[0]), first_active] = 0
+    r2 = solver.solve_label_host(A[ok], b[ok], c[ok], row_mask=bad)
+    assert ((r2['status'] != 2) | (r2['violations'] > 0)).all()
+
+
+def test_philox_generator_matches_cpu_restatement(cuda_device):
+    from deep_dantzig_b200 import solver
+    for (m, n, dens) in [(50, 20, 1.0), (33, 17, 1.0), (64, 32, 0.3)]:
+        A, b, c, x0 = solver.generate(99, 5, 4, m, n, density=dens, want_x0=True)
+        A, b, c, x0 = [t.cpu().numpy() for t in (A, b, c, x0)]
+        for k in range(4):
+            Ar, br, cr, x0r = philox.generate_instance(99, 5 + k, m, n, dens)
+            assert ((A[k] == 0) == (Ar == 0)).all()
+            np.testing.assert_allclose(A[k], Ar, rtol=1e-13, atol=1e-15)   # libm log/sincos differ by a few ulp
+            np.testing.assert_allclose(x0[k], x0r, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(c[k], cr, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(b[k], br, rtol=1e-11, atol=1e-12)
+    # chunk-independence: instance i is a function of (key, i) only
+    A1, _, _ = solver.generate(7, 0, 8, 20, 10)
+    A2, _, _ = solver.generate(7, 4, 4, 20, 10)
+    assert (A1[4:] == A2).all()
+
+
+def test_fused_generate_solve_label_vs_oracle_on_downloaded_instances(cuda_device):
+    """Throughput mode: the oracle consumes the instances the device generated."""
+    from deep_dantzig_b200 import solver
+    r = solver.generate_solve_label(2024, 0, 300, 200, 100, keep_instances=True)
+    A, b, c = r['A'].cpu().numpy(), r['b'].cpu().numpy(), r['c'].cpu().numpy()
+    ref = oracle.solve_batch(A[:120], b[:120], c[:120])
+    rn = {k: v[:120] for k, v in _to_np(r).items()}
+    _check_against_oracle(rn, ref, A[:120], b[:120], c[:120])
+    # and the non-materialising call returns the same answers
+    r2 = _to_np(solver.generate_solve_label(2024, 0, 300, 200, 100))
+    assert (r2['status'] == r['status'].cpu().numpy()).all() and (r2['labels'] == r['labels'].cpu().numpy()).all()
+
+
+def test_full_size_properties(cuda_device):
+    """BASELINE.json configs[1] shape at scale, through size-independent properties (no oracle at this size)."""
+    from deep_dantzig_b200 import solver
+    B, m, n = 20000, 200, 100
+    r = solver.generate_solve_label(11, 0, B, m, n, keep_instances=True)
+    st = r['status'].cpu().numpy(); lab = r['labels']; na = r['n_active'].cpu().numpy()
+    assert set(np.unique(st)) <= {2, 5}
+    frac_unb = (st == 5).mean()
+    assert abs(frac_unb - 0.472) < 0.02, frac_unb              # Wendel: 2^-m sum_{k<n} C(m,k) at m = 2n -> ~0.472
+    ok = st == 2
+    assert (na[ok] == n).all() and (na[~ok] == 0).all()        # non-degenerate: exactly n active rows
+    assert (r['ties'].cpu().numpy() == 0).all()
+    # KKT certificate on the device data, independent of the solver: primal feasibility and objective consistency
+    okt = torch.from_numpy(ok).cuda()
+    A, b, c, x = r['A'][okt], r['b'][okt], r['c'][okt], r['x'][okt]
+    slack = b - torch.bmm(A, x.unsqueeze(2)).squeeze(2)
+    assert slack.min().item() >= -1e-7
+    assert ((slack.abs() <= 1e-7) == lab[okt].bool()).all()
+    assert torch.allclose((c * x).sum(1), r['obj'][okt], rtol=1e-12, atol=0)
+    # dual certificate: c = -A_B' y with y >= 0 on the active rows  (solve the n x n system with torch)
+    sub = torch.arange(0, int(okt.sum().item()), 97, device='cuda')[:64]
+    AB = torch.stack([A[i][lab[okt][i].bool()] for i in sub.tolist()])
+    y = torch.linalg.solve(AB.transpose(1, 2), -c[sub].unsqueeze(2)).squeeze(2)
+    assert y.min().item() >= -1e-7
+    # linearity: scaling the objective scales the optimum, labels unchanged; row permutation permutes labels
+    r2 = solver.solve_label(r['A'][:512], r['b'][:512], (r['c'][:512] * 3.0).contiguous())
+    assert (r2['labels'] == lab[:512]).all()
+    assert torch.allclose(r2['obj'][ok[:512]], 3.0 * r['obj'][:512][ok[:512]], rtol=1e-9, atol=0)
+    perm = torch.randperm(m, device='cuda')
+    r3 = solver.solve_label(r['A'][:512][:, perm].contiguous(), r['b'][:512][:, perm].contiguous(), r['c'][:512])
+    assert (r3['labels'] == lab[:512][:, perm]).all()
+
+
+def test_dropin_dataset_and_linprog(cuda_device):
+    """The reference-facing classes: same names, arguments, item layout and error behaviour."""
+    from deep_dantzig_b200.data.randomlp_dataset import RandomLPDataset
+    from deep_dantzig_b200.data.gurobi_lp import LinProg
+    ds = RandomLPDataset(10, 5, num_lps=6, seed=0)
+    ods = oracle.RandomLPDataset(10, 5, num_lps=6, seed=0)
+    assert len(ds) == 6
+    for i in range(7):
+        a, o_ = ds[i], ods[i]
+        assert (a['lp']['A'] == o_['lp']['A']).all() and (a['lp']['b'] == o_['lp']['b']).all()
+        assert a['labels'] == o_['labels']
+    for s, so in zip(ds.get_lp_params(), ods.get_lp_params()):
+        assert s['id'] == so['id'] and s['success'] == so['success'] and s['active'] == so['active']
+        assert (s['sc'] in (1, 2)) == (so['sc'] in (1, 2))
+        if s['success']:
+            assert s['objval'] == pytest.approx(so['objval'], rel=1e-9)
+    p = RandomLPDataset.create_lp_problem(10, 5, 0, with_stats=True)     # the reference's own main() case
+    assert list(p['active']) == [0, 5, 6, 8, 9] and p['stats']['objval'] == pytest.approx(-2.56554105335413, rel=1e-9)
+    A, b, c = oracle.generate_instance(10, 5, 3)
+    lp = LinProg(A, b, c, 'min', ['<'] * 10)
+    assert lp.get_statuscode() == 1
+    lp.optimize()
+    assert lp.get_statuscode() == 2 and list(lp.get_active_constraints()) == [0, 3, 4, 6, 9]
+    assert lp.model.objVal == pytest.approx(2.368364743974648, rel=1e-9) and lp.model.status == 2
+    lp = LinProg(*oracle.generate_instance(10, 5, 1))
+    lp.optimize()
+    assert lp.get_statuscode() not in (1, 2)
+    with pytest.raises(AttributeError):
+        lp.model.objVal
+    with pytest.raises(ValueError):
+        LinProg(A, b, c, 'sideways')
+    # 'max' and '>' are sign flips of the canonical form
+    lp = LinProg(-A, -b, -c, 'max', ['>'] * 10)
+    lp.optimize()
+    assert list(lp.get_active_constraints()) == [0, 3, 4, 6, 9]
+    ph = RandomLPDataset(50, 20, num_lps=32, seed=5, generator='philox')
+    assert len(ph) == 32 and ph[0]['lp']['A'].shape == (50, 20)
