@@ -58,7 +58,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t done;
+    const long long t0 = clock64();
     do {
+        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a lost TMA transaction becomes an error, not a hang
         asm volatile(
             "{\n"
             ".reg .pred p;\n"
