@@ -53,7 +53,7 @@ struct ddb_ctx {
     int device = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     int64_t smem_optin = 0;
-    unsigned long long* counters = nullptr;
+    unsigned long long* counters = nullptr;   // kCounters work-queue counters followed by kCounters flag counters
     int next_counter = 0;
     DevBuf scratch;            // global tableau slabs / register-tile scratch
     cudaEvent_t scratch_free = nullptr;
@@ -99,7 +99,7 @@ extern "C" int ddb_create(int device, ddb_ctx** out) {
     if (prop.major != 10)
         return fail(DDB_EUNSUPPORTED, "ddb_create: device is sm_%d%d; this library is built for sm_100a only",
                     prop.major, prop.minor);
-    CUDA_TRY(cudaMalloc(&ctx->counters, kCounters * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMalloc(&ctx->counters, 3 * kCounters * sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
     for (int i = 0; i < kSlots; ++i) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
@@ -194,6 +194,36 @@ static int pick_block(int m, int n) {
     return 1024;
 }
 
+static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_t st) {
+    const int m = a.m, n = a.n;
+    const bool smem_tab = (plan == 1);
+    const int block = pick_block(m, n);
+    const size_t smem = ddb::generic_smem_bytes(m, n, smem_tab);
+    // persistent grid: as many CTAs as are co-resident (bounded by shared memory and threads), never more than B
+    int per_sm = (int)((size_t)ctx->smem_optin / (smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    const int by_threads = 2048 / block;
+    if (per_sm > by_threads) per_sm = by_threads;
+    if (per_sm > 16) per_sm = 16;
+    long long grid = (long long)ctx->sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    if (!smem_tab) {
+        const size_t need = (size_t)grid * m * n * sizeof(double);
+        if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
+        if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
+        int rc = ensure(ctx->scratch, need);
+        if (rc) return rc;
+        a.gtab = (double*)ctx->scratch.p;
+    }
+    CUDA_TRY(ddb::launch_simplex_generic(a, smem_tab, (int)grid, block, st));
+    if (!smem_tab) {
+        CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
+        ctx->scratch_in_use = true;
+    }
+    ctx->launches += 1;
+    return DDB_OK;
+}
+
 extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b,
                                    const double* c, double threshold, const uint8_t* row_mask, int32_t* status,
                                    double* x, double* obj, uint8_t* labels, int32_t* n_active, int32_t* pivots,
@@ -214,9 +244,12 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
     a.pivots = pivots; a.ties = ties; a.violations = violations;
     a.max_iter = 50 * (m + n);
     a.gtab = nullptr;
-    a.counter = ctx->counters + ctx->next_counter;
+    const int slot = ctx->next_counter;
     ctx->next_counter = (ctx->next_counter + 1) % kCounters;
-    CUDA_TRY(cudaMemsetAsync(a.counter, 0, sizeof(unsigned long long), st));
+    a.counter = ctx->counters + 3 * slot;               // [0] plan-0 queue, [1] fix-up queue, [2] flag count
+    a.flag_count = reinterpret_cast<int*>(ctx->counters + 3 * slot + 2);
+    a.only_flagged = 0;
+    CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
 
     if (plan == 0) {
         const size_t need = ddb::regtile_scratch_bytes(m, n, ctx->sm_count);
@@ -233,35 +266,16 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
             ctx->scratch_in_use = true;
         }
         ctx->launches += 1;
-        return DDB_OK;
+        // fix-up pass: instances the tile could not hold / whose static crash basis was singular were flagged
+        // status = -1; the generic kernel re-solves exactly those (it returns at once when none were flagged).
+        a.only_flagged = 1;
+        a.counter = ctx->counters + 3 * slot + 1;
+        const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
+        int rc = launch_generic(ctx, a, fplan, st);
+        return rc;
     }
 
-    const bool smem_tab = (plan == 1);
-    const int block = pick_block(m, n);
-    const size_t smem = ddb::generic_smem_bytes(m, n, smem_tab);
-    // persistent grid: as many CTAs as are co-resident (bounded by shared memory and threads), never more than B
-    int per_sm = (int)((size_t)ctx->smem_optin / (smem + 1024));
-    if (per_sm < 1) per_sm = 1;
-    const int by_threads = 2048 / block;
-    if (per_sm > by_threads) per_sm = by_threads;
-    if (per_sm > 16) per_sm = 16;
-    long long grid = (long long)ctx->sm_count * per_sm;
-    if (grid > B) grid = B;
-    if (!smem_tab) {
-        const size_t need = (size_t)grid * m * n * sizeof(double);
-        if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
-        if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
-        int rc = ensure(ctx->scratch, need);
-        if (rc) return rc;
-        a.gtab = (double*)ctx->scratch.p;
-    }
-    CUDA_TRY(ddb::launch_simplex_generic(a, smem_tab, (int)grid, block, st));
-    if (!smem_tab) {
-        CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
-        ctx->scratch_in_use = true;
-    }
-    ctx->launches += 1;
-    return DDB_OK;
+    return launch_generic(ctx, a, plan, st);
 }
 
 // ---------------------------------------------------------------------------------------------------------

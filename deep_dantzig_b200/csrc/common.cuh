@@ -35,6 +35,8 @@ struct SolveArgs {
     unsigned long long* counter;   // work queue
     double* gtab;              // per-CTA global tableau slabs (plan 2) or per-CTA scratch (plan 0)
     int max_iter;
+    int only_flagged;          // generic kernel: solve only instances whose status is -1 (flagged by plan 0)
+    int* flag_count;           // number of instances plan 0 flagged for the generic kernel
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -150,11 +150,17 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
         __syncthreads();
     };
 
+    if (a.only_flagged && *a.flag_count == 0) return;   // nothing was handed over by the register-tiled kernel
+
     for (;;) {
         if (tid == 0) cur_lp = (long long)atomicAdd(a.counter, 1ull);
         __syncthreads();
         const long long lp = cur_lp;
         if (lp >= a.B) break;
+        if (a.only_flagged && a.status[lp] != -1) {
+            __syncthreads();   // everyone has read cur_lp before thread 0 overwrites it
+            continue;
+        }
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;

@@ -294,3 +294,44 @@ def test_dropin_dataset_and_linprog(cuda_device):
     assert list(lp.get_active_constraints()) == [0, 3, 4, 6, 9]
     ph = RandomLPDataset(50, 20, num_lps=32, seed=5, generator='philox')
     assert len(ph) == 32 and ph[0]['lp']['A'].shape == (50, 20)
+
+
+@pytest.mark.parametrize('m,n,N', [(10, 5, 300), (50, 20, 300), (100, 50, 100), (200, 100, 200)])
+def test_register_tiled_and_generic_kernels_agree(cuda_device, m, n, N):
+    """plan 0 (tableau in registers) and plan 1 (tableau in shared memory) implement the same algorithm."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    assert ctx.solve_plan(m, n) == 0
+    A, b, c = _numpy_batch(m, n, [17 + 3 * i for i in range(N)])
+    dA, db, dc = _dev(A, b, c)
+    try:
+        ctx.set_solve_plan(0)
+        r0 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(1)
+        r1 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    assert (r0['status'] == r1['status']).all()
+    assert (r0['labels'] == r1['labels']).all()
+    assert (r0['n_active'] == r1['n_active']).all()
+    assert (r0['pivots'][:, 0] == r1['pivots'][:, 0]).all()
+    ok = r0['status'] == 2
+    assert np.abs(r0['x'][ok] - r1['x'][ok]).max() <= 1e-9 * np.abs(r1['x'][ok]).max()
+    assert np.abs(r0['obj'][ok] - r1['obj'][ok]).max() <= 1e-9 * np.abs(r1['obj'][ok]).max()
+
+
+def test_singular_crash_basis_is_handed_to_the_generic_kernel(cuda_device):
+    """A duplicated top-ranked row makes the static crash basis singular: plan 0 flags the instance and the
+    generic kernel re-solves it on the device; results still match the oracle."""
+    from deep_dantzig_b200 import solver
+    A, b, c = _numpy_batch(50, 20, list(range(40)))
+    for i in range(0, 40, 2):
+        score = (A[i] @ c[i]) / np.linalg.norm(A[i], axis=1)
+        r0, r1 = np.argsort(score)[:2]
+        A[i, r1] = A[i, r0]; b[i, r1] = b[i, r0] + 0.5          # parallel, never-active copy inside the crash basis
+    r = solver.solve_label_host(A, b, c)
+    ref = oracle.solve_batch(A, b, c)
+    assert ((r['status'] == 2) == (ref['status'] == 2)).all()
+    ok = ref['status'] == 2
+    assert (r['labels'][ok] == ref['labels'][ok]).all()
+    assert np.abs(r['obj'][ok] - ref['obj'][ok]).max() <= 1e-9 * np.abs(ref['obj'][ok]).max()
