@@ -25,6 +25,7 @@
 // Instances the tile cannot hold or whose static crash basis is singular are flagged status = -1 and re-solved by
 // the generic kernel on the device (capi.cu); nothing ever falls back to the CPU.
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -47,6 +48,32 @@ __device__ __forceinline__ int warp_argmin_key(unsigned long long key, unsigned 
     return __ffs(ball) - 1;
 }
 constexpr unsigned long long KEY_INF = 0xfff0000000000000ull;   // dkey(+inf)
+
+// Warp-uniform dynamic index -> compile-time index (jump table instead of chains of predicated moves).
+template <int N, class F>
+__device__ __forceinline__ void static_switch(int i, F&& f) {
+    switch (i) {
+#define DDB_CASE(I) \
+    case I:         \
+        if constexpr (I < N) f(std::integral_constant<int, I>{}); \
+        break;
+        DDB_CASE(0) DDB_CASE(1) DDB_CASE(2) DDB_CASE(3) DDB_CASE(4) DDB_CASE(5) DDB_CASE(6) DDB_CASE(7)
+        DDB_CASE(8) DDB_CASE(9) DDB_CASE(10) DDB_CASE(11) DDB_CASE(12) DDB_CASE(13) DDB_CASE(14) DDB_CASE(15)
+#undef DDB_CASE
+        default: break;
+    }
+}
+
+// 1/p to ~1 ulp: 20-bit hardware seed + two Newton steps (5 instructions instead of the ~35 of an IEEE division).
+__device__ __forceinline__ double fast_rcp(double p) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(p));
+    double e = fma(-p, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-p, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
 
 struct PubHdr {          // one per (buffer, warp): the speculative candidate
     unsigned long long key;   // dkey(s_min) in phase 1, dkey(ratio) in phase 2, KEY_INF = no candidate
@@ -91,7 +118,7 @@ template <int NW, int RS, int CS, int MINB>
 __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArgs a) {
     using Cfg = RegCfg<NW, RS, CS>;
     constexpr int RT = Cfg::RT, CT = Cfg::CT;
-    static_assert(RS <= 32, "row slots are mapped onto lanes");
+    static_assert(RS <= 16 && CS <= 16, "static_switch covers 16 cases");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = a.m, n = a.n;
     const RegLayout L = make_reg_layout(m, n, NW, CT);
@@ -108,7 +135,6 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
     double* gbuf = reinterpret_cast<double*>(smem_raw + L.gbuf);
     int* red = reinterpret_cast<int*>(smem_raw + L.red);
     __shared__ long long cur_lp;
-    __shared__ int sh_flag;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -127,58 +153,69 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
 #pragma unroll
     for (int cs = 0; cs < CS; ++cs) col_struct[cs] = (lane + 32 * cs) < n;
 
-    // dynamic-slot helpers (warp-uniform switches keep register indices static)
-    auto get_row = [&](int slot, double (&out)[CS]) {
+    // dynamic-slot helpers: warp-uniform jump tables keep every register index static
+    const bool has_g = (warp == NW - 1);         // this warp owns the cost row (slot RS-1)
+    // publish row `slot` scaled by rp into dst[0..CT) with the pivot entry replaced by rp; returns its raw rhs
+    auto publish_row = [&](int slot, double rp, int k, double* dst) -> double {
+        double sraw = 0.0;
+        static_switch<RS>(slot, [&](auto Rc) {
+            constexpr int R = decltype(Rc)::value;
 #pragma unroll
-        for (int rs = 0; rs < RS; ++rs)
-            if (rs == slot) {
-#pragma unroll
-                for (int cs = 0; cs < CS; ++cs) out[cs] = T[rs][cs];
-            }
+            for (int cs = 0; cs < CS; ++cs) dst[lane + 32 * cs] = T[R][cs] * rp;
+            sraw = sv[R];
+        });
+        if (lane == (k & 31)) dst[k] = rp;       // same thread wrote dst[k] above: program order makes this one win
+        return sraw;
     };
     auto set_row = [&](int slot, const double (&in)[CS], double s_new) {
+        static_switch<RS>(slot, [&](auto Rc) {
+            constexpr int R = decltype(Rc)::value;
 #pragma unroll
-        for (int rs = 0; rs < RS; ++rs)
-            if (rs == slot) {
-#pragma unroll
-                for (int cs = 0; cs < CS; ++cs) T[rs][cs] = in[cs];
-                sv[rs] = s_new;
-            }
+            for (int cs = 0; cs < CS; ++cs) T[R][cs] = in[cs];
+            sv[R] = s_new;
+        });
     };
-    auto sel_d = [&](const double (&v)[CS], int q) {
-        double r = v[0];
+    // rank-1 update of this warp's live rows (slots < nslots, plus the cost row) from the published pivot row.
+    // The pivot row itself is updated too (garbage) and restored by set_row afterwards.
+    auto update_crash = [&](int kq, int kl, const double (&pr)[CS], int nslots) {
+        const bool is_kl = (lane == kl);
+        static_switch<CS>(kq, [&](auto Kc) {
+            constexpr int KQ = decltype(Kc)::value;
 #pragma unroll
-        for (int cs = 1; cs < CS; ++cs)
-            if (q == cs) r = v[cs];
-        return r;
-    };
-    auto sel_i = [&](const int (&v)[CS], int q) {
-        int r = v[0];
+            for (int rs = 0; rs < RS; ++rs) {
+                if (rs < nslots || (rs == RS - 1 && has_g)) {
+                    const double f = __shfl_sync(FULL, T[rs][KQ], kl);
+                    if (is_kl) T[rs][KQ] = 0.0;
 #pragma unroll
-        for (int cs = 1; cs < CS; ++cs)
-            if (q == cs) r = v[cs];
-        return r;
-    };
-    // rank-1 update of every live row of this warp from the published pivot row `pr` (entering column (kq,kl)).
-    // `skip` = slot of the pivot row if it is mine (else -1); nlive = rows below it are live; the cost row always is.
-    auto pivot_update = [&](int kq, int kl, const double (&pr)[CS], double srow, int skip, int nlive, bool with_sv) {
-#pragma unroll
-        for (int KQ = 0; KQ < CS; ++KQ) {
-            if (kq == KQ) {
-#pragma unroll
-                for (int rs = 0; rs < RS; ++rs) {
-                    const int ti = rs * NW + warp;
-                    if (ti < nlive || ti == RT - 1) {
-                        double f = __shfl_sync(FULL, T[rs][KQ], kl);
-                        if (rs == skip) f = 0.0;
-                        if (lane == kl) T[rs][KQ] = 0.0;
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs) T[rs][cs] = fma(-f, pr[cs], T[rs][cs]);
-                        if (with_sv) sv[rs] = fma(-f, srow, sv[rs]);
-                    }
+                    for (int cs = 0; cs < CS; ++cs) T[rs][cs] = fma(-f, pr[cs], T[rs][cs]);
                 }
             }
-        }
+        });
+    };
+    // same, plus the replicated right-hand sides, the replicated pricing vector and the column bookkeeping;
+    // returns the constraint that was nonbasic in column k (it becomes basic in the pivot row)
+    auto update_simplex = [&](int kq, int kl, const double (&pr)[CS], double srow, int nslots, int var_r) -> int {
+        const bool is_kl = (lane == kl);
+        int cv = -1;
+        static_switch<CS>(kq, [&](auto Kc) {
+            constexpr int KQ = decltype(Kc)::value;
+#pragma unroll
+            for (int rs = 0; rs < RS; ++rs) {
+                if (rs < nslots || (rs == RS - 1 && has_g)) {
+                    const double f = __shfl_sync(FULL, T[rs][KQ], kl);
+                    if (is_kl) T[rs][KQ] = 0.0;
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) T[rs][cs] = fma(-f, pr[cs], T[rs][cs]);
+                    sv[rs] = fma(-f, srow, sv[rs]);
+                }
+            }
+            const double vk = __shfl_sync(FULL, vec[KQ], kl);
+            cv = __shfl_sync(FULL, colvar[KQ], kl);
+            if (is_kl) { vec[KQ] = 0.0; colvar[KQ] = var_r; }
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) vec[cs] = fma(-vk, pr[cs], vec[cs]);
+        });
+        return cv;
     };
 
     for (;;) {
@@ -206,10 +243,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                 gbuf[i] = excl ? kInf : (nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5);
             }
         }
-        if (tid == 0) {
-            sh_flag = 0;
-            Dsm[ZERO_OFF] = 0.0;
-        }
+        if (tid == 0) Dsm[ZERO_OFF] = 0.0;
         __syncthreads();
         int m_eff = 0;
         for (int i = tid; i < m; i += NW * 32) {
@@ -258,50 +292,52 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) T[rs][cs] = 0.0;
                 }
+                sv[rs] = 0.0;
             }
             unsigned freemask = 0;   // bit cs set: column (lane + 32 cs) is still a free x_j
 #pragma unroll
             for (int cs = 0; cs < CS; ++cs)
                 if (col_struct[cs]) freemask |= 1u << cs;
+            const int nslots_c = (n > warp) ? (n - warp + NW - 1) / NW : 0;
 
             for (int t = 0; t < n; ++t) {
                 const int wo = t % NW, so = t / NW;
                 if (warp == wo) {
-                    double row[CS];
-                    get_row(so, row);
-                    // largest |entry| among free columns
+                    // largest |entry| of my pivot row among free columns
                     unsigned long long best = 0ull;
                     int bq = 0;
+                    static_switch<RS>(so, [&](auto Rc) {
+                        constexpr int R = decltype(Rc)::value;
 #pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) {
-                        const unsigned long long kk = (freemask >> cs & 1u) ? (unsigned long long)__double_as_longlong(fabs(row[cs])) : 0ull;
-                        if (kk > best) { best = kk; bq = cs; }
-                    }
+                        for (int cs = 0; cs < CS; ++cs) {
+                            const unsigned long long kk =
+                                (freemask >> cs & 1u) ? (unsigned long long)__double_as_longlong(fabs(T[R][cs])) : 0ull;
+                            if (kk > best) { best = kk; bq = cs; }
+                        }
+                    });
                     unsigned long long kmin;
-                    const int kl = warp_argmin_key(~best, kmin);   // argmax via complemented key
+                    const int kl = warp_argmin_key(~best, kmin);   // argmax through the complemented key
                     const int kq = __shfl_sync(FULL, bq, kl);
-                    const double p = __shfl_sync(FULL, sel_d(row, kq), kl);
-                    const int k = kl + 32 * kq;
-                    const bool bad = !(fabs(p) >= kTolCrash);
-                    const double rp = 1.0 / p;
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) row[cs] *= rp;
-                    if (lane == kl) {
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs)
-                            if (cs == kq) row[cs] = rp;
-                    }
+                    const double p = __longlong_as_double((long long)~kmin);   // |pivot|; the sign is folded in below
+                    const bool bad = !(p >= kTolCrash);
                     double* pr = pub_row + (size_t)(buf * NW) * CT;
+                    // sign of the pivot: read it back from the owning lane
+                    double pv = 0.0;
+                    static_switch<RS>(so, [&](auto Rc) {
+                        constexpr int R = decltype(Rc)::value;
+                        double mine = T[R][0];
 #pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) pr[lane + 32 * cs] = row[cs];
-                    const double srow = __shfl_sync(FULL, row[CS - 1], 31);
-                    set_row(so, row, srow);
+                        for (int cs = 1; cs < CS; ++cs)
+                            if (kq == cs) mine = T[R][cs];
+                        pv = __shfl_sync(FULL, mine, kl);
+                    });
+                    const double rp = fast_rcp(pv);
+                    publish_row(so, rp, kl + 32 * kq, pr);
                     if (lane == 0) {
                         PubHdr* h = pub_hdr + buf * NW;
-                        h->k = k;
+                        h->k = kl + 32 * kq;
                         h->flag = bad ? 2 : 0;
-                        h->srow = srow;
-                        pivcol[t] = k;
+                        pivcol[t] = kl + 32 * kq;
                     }
                 }
                 __syncthreads();
@@ -314,10 +350,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) pr[cs] = prs[lane + 32 * cs];
                 if (lane == kl) freemask &= ~(1u << kq);
-                pivot_update(kq, kl, pr, 0.0, (warp == wo) ? so : -1, n, false);
-                if (warp == wo) {   // the update zeroed the pivot entry of the pivot row: restore the normalised row
-                    set_row(so, pr, 0.0);
-                }
+                update_crash(kq, kl, pr, nslots_c);
+                if (warp == wo) set_row(so, pr, 0.0);   // restore the normalised pivot row
                 buf ^= 1;
                 ++npiv_crash;
             }
@@ -349,47 +383,50 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
             }
 
             // ---- stage 2: P_N = -A_N D, s_N = b_N - A_N xv ---------------------------------------------------
-            int doff[CS], dstr[CS];
+            {
+                int doff[CS], dstr[CS];
 #pragma unroll
-            for (int cs = 0; cs < CS; ++cs) {
-                const int j = lane + 32 * cs;
-                const bool rhs = (cs == CS - 1) && (lane == 31);
-                const bool valid = (j < n) || rhs;
-                doff[cs] = valid ? (rhs ? n : j) : ZERO_OFF;
-                dstr[cs] = valid ? PD : 0;
-            }
-            int arow[RS];
-#pragma unroll
-            for (int rs = 0; rs < RS; ++rs) {
-                const int u = rs * NW + warp;
-                arow[rs] = (u < nN) ? order[n + u] * n : -1;
-                if (u < nN) {
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) T[rs][cs] = 0.0;
-                    if (lane == 31) T[rs][CS - 1] = __ldg(bg + order[n + u]);
-                    if (lane == rs) rowvar_l = order[n + u];
-                } else if (u != RT - 1) {
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) T[rs][cs] = 0.0;
-                    if (lane == rs) rowvar_l = -1;
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    const bool rhs = (cs == CS - 1) && (lane == 31);
+                    const bool valid = (j < n) || rhs;
+                    doff[cs] = valid ? (rhs ? n : j) : ZERO_OFF;
+                    dstr[cs] = valid ? PD : 0;
                 }
-            }
-#pragma unroll 2
-            for (int k = 0; k < n; ++k) {
-                double d[CS];
-#pragma unroll
-                for (int cs = 0; cs < CS; ++cs) d[cs] = Dsm[doff[cs] + k * dstr[cs]];
+                int arow[RS];
 #pragma unroll
                 for (int rs = 0; rs < RS; ++rs) {
-                    if (arow[rs] >= 0) {
-                        const double av = __ldg(Ag + arow[rs] + k);
+                    const int u = rs * NW + warp;
+                    arow[rs] = (u < nN) ? order[n + u] * n : -1;
+                    if (u < nN) {
 #pragma unroll
-                        for (int cs = 0; cs < CS; ++cs) T[rs][cs] = fma(-av, d[cs], T[rs][cs]);
+                        for (int cs = 0; cs < CS; ++cs) T[rs][cs] = 0.0;
+                        if (lane == 31) T[rs][CS - 1] = __ldg(bg + order[n + u]);
+                        if (lane == rs) rowvar_l = order[n + u];
+                    } else if (u != RT - 1) {
+#pragma unroll
+                        for (int cs = 0; cs < CS; ++cs) T[rs][cs] = 0.0;
+                        if (lane == rs) rowvar_l = -1;
+                    }
+                }
+#pragma unroll 2
+                for (int k = 0; k < n; ++k) {
+                    double d[CS];
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) d[cs] = Dsm[doff[cs] + k * dstr[cs]];
+#pragma unroll
+                    for (int rs = 0; rs < RS; ++rs) {
+                        if (arow[rs] >= 0) {
+                            const double av = __ldg(Ag + arow[rs] + k);
+#pragma unroll
+                            for (int cs = 0; cs < CS; ++cs) T[rs][cs] = fma(-av, d[cs], T[rs][cs]);
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int rs = 0; rs < RS; ++rs) sv[rs] = __shfl_sync(FULL, T[rs][CS - 1], 31);
+            const int nslots = (nN > warp) ? (nN - warp + NW - 1) / NW : 0;
 
             // ---- stage 3a: phase 1 ----------------------------------------------------------------------------
             for (;;) {
@@ -397,42 +434,32 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                 double smin = kInf;
                 int slot = -1;
 #pragma unroll
-                for (int rs = 0; rs < RS; ++rs) {
-                    const int u = rs * NW + warp;
-                    if (u < nN && sv[rs] < smin) { smin = sv[rs]; slot = rs; }
-                }
+                for (int rs = 0; rs < RS; ++rs)
+                    if (rs < nslots && sv[rs] < smin) { smin = sv[rs]; slot = rs; }
                 PubHdr* myh = pub_hdr + buf * NW + warp;
                 if (slot >= 0 && smin < -kTolFeas) {
-                    double row[CS];
-                    get_row(slot, row);
                     // ratio test along the row: min ghat_j / (-e_j) over e_j < -tol
                     double bn = 0.0, bd = 0.0;   // best numerator / denominator (bd == 0: none)
                     int bq = 0;
+                    static_switch<RS>(slot, [&](auto Rc) {
+                        constexpr int R = decltype(Rc)::value;
 #pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) {
-                        const double e = -row[cs];
-                        if (colvar[cs] >= 0 && e > kTolPivot) {
-                            const double num = fmax(vec[cs], 0.0);
-                            if (bd == 0.0 || num * bd < bn * e) { bn = num; bd = e; bq = cs; }
+                        for (int cs = 0; cs < CS; ++cs) {
+                            const double e = -T[R][cs];
+                            if (colvar[cs] >= 0 && e > kTolPivot) {
+                                const double num = fmax(vec[cs], 0.0);
+                                if (bd == 0.0 || num * bd < bn * e) { bn = num; bd = e; bq = cs; }
+                            }
                         }
-                    }
-                    const double ratio = (bd > 0.0) ? bn / bd : kInf;
+                    });
+                    const double ratio = bn * fast_rcp(bd > 0.0 ? bd : 1.0);
                     unsigned long long kmin;
                     const int kl = warp_argmin_key((bd > 0.0) ? dkey(ratio) : KEY_INF, kmin);
                     const bool none = (kmin == KEY_INF);
                     const int kq = __shfl_sync(FULL, bq, kl);
-                    const double p = __shfl_sync(FULL, sel_d(row, kq), kl);
-                    const double rp = 1.0 / p;
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) row[cs] *= rp;
-                    if (lane == kl) {
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs)
-                            if (cs == kq) row[cs] = rp;
-                    }
-                    double* pr = pub_row + (size_t)(buf * NW + warp) * CT;
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) pr[lane + 32 * cs] = row[cs];
+                    const double p = -__shfl_sync(FULL, bd, kl);       // the pivot entry itself
+                    const double rp = fast_rcp(p);
+                    publish_row(slot, rp, kl + 32 * kq, pub_row + (size_t)(buf * NW + warp) * CT);
                     const int var = __shfl_sync(FULL, rowvar_l, slot);
                     if (lane == 0) {
                         myh->key = dkey(smin);
@@ -460,21 +487,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                 const double* prs = pub_row + (size_t)(buf * NW + ww) * CT;
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) pr[cs] = prs[lane + 32 * cs];
-                const int myslot = (warp == ww) ? (tr / NW) : -1;
-                pivot_update(kq, kl, pr, srow, myslot, nN, true);
-                if (warp == ww) set_row(myslot, pr, srow);
-                // ghat and the column/row bookkeeping (replicated in every warp)
-                {
-                    const double vk = __shfl_sync(FULL, sel_d(vec, kq), kl);
-                    const int cv = __shfl_sync(FULL, sel_i(colvar, kq), kl);
-                    if (lane == kl) {
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs)
-                            if (cs == kq) { vec[cs] = 0.0; colvar[cs] = var_r; }
-                    }
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) vec[cs] = fma(-vk, pr[cs], vec[cs]);
-                    if (warp == ww && lane == myslot) rowvar_l = cv;
+                const int cv = update_simplex(kq, kl, pr, srow, nslots, var_r);
+                if (warp == ww) {
+                    const int myslot = tr / NW;
+                    set_row(myslot, pr, srow);
+                    if (lane == myslot) rowvar_l = cv;
                 }
                 buf ^= 1;
                 ++npiv_p1;
@@ -504,49 +521,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                 const int kl = warp_argmin_key(dkey(gmin), kmin);
                 if (kmin >= dkey(-kTolFeas)) break;                // optimal
                 const int kq = __shfl_sync(FULL, bq, kl);
-                // ratio test over my rows, evaluated in the lane that owns column k
-                double bs = 0.0, be = 0.0;
+                // ratio test over my rows, evaluated in the lane that owns column k (cross-multiplied, no division)
+                double bs = 1.0, be = 0.0;                         // best ratio bs/be; be == 0: none yet (ratio +inf)
                 int slot = -1;
+                static_switch<CS>(kq, [&](auto Kc) {
+                    constexpr int KQ = decltype(Kc)::value;
 #pragma unroll
-                for (int KQ = 0; KQ < CS; ++KQ) {
-                    if (kq == KQ) {
-#pragma unroll
-                        for (int rs = 0; rs < RS; ++rs) {
-                            const int u = rs * NW + warp;
-                            const double e = T[rs][KQ];
-                            if (u < nN && e > kTolPivot) {
-                                const double s = fmax(sv[rs], 0.0);
-                                if (slot < 0 || s * be < bs * e) { bs = s; be = e; slot = rs; }
-                            }
-                        }
+                    for (int rs = 0; rs < RS; ++rs) {
+                        const double e = T[rs][KQ];
+                        const double sc = fmax(sv[rs], 0.0);
+                        if (rs < nslots && e > kTolPivot && sc * be < bs * e) { bs = sc; be = e; slot = rs; }
                     }
-                }
+                });
                 slot = __shfl_sync(FULL, slot, kl);
                 PubHdr* myh = pub_hdr + buf * NW + warp;
                 if (slot >= 0) {
                     bs = __shfl_sync(FULL, bs, kl);
                     be = __shfl_sync(FULL, be, kl);
-                    const double rp = 1.0 / be;
-                    const double ratio = bs * rp;
-                    double row[CS];
-                    get_row(slot, row);
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) row[cs] *= rp;
-                    if (lane == kl) {
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs)
-                            if (cs == kq) row[cs] = rp;
-                    }
-                    double* pr = pub_row + (size_t)(buf * NW + warp) * CT;
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) pr[lane + 32 * cs] = row[cs];
+                    const double rp = fast_rcp(be);
+                    const double sraw = publish_row(slot, rp, kl + 32 * kq, pub_row + (size_t)(buf * NW + warp) * CT);
                     const int var = __shfl_sync(FULL, rowvar_l, slot);
-                    double sraw = 0.0;
-#pragma unroll
-                    for (int rs = 0; rs < RS; ++rs)
-                        if (rs == slot) sraw = sv[rs];
                     if (lane == 0) {
-                        myh->key = dkey(ratio);
+                        myh->key = dkey(bs * rp);
                         myh->srow = sraw * rp;
                         myh->var = var;
                         myh->k = kl + 32 * kq;
@@ -568,20 +564,11 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                 const double* prs = pub_row + (size_t)(buf * NW + ww) * CT;
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) pr[cs] = prs[lane + 32 * cs];
-                const int myslot = (warp == ww) ? (tr / NW) : -1;
-                pivot_update(kq, kl, pr, srow, myslot, nN, true);
-                if (warp == ww) set_row(myslot, pr, srow);
-                {
-                    const double vk = __shfl_sync(FULL, sel_d(vec, kq), kl);
-                    const int cv = __shfl_sync(FULL, sel_i(colvar, kq), kl);
-                    if (lane == kl) {
-#pragma unroll
-                        for (int cs = 0; cs < CS; ++cs)
-                            if (cs == kq) { vec[cs] = 0.0; colvar[cs] = var_r; }
-                    }
-#pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) vec[cs] = fma(-vk, pr[cs], vec[cs]);
-                    if (warp == ww && lane == myslot) rowvar_l = cv;
+                const int cv = update_simplex(kq, kl, pr, srow, nslots, var_r);
+                if (warp == ww) {
+                    const int myslot = tr / NW;
+                    set_row(myslot, pr, srow);
+                    if (lane == myslot) rowvar_l = cv;
                 }
                 buf ^= 1;
                 ++npiv_p2;
