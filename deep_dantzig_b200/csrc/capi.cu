@@ -15,6 +15,20 @@ cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, i
 bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
+struct S2vArgs {
+    int graph;
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;
+    float* logp;
+    float* probs;
+    int* error_flag;
+    int store_A;
+};
+cudaError_t launch_s2v_forward(const S2vArgs& a, int sm_count, long long smem_optin, cudaStream_t st, const char** why);
 }  // namespace ddb
 
 static thread_local char g_err[512] = "";
@@ -378,5 +392,43 @@ extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t 
                                  stream);
         if (rc) return rc;
     }
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// classifier forward
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ddb_s2v_param_count(int graph, int p) {
+    if (p < 1) return DDB_EINVAL;
+    if (graph == 0) return 2 * p + 6 * p * p + 3 * p + 3 * p * p + 2 * 2 * p;
+    if (graph == 1) return p + 4 * p + p + 4 * p * p + 2 * p + 3 * p * p + 2 * (2 * p + 4);
+    return DDB_EINVAL;
+}
+
+extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
+                                   const double* b, const double* c, const float* params, float* logp, float* probs,
+                                   void* stream) {
+    if (!ctx || !A || !b || !c || !params || !logp) return fail(DDB_EINVAL, "ddb_s2v_forward_dev: NULL argument");
+    if (graph != 0 && graph != 1) return fail(DDB_EINVAL, "ddb_s2v_forward_dev: Graph not recognised (%d)", graph);
+    if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
+        return fail(DDB_EINVAL, "ddb_s2v_forward_dev: B=%lld m=%d n=%d p=%d T=%d", (long long)B, m, n, p, T);
+    if (B == 0) return DDB_OK;
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int slot = ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
+    int* err = reinterpret_cast<int*>(ctx->counters + 3 * slot);
+    CUDA_TRY(cudaMemsetAsync(err, 0, sizeof(int), st));
+    ddb::S2vArgs a;
+    a.graph = graph; a.B = B; a.m = m; a.n = n; a.p = p; a.T = T;
+    a.A = A; a.b = b; a.c = c; a.params = params; a.logp = logp; a.probs = probs;
+    a.error_flag = err; a.store_A = 0;
+    const char* why = "";
+    cudaError_t e = ddb::launch_s2v_forward(a, ctx->sm_count, ctx->smem_optin, st, &why);
+    if (e != cudaSuccess) {
+        if (why[0]) return fail(DDB_EUNSUPPORTED, "%s (m=%d n=%d p=%d)", why, m, n, p);
+        return fail(DDB_ECUDA, "s2v forward launch: %s", cudaGetErrorString(e));
+    }
+    ctx->launches += 1;
     return DDB_OK;
 }

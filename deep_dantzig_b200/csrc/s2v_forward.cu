@@ -1,0 +1,605 @@
+// Batched forward pass of the reference classifier (structure2vec), one CTA per LP instance, fp32.
+//
+// Replaces Model.forward for a whole batch (reference src/ml/models/s2v.py:45-54): _forward_bipartite + _s2v_bipartite
+// (:253-323, 218-251) and _forward_complete + _s2v_complete (:124-187, 91-122), plus the per-instance Python batch
+// loop of ml/utils.py:3-25.  Inputs are the fp64 (A, b, c) the solver path produces; in_loss is every row (A1).
+//
+// What makes it cheap (SURVEY.md section 7 "classifier is thin"):
+//   * the bmm -> relu -> sum terms (s2v.py:112, 236, 239) are linear in relu(+t4), relu(-t4):
+//         sum_j relu(t4_k w_j) = relu(t4_k) sum_j relu(w_j) + relu(-t4_k) sum_j relu(-w_j),
+//     so only two row sums / column sums of the normalised matrix are needed, and t3 . relu(+-t4) are p-vectors
+//     computed once per launch;
+//   * bipartite, dense instance: adj is all ones, so mu . normalize(adj) is a broadcast mean -> a round costs
+//     O(p^2 + p (m+n)); the whole forward is one pass over A (HBM-bound);
+//   * complete: only row sums of relu(+-W), W = G G^T, are needed, never W itself: the Gram product is fused with
+//     its relu-row-sum epilogue and W is never stored.
+// Quirks B9 (term2 laid out variables-first) and B10 (scalar t4rc . relu_rc added to every row) are reproduced.
+#include "common.cuh"
+
+namespace ddb {
+
+struct S2vArgs {
+    int graph;                 // 0 complete, 1 bipartite
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;       // flat, reference state_dict order (oracle/classifier.py: *_PARAMS)
+    float* logp;               // [B, m, 2]
+    float* probs;              // [B, m, 2] (nullable)
+    int* error_flag;           // set to 1 if a sparse instance did not fit the shared-memory plan
+    int store_A;               // bipartite: normalised A kept in shared memory (general adjacency supported)
+};
+
+__host__ __device__ inline int pad4(int v) { return (v + 3) & ~3; }
+
+// out[k][q] = sum_l Wt[l][k] * X[l][q] for nodes q in [0, nq); Wt is the transposed weight (pitch PP, multiple of 4),
+// X has pitch px, out has pitch po.  One thread per node, 4 outputs per inner loop (1 LDS.32 + 1 LDS.128 per 4 FMA).
+__device__ __forceinline__ void node_matvec(const float* __restrict__ Wt, int PP, int p, const float* X, int px,
+                                            float* out, int po, int nq, int tid, int nt) {
+    for (int q = tid; q < nq; q += nt) {
+        for (int kb = 0; kb < PP; kb += 4) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int l = 0; l < p; ++l) {
+                const float x = X[l * px + q];
+                const float4 w = *reinterpret_cast<const float4*>(Wt + l * PP + kb);
+                a0 = fmaf(w.x, x, a0);
+                a1 = fmaf(w.y, x, a1);
+                a2 = fmaf(w.z, x, a2);
+                a3 = fmaf(w.w, x, a3);
+            }
+            if (kb + 0 < p) out[(kb + 0) * po + q] = a0;
+            if (kb + 1 < p) out[(kb + 1) * po + q] = a1;
+            if (kb + 2 < p) out[(kb + 2) * po + q] = a2;
+            if (kb + 3 < p) out[(kb + 3) * po + q] = a3;
+        }
+    }
+}
+
+// y[k] = sum_l W[k][l] x[l] (row-major W in global memory), one warp per output.
+__device__ __forceinline__ void small_matvec(const float* __restrict__ W, int p, const float* x, float* y, int warp,
+                                             int lane, int nw) {
+    for (int k = warp; k < p; k += nw) {
+        float acc = 0.f;
+        for (int l = lane; l < p; l += 32) acc = fmaf(__ldg(W + k * p + l), x[l], acc);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+        if (lane == 0) y[k] = acc;
+    }
+}
+
+__device__ __forceinline__ float warp_sumf(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// stage a p x p row-major matrix from global memory into shared memory transposed: Wt[l][k] = W[k][l]
+__device__ __forceinline__ void stage_transposed(const float* __restrict__ W, int p, int PP, float* Wt, int tid, int nt) {
+    for (int e = tid; e < p * PP; e += nt) {
+        const int l = e / PP, k = e - l * PP;
+        Wt[e] = (k < p) ? __ldg(W + k * p + l) : 0.f;
+    }
+}
+
+// =====================================================================================================================
+// bipartite
+// =====================================================================================================================
+struct BipLayout {
+    size_t t2c, t2v, t7, mu, agg, An, vecs, total;   // offsets in floats
+};
+__host__ __device__ inline BipLayout bip_layout(int m, int n, int p, bool store_A) {
+    const int PP = pad4(p);
+    BipLayout L;
+    size_t off = 0;
+    L.t2c = off; off += (size_t)p * PP;
+    L.t2v = off; off += (size_t)p * PP;
+    L.t7 = off;  off += (size_t)p * PP;
+    L.mu = off;  off += (size_t)p * (m + n);
+    L.agg = off; off += store_A ? (size_t)p * (m + n) : 0;
+    L.An = off;  off += store_A ? (size_t)m * n : 0;
+    L.vecs = off;
+    off += (size_t)6 * m + 5 * n + 16 * PP + 64;     // row/col statistics + small p-vectors
+    L.total = off;
+    return L;
+}
+size_t s2v_bipartite_smem_bytes(int m, int n, int p, bool store_A) { return bip_layout(m, n, p, store_A).total * 4; }
+
+__global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int m = a.m, n = a.n, p = a.p, PP = pad4(p), NP = m + n;
+    const BipLayout L = bip_layout(m, n, p, a.store_A != 0);
+    float* t2cT = sm + L.t2c;
+    float* t2vT = sm + L.t2v;
+    float* t7T = sm + L.t7;
+    float* mu = sm + L.mu;
+    float* agg = sm + L.agg;
+    float* An = sm + L.An;
+    float* v = sm + L.vecs;
+    float* rb = v;            v += m;    // b_i / norm_i            (c_feats[:,1] after s2v.py:293)
+    float* cosv = v;          v += m;    // <a_i', c>               (c_feats[:,3], s2v.py:297)
+    float* Sp = v;            v += m;    // sum_j relu(a'_ij)
+    float* Sn = v;            v += m;    // sum_j relu(-a'_ij)
+    float* rcnt = v;          v += m;    // nonzeros in row i
+    float* z7 = v;            v += m;    // scratch
+    float* cj = v;            v += n;    // objective coefficients (v_feats)
+    float* Cp = v;            v += n;    // sum_i relu(a'_ij)
+    float* Cn = v;            v += n;    // sum_i relu(-a'_ij)
+    float* ccnt = v;          v += n;    // nonzeros in column j
+    float* ctmp = v;          v += n;
+    float* w3cp = v;          v += PP;   // t3c . relu(t4c)
+    float* w3cn = v;          v += PP;   // t3c . relu(-t4c)
+    float* w3vp = v;          v += PP;
+    float* w3vn = v;          v += PP;
+    float* meanc = v;         v += PP;
+    float* meanv = v;         v += PP;
+    float* yv = v;            v += PP;   // t2c . mean_c   (goes to node positions < n : quirk B9)
+    float* yc = v;            v += PP;   // t2v . mean_v   (goes to node positions >= n)
+    float* u6 = v;            v += PP;
+    float* tmp1 = v;          v += PP;
+    float* tmp2 = v;          v += PP;
+    float* r4 = v;            v += 4 * PP;
+    int* iflag = reinterpret_cast<int*>(v);
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    // parameter block offsets (reference state_dict order)
+    const float* P = a.params;
+    const float* t0 = P;                 P += p;
+    const float* t1c = P;                P += 4 * p;
+    const float* t1v = P;                P += p;
+    const float* t2c = P;                P += p * p;
+    const float* t2v = P;                P += p * p;
+    const float* t3c = P;                P += p * p;
+    const float* t3v = P;                P += p * p;
+    const float* t4c = P;                P += p;
+    const float* t4v = P;                P += p;
+    const float* t6c = P;                P += p * p;
+    const float* t6v = P;                P += p * p;
+    const float* t7 = P;                 P += p * p;
+    const float* t8 = P;
+
+    // ---- once per CTA: weights into shared memory, t3 . relu(+-t4) ---------------------------------------------------
+    stage_transposed(t2c, p, PP, t2cT, tid, nt);
+    stage_transposed(t2v, p, PP, t2vT, tid, nt);
+    stage_transposed(t7, p, PP, t7T, tid, nt);
+    for (int l = tid; l < p; l += nt) {
+        r4[l] = fmaxf(__ldg(t4c + l), 0.f);
+        r4[PP + l] = fmaxf(-__ldg(t4c + l), 0.f);
+        r4[2 * PP + l] = fmaxf(__ldg(t4v + l), 0.f);
+        r4[3 * PP + l] = fmaxf(-__ldg(t4v + l), 0.f);
+    }
+    __syncthreads();
+    small_matvec(t3c, p, r4, w3cp, warp, lane, nw);
+    small_matvec(t3c, p, r4 + PP, w3cn, warp, lane, nw);
+    small_matvec(t3v, p, r4 + 2 * PP, w3vp, warp, lane, nw);
+    small_matvec(t3v, p, r4 + 3 * PP, w3vn, warp, lane, nw);
+    __syncthreads();
+
+    for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        for (int j = tid; j < n; j += nt) {
+            cj[j] = (float)cg[j];
+            Cp[j] = 0.f; Cn[j] = 0.f; ccnt[j] = 0.f;
+        }
+        if (tid == 0) *iflag = 0;
+        __syncthreads();
+
+        // ---- pass over A: row normalisation, cosines, relu row/column sums, adjacency degrees -------------------------
+        for (int i = warp; i < m; i += nw) {
+            const float bi = (float)bg[i];
+            float ss = 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const float x = (float)Ag[(size_t)i * n + j];
+                ss = fmaf(x, x, ss);
+            }
+            ss = warp_sumf(ss) + bi * bi;                     // ||[a_i | -b_i]||^2
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);  // F.normalize eps
+            float cs = 0.f, sp = 0.f, sn = 0.f, cnt = 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const float x = (float)Ag[(size_t)i * n + j] * inv;
+                cs = fmaf(x, cj[j], cs);
+                sp += fmaxf(x, 0.f);
+                sn += fmaxf(-x, 0.f);
+                const float nz = (x != 0.f) ? 1.f : 0.f;
+                cnt += nz;
+                // column statistics: every (warp, j) pair is touched by one lane only -> shared-memory atomics are cheap
+                atomicAdd(&Cp[j], fmaxf(x, 0.f));
+                atomicAdd(&Cn[j], fmaxf(-x, 0.f));
+                atomicAdd(&ccnt[j], nz);
+                if (a.store_A) An[(size_t)i * n + j] = x;
+            }
+            cs = warp_sumf(cs); sp = warp_sumf(sp); sn = warp_sumf(sn); cnt = warp_sumf(cnt);
+            if (lane == 0) {
+                rb[i] = bi * inv;
+                cosv[i] = cs;
+                Sp[i] = sp; Sn[i] = sn; rcnt[i] = cnt;
+                if (cnt != (float)n) *iflag = 1;              // benign race: any writer sets the same value
+            }
+        }
+        for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
+        __syncthreads();
+        const bool dense = (*iflag == 0);
+        if (!dense && !a.store_A) {
+            if (tid == 0) *a.error_flag = 1;
+        }
+
+        // ---- T rounds of message passing ---------------------------------------------------------------------------------
+        for (int t = 0; t < a.T; ++t) {
+            if (dense || !a.store_A) {
+                for (int l = warp; l < p; l += nw) {
+                    float sc = 0.f, svv = 0.f;
+                    for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
+                    for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
+                    sc = warp_sumf(sc); svv = warp_sumf(svv);
+                    if (lane == 0) { meanc[l] = sc / (float)m; meanv[l] = svv / (float)n; }
+                }
+                __syncthreads();
+                small_matvec(t2c, p, meanc, yv, warp, lane, nw);
+                small_matvec(t2v, p, meanv, yc, warp, lane, nw);
+                __syncthreads();
+            } else {
+                // general adjacency: agg_v[:,j] = mean of mu_c over rows adjacent to j, agg_c[:,i] likewise over columns
+                for (int e = tid; e < p * n; e += nt) {
+                    const int l = e / n, j = e - l * n;
+                    float acc = 0.f;
+                    for (int i = 0; i < m; ++i)
+                        if (An[(size_t)i * n + j] != 0.f) acc += mu[l * NP + i];
+                    agg[l * NP + j] = acc / fmaxf(ccnt[j], 1e-12f);
+                }
+                for (int e = tid; e < p * m; e += nt) {
+                    const int l = e / m, i = e - l * m;
+                    float acc = 0.f;
+                    for (int j = 0; j < n; ++j)
+                        if (An[(size_t)i * n + j] != 0.f) acc += mu[l * NP + m + j];
+                    agg[l * NP + n + i] = acc / fmaxf(rcnt[i], 1e-12f);
+                }
+                __syncthreads();
+                // term2 in place: positions < n get t2c . agg_v, positions >= n get t2v . agg_c  (B9 layout)
+                node_matvec(t2cT, PP, p, agg, NP, mu, NP, n, tid, nt);
+                node_matvec(t2vT, PP, p, agg + n, NP, mu + n, NP, m, tid, nt);
+                __syncthreads();
+            }
+            for (int e = tid; e < p * NP; e += nt) {
+                const int l = e / NP, q = e - l * NP;
+                float val = __ldg(t0 + l);
+                if (q < m) {
+                    val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
+                    val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
+                } else {
+                    const int j = q - m;
+                    val += __ldg(t1v + l) * cj[j] + w3vp[l] * Cp[j] + w3vn[l] * Cn[j];
+                }
+                if (dense || !a.store_A) val += (q < n) ? yv[l] : yc[l];
+                else val += mu[e];
+                mu[e] = fmaxf(val, 0.f);
+            }
+            __syncthreads();
+        }
+
+        // ---- head: u6, t7 . mu[:, i], relu, t8, (log-)softmax ----------------------------------------------------------------
+        for (int l = warp; l < p; l += nw) {
+            float sc = 0.f, svv = 0.f;
+            for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
+            for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
+            sc = warp_sumf(sc); svv = warp_sumf(svv);
+            if (lane == 0) { meanc[l] = sc / (float)m; meanv[l] = svv / (float)n; }
+        }
+        __syncthreads();
+        small_matvec(t6c, p, meanc, tmp1, warp, lane, nw);
+        small_matvec(t6v, p, meanv, tmp2, warp, lane, nw);
+        __syncthreads();
+        for (int l = tid; l < p; l += nt) u6[l] = fmaxf(tmp1[l] + tmp2[l], 0.f);   // relu(u6) is what t8 sees
+        __syncthreads();
+        // scores_i = t8[:, :p] . relu(u6) + t8[:, p:2p] . relu(t7 mu_i) + t8[:, 2p:2p+4] . c_feats_i
+        const int W8 = 2 * p + 4;
+        for (int i = tid; i < m; i += nt) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int l = 0; l < p; ++l) {
+                s0 = fmaf(__ldg(t8 + l), u6[l], s0);
+                s1 = fmaf(__ldg(t8 + W8 + l), u6[l], s1);
+            }
+            for (int kb = 0; kb < PP; kb += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int l = 0; l < p; ++l) {
+                    const float x = mu[l * NP + i];
+                    const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
+                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                }
+                const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (kb + u < p) {
+                        s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
+                        s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
+                    }
+                }
+            }
+            const float f0 = 1.f, f1 = rb[i], f3 = cosv[i];   // c_feats = [is_inequality, rhs', is_bound = 0, cosine]
+            s0 += __ldg(t8 + 2 * p) * f0 + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 3) * f3;
+            s1 += __ldg(t8 + W8 + 2 * p) * f0 + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 3) * f3;
+            const float mx = fmaxf(s0, s1);
+            const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
+            float* lo = a.logp + ((size_t)lp * m + i) * 2;
+            lo[0] = s0 - lse;
+            lo[1] = s1 - lse;
+            if (a.probs) {
+                float* po = a.probs + ((size_t)lp * m + i) * 2;
+                po[0] = expf(s0 - lse);
+                po[1] = expf(s1 - lse);
+            }
+        }
+        __syncthreads();
+    }
+    (void)z7; (void)ctmp;
+}
+
+// =====================================================================================================================
+// complete
+// =====================================================================================================================
+struct CmpLayout {
+    size_t t2rr, t7, G, mu, mu2, vecs, total;   // floats
+};
+__host__ __device__ inline CmpLayout cmp_layout(int m, int n, int p) {
+    const int PP = pad4(p);
+    int PG = n + 1;
+    if ((PG & 1) == 0) PG += 1;                 // odd pitch: conflict-free column walks
+    CmpLayout L;
+    size_t off = 0;
+    L.t2rr = off; off += (size_t)p * PP;
+    L.t7 = off;   off += (size_t)p * PP;
+    L.G = off;    off += (size_t)(m + 1) * PG;
+    L.mu = off;   off += (size_t)p * (m + 1);
+    L.mu2 = off;  off += (size_t)p * (m + 1);
+    L.vecs = off; off += (size_t)3 * (m + 1) + 16 * PP + 64;
+    L.total = off;
+    return L;
+}
+size_t s2v_complete_smem_bytes(int m, int n, int p) { return cmp_layout(m, n, p).total * 4; }
+
+__global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
+    extern __shared__ __align__(16) float sm[];
+    const int m = a.m, n = a.n, p = a.p, PP = pad4(p), M1 = m + 1;
+    int PG = n + 1;
+    if ((PG & 1) == 0) PG += 1;
+    const CmpLayout L = cmp_layout(m, n, p);
+    float* t2rrT = sm + L.t2rr;
+    float* t7T = sm + L.t7;
+    float* G = sm + L.G;
+    float* mu = sm + L.mu;
+    float* mu2 = sm + L.mu2;
+    float* v = sm + L.vecs;
+    float* Wp = v;     v += M1;    // sum_{j<m, j!=i} relu(W_ij)
+    float* Wn = v;     v += M1;    // sum_{j<m, j!=i} relu(-W_ij)
+    float* wc = v;     v += M1;    // W[m][j] = <c, a_j'> (cost node against row j)
+    float* w3p = v;    v += PP;    // t3rr . relu(t4rr)
+    float* w3n = v;    v += PP;    // t3rr . relu(-t4rr)
+    float* meanr = v;  v += PP;
+    float* muc = v;    v += PP;
+    float* y1 = v;     v += PP;    // t2rc . mu_c
+    float* y2 = v;     v += PP;    // t2cr . mean(mu_r)
+    float* u3c = v;    v += PP;    // t3cr . relu_cr
+    float* u6 = v;     v += PP;
+    float* tmp1 = v;   v += PP;
+    float* tmp2 = v;   v += PP;
+    float* r4 = v;     v += 4 * PP;
+    float* scal = v;               // [0] = scalar t4rc . relu_rc (B10), [1] = sum relu(wc), [2] = sum relu(-wc)
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const float* P = a.params;
+    const float* t0 = P;     P += p;
+    const float* t1 = P;     P += p;
+    const float* t2rr = P;   P += p * p;
+    const float* t2rc = P;   P += p * p;
+    const float* t2cr = P;   P += p * p;
+    const float* t3rr = P;   P += p * p;
+    P += p * p;              // t3rc: unused by the reference forward (B10)
+    const float* t3cr = P;   P += p * p;
+    const float* t4rr = P;   P += p;
+    const float* t4rc = P;   P += p;
+    const float* t4cr = P;   P += p;
+    const float* t6r = P;    P += p * p;
+    const float* t6c = P;    P += p * p;
+    const float* t7 = P;     P += p * p;
+    const float* t8 = P;
+
+    stage_transposed(t2rr, p, PP, t2rrT, tid, nt);
+    stage_transposed(t7, p, PP, t7T, tid, nt);
+    for (int l = tid; l < p; l += nt) {
+        r4[l] = fmaxf(__ldg(t4rr + l), 0.f);
+        r4[PP + l] = fmaxf(-__ldg(t4rr + l), 0.f);
+    }
+    __syncthreads();
+    small_matvec(t3rr, p, r4, w3p, warp, lane, nw);
+    small_matvec(t3rr, p, r4 + PP, w3n, warp, lane, nw);
+    __syncthreads();
+
+    for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        // ---- G = [normalize([A | b]) ; [c, 0]]  (normalisation in fp64 as the reference does, s2v.py:145) ----------------
+        for (int i = warp; i < m; i += nw) {
+            const double bi = bg[i];
+            double ss = 0.0;
+            for (int j = lane; j < n; j += 32) {
+                const double x = Ag[(size_t)i * n + j];
+                ss = fma(x, x, ss);
+            }
+            ss = warp_sum(ss) + bi * bi;
+            const double inv = 1.0 / fmax(sqrt(ss), 1e-12);
+            for (int j = lane; j < n; j += 32) G[i * PG + j] = (float)(Ag[(size_t)i * n + j] * inv);
+            if (lane == 0) G[i * PG + n] = (float)(bi * inv);
+        }
+        for (int j = tid; j <= n; j += nt) G[m * PG + j] = (j < n) ? (float)cg[j] : 0.f;
+        for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
+        __syncthreads();
+
+        // ---- fused Gram + relu row sums: W_ij = <G_i, G_j>, never stored ----------------------------------------------------
+        // each warp takes 4 rows at a time; lanes walk the columns j (conflict-free: odd pitch)
+        for (int i0 = warp * 4; i0 < M1; i0 += nw * 4) {
+            float sp[4] = {0.f, 0.f, 0.f, 0.f}, sn[4] = {0.f, 0.f, 0.f, 0.f}, wl[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int j = lane; j < M1; j += 32) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                const float* gj = G + j * PG;
+                for (int k = 0; k <= n; ++k) {
+                    const float x = gj[k];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = (i0 + u < M1) ? i0 + u : m;
+                        acc[u] = fmaf(G[i * PG + k], x, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + u;
+                    if (i < M1 && j != i) {
+                        if (j < m) { sp[u] += fmaxf(acc[u], 0.f); sn[u] += fmaxf(-acc[u], 0.f); }
+                        else wl[u] = acc[u];                      // column m: against the cost node
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float a0 = warp_sumf(sp[u]), a1 = warp_sumf(sn[u]), a2 = warp_sumf(wl[u]);
+                if (lane == 0 && i0 + u < M1) {
+                    Wp[i0 + u] = a0; Wn[i0 + u] = a1; wc[i0 + u] = a2;
+                }
+            }
+        }
+        __syncthreads();
+        // cost-node statistics: sums of relu(+-W[m][j]) over rows j < m  (W is symmetric: W[:m, m] == W[m, :m])
+        if (warp == 0) {
+            float sp = 0.f, sn = 0.f;
+            for (int j = lane; j < m; j += 32) { sp += fmaxf(wc[j], 0.f); sn += fmaxf(-wc[j], 0.f); }
+            sp = warp_sumf(sp); sn = warp_sumf(sn);
+            if (lane == 0) { scal[1] = sp; scal[2] = sn; }
+        }
+        __syncthreads();
+        if (warp == 0) {   // scalar of B10: t4rc . (relu(t4rc) S+ + relu(-t4rc) S-)
+            float acc = 0.f;
+            for (int l = lane; l < p; l += 32) {
+                const float tv = __ldg(t4rc + l);
+                acc += tv * (fmaxf(tv, 0.f) * scal[1] + fmaxf(-tv, 0.f) * scal[2]);
+            }
+            acc = warp_sumf(acc);
+            if (lane == 0) scal[0] = acc;
+        }
+        for (int l = tid; l < p; l += nt) {
+            const float tv = __ldg(t4cr + l);
+            tmp1[l] = fmaxf(tv, 0.f) * scal[1] + fmaxf(-tv, 0.f) * scal[2];      // relu_cr
+        }
+        __syncthreads();
+        small_matvec(t3cr, p, tmp1, u3c, warp, lane, nw);
+        __syncthreads();
+
+        // ---- T rounds ----------------------------------------------------------------------------------------------------------
+        for (int t = 0; t < a.T; ++t) {
+            for (int l = warp; l < p; l += nw) {
+                float sr = 0.f;
+                for (int i = lane; i < m; i += 32) sr += mu[l * M1 + i];
+                sr = warp_sumf(sr);
+                if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * M1 + m]; }
+            }
+            __syncthreads();
+            small_matvec(t2rc, p, muc, y1, warp, lane, nw);
+            small_matvec(t2cr, p, meanr, y2, warp, lane, nw);
+            node_matvec(t2rrT, PP, p, mu, M1, mu2, M1, m, tid, nt);          // t2rr . mu_r
+            __syncthreads();
+            for (int e = tid; e < p * M1; e += nt) {
+                const int l = e / M1, q = e - l * M1;
+                float val;
+                if (q < m) {
+                    val = __ldg(t0 + l) + __ldg(t1 + l) + mu2[e] + y1[l] + w3p[l] * Wp[q] + w3n[l] * Wn[q] + scal[0];
+                } else {
+                    val = __ldg(t0 + l) + y2[l] + u3c[l];                    // node feature of the cost node is 0
+                }
+                mu[e] = fmaxf(val, 0.f);
+            }
+            __syncthreads();
+        }
+
+        // ---- head -----------------------------------------------------------------------------------------------------------------
+        for (int l = warp; l < p; l += nw) {
+            float sr = 0.f;
+            for (int i = lane; i < m; i += 32) sr += mu[l * M1 + i];
+            sr = warp_sumf(sr);
+            if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * M1 + m]; }
+        }
+        __syncthreads();
+        small_matvec(t6r, p, meanr, tmp1, warp, lane, nw);
+        small_matvec(t6c, p, muc, tmp2, warp, lane, nw);
+        __syncthreads();
+        for (int l = tid; l < p; l += nt) u6[l] = fmaxf(tmp1[l] + tmp2[l], 0.f);
+        __syncthreads();
+        const int W8 = 2 * p;
+        for (int i = tid; i < m; i += nt) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int l = 0; l < p; ++l) {
+                s0 = fmaf(__ldg(t8 + l), u6[l], s0);
+                s1 = fmaf(__ldg(t8 + W8 + l), u6[l], s1);
+            }
+            for (int kb = 0; kb < PP; kb += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int l = 0; l < p; ++l) {
+                    const float x = mu[l * M1 + i];
+                    const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
+                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                }
+                const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (kb + u < p) {
+                        s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
+                        s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
+                    }
+                }
+            }
+            const float mx = fmaxf(s0, s1);
+            const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
+            float* lo = a.logp + ((size_t)lp * m + i) * 2;
+            lo[0] = s0 - lse;
+            lo[1] = s1 - lse;
+            if (a.probs) {
+                float* po = a.probs + ((size_t)lp * m + i) * 2;
+                po[0] = expf(s0 - lse);
+                po[1] = expf(s1 - lse);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+cudaError_t launch_s2v_forward(const S2vArgs& a0, int sm_count, long long smem_optin, cudaStream_t st, const char** why) {
+    S2vArgs a = a0;
+    *why = "";
+    if (a.graph == 1) {
+        a.store_A = (long long)s2v_bipartite_smem_bytes(a.m, a.n, a.p, true) <= smem_optin ? 1 : 0;
+        const size_t smem = s2v_bipartite_smem_bytes(a.m, a.n, a.p, a.store_A != 0);
+        if ((long long)smem > smem_optin) { *why = "bipartite forward: embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
+        cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_bipartite_kernel, 256, smem);
+        if (e != cudaSuccess) return e;
+        long long grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
+        if (grid > a.B) grid = a.B;
+        s2v_bipartite_kernel<<<(int)grid, 256, smem, st>>>(a);
+    } else {
+        const size_t smem = s2v_complete_smem_bytes(a.m, a.n, a.p);
+        if ((long long)smem > smem_optin) { *why = "complete forward: G and embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
+        cudaError_t e = cudaFuncSetAttribute(s2v_complete_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_complete_kernel, 256, smem);
+        if (e != cudaSuccess) return e;
+        long long grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
+        if (grid > a.B) grid = a.B;
+        s2v_complete_kernel<<<(int)grid, 256, smem, st>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace ddb

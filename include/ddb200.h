@@ -113,6 +113,21 @@ int ddb_generate_solve_label_dev(ddb_ctx *ctx, uint64_t key, int64_t first_insta
                                  int32_t *n_active, int32_t *pivots, int32_t *ties,
                                  double *A_out, double *b_out, double *c_out, void *stream);
 
+/*
+ * (4) CLASSIFIER FORWARD -- replaces Model.forward (src/ml/models/s2v.py:45-54; _forward_complete :124-187,
+ * _forward_bipartite :253-323) and the per-instance batch loop of ml/utils.py:3-25 for B instances of one shape.
+ * graph: 0 = 'complete', 1 = 'bipartite'.  p = embedding dimension, T = rounds_s2v.  A, b, c are the fp64 arrays of
+ * (2); in_loss is every row (the random-LP feature adapter).
+ * params: flat fp32 block in the reference's state_dict order and shapes (s2v.py:60-89 / 189-216):
+ *   complete : t0[p] t1[p] t2rr t2rc t2cr t3rr t3rc t3cr [p*p each] t4rr[p] t4rc[p] t4cr[p] t6r t6c t7 [p*p] t8[2*2p]
+ *   bipartite: t0[p] t1c[p*4] t1v[p] t2c t2v t3c t3v [p*p] t4c[p] t4v[p] t6c t6v t7 [p*p] t8[2*(2p+4)]
+ * Outputs: logp[B,m,2] = log_softmax(scores) (what forward returns), probs[B,m,2] (Model.probs; nullable).
+ */
+int ddb_s2v_param_count(int graph, int p);
+int ddb_s2v_forward_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p, int T,
+                        const double *A, const double *b, const double *c, const float *params,
+                        float *logp, float *probs, void *stream);
+
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 int64_t ddb_launch_count(ddb_ctx *ctx);
 

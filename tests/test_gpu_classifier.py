@@ -1,0 +1,89 @@
+"""GPU: the batched classifier forward kernels (through the C ABI) against the reference-generated fixtures and the
+CPU oracle.  Tolerance: fp32, 5e-5 absolute on log-probabilities (re-association of the relu-sum identity)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import classifier as oc
+from oracle import randomlp as orl
+
+pytestmark = pytest.mark.gpu
+TOL = 5e-5
+
+
+def _load(golden_dir, graph):
+    g = np.load(os.path.join(golden_dir, 's2v_%s.npz' % graph))
+    for ci in range(6):
+        pre = 'case%d_' % ci
+        m, n, p, T, seed = [int(v) for v in g[pre + 'dims']]
+        P = {k[len(pre + 'param_'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + 'param_')}
+        yield (m, n, p, T), P, g[pre + 'A'], g[pre + 'b'], g[pre + 'c'], g[pre + 'logp'], g[pre + 'probs']
+
+
+@pytest.mark.parametrize('graph', ['bipartite', 'complete'])
+def test_kernel_matches_reference_fixtures(cuda_device, golden_dir, graph):
+    from deep_dantzig_b200.ml.models.s2v import Model
+    for dims, P, A, b, c, logp, probs in _load(golden_dir, graph):
+        model = Model(graph, dims[2], dims[3], on_cuda=True, verbose_init=False)
+        model.load_state_dict(P)
+        with torch.no_grad():
+            lp = model.forward_batch(torch.from_numpy(A)[None].cuda(), torch.from_numpy(b)[None].cuda(), torch.from_numpy(c)[None].cuda())
+        assert lp.shape == (1, dims[0], 2)
+        assert np.abs(lp[0].cpu().numpy() - logp).max() <= TOL, (graph, dims)
+        assert np.abs(model.probs[0].cpu().numpy() - probs).max() <= TOL, (graph, dims)
+
+
+@pytest.mark.parametrize('graph,m,n,p,T', [('bipartite', 50, 20, 12, 3), ('bipartite', 200, 100, 40, 3), ('bipartite', 500, 250, 40, 3),
+                                           ('complete', 50, 20, 12, 4), ('complete', 200, 100, 40, 3), ('bipartite', 37, 19, 13, 2),
+                                           ('complete', 37, 19, 5, 1)])
+def test_batched_kernel_vs_oracle(cuda_device, graph, m, n, p, T):
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import solver
+    torch.manual_seed(3)
+    model = Model(graph, p, T, on_cuda=True, verbose_init=False)
+    B = 40
+    A, b, c = solver.generate(5, 0, B, m, n)
+    with torch.no_grad():
+        lp = model.forward_batch(A, b, c).cpu().numpy()
+        lpt = model.forward_batch_torch(A, b, c).cpu().numpy()          # the autograd path computes the same thing
+    assert np.abs(lp - lpt).max() <= TOL
+    P = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    An, bn, cn = A.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    for k in (0, 7, B - 1):
+        ref, _ = oc.forward(graph, P, An[k], bn[k], cn[k], T)
+        assert np.abs(lp[k] - ref.numpy()).max() <= TOL, k
+    assert np.isfinite(lp).all() and np.allclose(np.exp(lp).sum(2), 1.0, atol=1e-5)
+
+
+def test_sparse_instances_use_the_adjacency(cuda_device):
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import solver
+    torch.manual_seed(4)
+    model = Model('bipartite', 10, 3, on_cuda=True, verbose_init=False)
+    A, b, c = solver.generate(6, 0, 16, 60, 30, density=0.3)
+    with torch.no_grad():
+        lp = model.forward_batch(A, b, c).cpu().numpy()
+    P = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    for k in (0, 5, 15):
+        ref, _ = oc.forward('bipartite', P, A[k].cpu().numpy(), b[k].cpu().numpy(), c[k].cpu().numpy(), 3)
+        assert np.abs(lp[k] - ref.numpy()).max() <= TOL
+
+
+@pytest.mark.parametrize('graph', ['bipartite', 'complete'])
+def test_forward_item_dropin(cuda_device, graph):
+    """Model.forward(item) with the reference's item dictionaries and an in_loss subset."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    torch.manual_seed(5)
+    model = Model(graph, 12, 3, on_cuda=True, verbose_init=False)
+    A, b, c = orl.generate_instance(50, 20, 11)
+    item = oc.item_complete(A, b, c) if graph == 'complete' else oc.item_bipartite(A, b, c)
+    item['in_loss'] = [0, 3, 7, 49]
+    with torch.no_grad():
+        lp = model(item)
+    P = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    ref, refp = oc.forward(graph, P, A, b, c, 3, in_loss=[0, 3, 7, 49])
+    assert lp.shape == (4, 2) and model.probs.shape == (4, 2)
+    assert np.abs(lp.cpu().numpy() - ref.numpy()).max() <= TOL
+    assert np.abs(model.probs.cpu().numpy() - refp.numpy()).max() <= TOL
