@@ -13,6 +13,11 @@ pytestmark = pytest.mark.gpu
 TOL = 5e-5
 
 
+def _close(got, want):
+    """fp32: 5e-5 absolute + 1e-5 relative (random-init scores reach |log p| ~ 30 at p = 40)."""
+    return bool((np.abs(got - want) <= TOL + 1e-5 * np.abs(want)).all())
+
+
 def _load(golden_dir, graph):
     g = np.load(os.path.join(golden_dir, 's2v_%s.npz' % graph))
     for ci in range(6):
@@ -31,8 +36,8 @@ def test_kernel_matches_reference_fixtures(cuda_device, golden_dir, graph):
         with torch.no_grad():
             lp = model.forward_batch(torch.from_numpy(A)[None].cuda(), torch.from_numpy(b)[None].cuda(), torch.from_numpy(c)[None].cuda())
         assert lp.shape == (1, dims[0], 2)
-        assert np.abs(lp[0].cpu().numpy() - logp).max() <= TOL, (graph, dims)
-        assert np.abs(model.probs[0].cpu().numpy() - probs).max() <= TOL, (graph, dims)
+        assert _close(lp[0].cpu().numpy(), logp), (graph, dims)
+        assert _close(model.probs[0].cpu().numpy(), probs), (graph, dims)
 
 
 @pytest.mark.parametrize('graph,m,n,p,T', [('bipartite', 50, 20, 12, 3), ('bipartite', 200, 100, 40, 3), ('bipartite', 500, 250, 40, 3),
@@ -48,12 +53,12 @@ def test_batched_kernel_vs_oracle(cuda_device, graph, m, n, p, T):
     with torch.no_grad():
         lp = model.forward_batch(A, b, c).cpu().numpy()
         lpt = model.forward_batch_torch(A, b, c).cpu().numpy()          # the autograd path computes the same thing
-    assert np.abs(lp - lpt).max() <= TOL
+    assert _close(lp, lpt)
     P = {k: v.detach().cpu() for k, v in model.named_parameters()}
     An, bn, cn = A.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
     for k in (0, 7, B - 1):
         ref, _ = oc.forward(graph, P, An[k], bn[k], cn[k], T)
-        assert np.abs(lp[k] - ref.numpy()).max() <= TOL, k
+        assert _close(lp[k], ref.numpy()), k
     assert np.isfinite(lp).all() and np.allclose(np.exp(lp).sum(2), 1.0, atol=1e-5)
 
 
@@ -68,7 +73,7 @@ def test_sparse_instances_use_the_adjacency(cuda_device):
     P = {k: v.detach().cpu() for k, v in model.named_parameters()}
     for k in (0, 5, 15):
         ref, _ = oc.forward('bipartite', P, A[k].cpu().numpy(), b[k].cpu().numpy(), c[k].cpu().numpy(), 3)
-        assert np.abs(lp[k] - ref.numpy()).max() <= TOL
+        assert _close(lp[k], ref.numpy())
 
 
 @pytest.mark.parametrize('graph', ['bipartite', 'complete'])
@@ -85,5 +90,5 @@ def test_forward_item_dropin(cuda_device, graph):
     P = {k: v.detach().cpu() for k, v in model.named_parameters()}
     ref, refp = oc.forward(graph, P, A, b, c, 3, in_loss=[0, 3, 7, 49])
     assert lp.shape == (4, 2) and model.probs.shape == (4, 2)
-    assert np.abs(lp.cpu().numpy() - ref.numpy()).max() <= TOL
-    assert np.abs(model.probs.cpu().numpy() - refp.numpy()).max() <= TOL
+    assert _close(lp.cpu().numpy(), ref.numpy())
+    assert _close(model.probs.cpu().numpy(), refp.numpy())
