@@ -60,6 +60,9 @@ class Model(nn.Module):
         else:
             raise ValueError('Graph not recognised')
         self.probs = None
+        # explicit opt-in (tests of the host-side training logic on CPU/gloo); never set implicitly: inference
+        # without it goes to the CUDA kernel or raises
+        self.force_torch = False
 
     def require_grads(self, req=True):
         for param in self.parameters():
@@ -75,7 +78,7 @@ class Model(nn.Module):
     def forward_batch(self, A, b, c):
         """A[B,m,n], b[B,m], c[B,n] float64 -> log-probs [B,m,2]; sets self.probs [B,m,2].  CUDA kernel unless
         autograd is recording for a parameter, in which case the differentiable torch path is used."""
-        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+        if self.force_torch or (torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())):
             return self.forward_batch_torch(A, b, c)
         return self.forward_batch_cuda(A, b, c)
 

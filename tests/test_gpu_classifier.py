@@ -92,3 +92,27 @@ def test_forward_item_dropin(cuda_device, graph):
     assert lp.shape == (4, 2) and model.probs.shape == (4, 2)
     assert _close(lp.cpu().numpy(), ref.numpy())
     assert _close(model.probs.cpu().numpy(), refp.numpy())
+
+
+def test_drivers_end_to_end(cuda_device, tmp_path):
+    """benchmark.run_benchmark / phase_transitions.compute_phaseTransitions / sweep_ratio_density on tiny settings:
+    dataset generated+solved+labelled on the GPU, classifier trained with the batched forward, records saved with the
+    reference's file naming and schema."""
+    import json
+    from deep_dantzig_b200.benchmark import run_benchmark
+    from deep_dantzig_b200.phase_transitions import compute_phaseTransitions, sweep_ratio_density
+    grid = {'dataset': ['randomlp'], 'graph': ['bipartite'], 'elem_type': ['lp'], 'num_elems': [48], 'p': [8],
+            'rounds_s2v': [2], 'epochs': [3], 'batch_size': [16], 'learning_rate': [0.01], 'momentum': [0.9],
+            'weight_decay': [0], 'seed': [0], 'm': [20], 'n': [10]}
+    stamps = run_benchmark(grid, str(tmp_path), cuda=True, tag='t')
+    res = json.load(open(tmp_path / ('benchmark_randomlp_res_%s.json' % stamps[0])))
+    assert set(res) == {'params', 'out', 'dataset', 'seed', 'cuda', 'tag'} and len(res['out']['results']['train']) == 3
+    assert (tmp_path / ('benchmark_randomlp_model_%s.json' % stamps[0])).exists()
+    assert res['out']['results']['train'][-1]['total_loss'] < res['out']['results']['train'][0]['total_loss'] * 1.5
+    bp = {'epochs': [2], 'seeds': [0], 'batch_sizes': [16], 'rounds_s2v': [1], 'learning_rates': [0.01],
+          'momentums': [0.9], 'weight_decays': [0], 'ps': [3]}
+    recs = compute_phaseTransitions(str(tmp_path), 'randomlp', bp, cuda=True, tag='t', num_elems=32, m=20, n=10)
+    assert len(recs) == 1 and set(recs[0]['out']) == {'accs', 'losses'} and 3 in recs[0]['out']['accs']
+    sw = sweep_ratio_density(n=20, ratios=(1.5, 3.0), densities=(1.0, 0.3), per_cell=300, chunk=128)
+    assert all(v['instances'] == 300 and v['optimal'] + v['unbounded'] + v['other'] == 300 for v in sw.values())
+    assert sw[(3.0, 1.0)]['optimal'] > sw[(1.5, 1.0)]['optimal']        # more rows -> fewer unbounded instances (Wendel)
