@@ -1,6 +1,7 @@
 // C ABI (include/ddb200.h): context management, kernel-plan selection, launch plumbing, host-buffer flavours.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -15,6 +16,8 @@ cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, i
 bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
+bool rowreg_supported(int m, int n);
+cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
 struct S2vArgs {
     int graph;
     long long B;
@@ -162,7 +165,7 @@ extern "C" int ddb_device_info(ddb_ctx* ctx, int* sm_count, int* cc_major, int* 
 extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static int auto_plan(const ddb_ctx* ctx, int m, int n) {
-    if (ddb::regtile_supported(m, n)) return 0;
+    if (ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
     if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
     return 2;
 }
@@ -172,7 +175,7 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
     if (m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_plan: m=%d n=%d", m, n);
     if (n > 512) return fail(DDB_EUNSUPPORTED, "ddb_solve_plan: n=%d > 512 is not supported yet", n);
     int plan = ctx->forced_plan >= 0 ? ctx->forced_plan : auto_plan(ctx, m, n);
-    if (plan == 0 && !ddb::regtile_supported(m, n))
+    if (plan == 0 && !ddb::rowreg_supported(m, n) && !ddb::regtile_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "register-tiled kernel does not cover m=%d n=%d", m, n);
     if (plan == 1 && (int64_t)ddb::generic_smem_bytes(m, n, true) > ctx->smem_optin)
         return fail(DDB_EUNSUPPORTED, "shared-memory tableau does not fit for m=%d n=%d", m, n);
@@ -266,7 +269,10 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
     CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
 
     if (plan == 0) {
-        const size_t need = ddb::regtile_scratch_bytes(m, n, ctx->sm_count);
+        // plan 0 has two register-resident kernels: row-per-thread (preferred) and warp-tiled (wider shapes)
+        static const bool force_tiled = [] { const char* e = getenv("DDB_PLAN0_TILED"); return e && e[0] == '1'; }();
+        const bool use_row = ddb::rowreg_supported(m, n) && !(force_tiled && ddb::regtile_supported(m, n));
+        const size_t need = use_row ? 0 : ddb::regtile_scratch_bytes(m, n, ctx->sm_count);
         if (need) {
             if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
             if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
@@ -274,7 +280,10 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
             if (rc) return rc;
             a.gtab = (double*)ctx->scratch.p;
         }
-        CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
+        if (use_row)
+            CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
+        else
+            CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
         if (need) {
             CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
             ctx->scratch_in_use = true;

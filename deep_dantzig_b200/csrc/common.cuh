@@ -113,6 +113,39 @@ __device__ __forceinline__ double warp_sum(double v) {
     return v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// order-preserving 64-bit keys + redux-based warp argmin, fast reciprocal (register-resident kernels)
+// ---------------------------------------------------------------------------------------------------------
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ unsigned long long dkey(double v) {   // order-preserving map double -> uint64
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+// lane holding the minimum key (lowest lane on ties); kmin = that key.  Two redux + one ballot.
+__device__ __forceinline__ int warp_argmin_key(unsigned long long key, unsigned long long& kmin) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mhi = __reduce_min_sync(FULL, hi);
+    const unsigned lo2 = (hi == mhi) ? lo : 0xffffffffu;
+    const unsigned mlo = __reduce_min_sync(FULL, lo2);
+    const unsigned ball = __ballot_sync(FULL, hi == mhi && lo2 == mlo);
+    kmin = ((unsigned long long)mhi << 32) | mlo;
+    return __ffs(ball) - 1;
+}
+constexpr unsigned long long KEY_INF = 0xfff0000000000000ull;   // dkey(+inf)
+
+// 1/p to ~1 ulp: 20-bit hardware seed + two Newton steps (5 instructions instead of the ~35 of an IEEE division).
+__device__ __forceinline__ double fast_rcp(double p) {
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(p));
+    double e = fma(-p, x, 1.0);
+    x = fma(x, e, x);
+    e = fma(-p, x, 1.0);
+    x = fma(x, e, x);
+    return x;
+}
+
 constexpr double kInf = 1e300;
 constexpr int kBigVar = 0x7fffffff;
 

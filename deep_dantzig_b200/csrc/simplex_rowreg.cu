@@ -1,0 +1,728 @@
+// Row-per-thread batched fp64 simplex (plan 0): one LP per CTA, ONE TABLEAU ROW PER THREAD, held in registers.
+//
+// Why this layout: a pivot is a rank-1 update  T[i][c] -= f_i * prow[c].  With a whole row in one thread's registers
+//   * the update is NC DFMAs per thread whose second operand (the pivot row) is the same for every thread: it is
+//     read from shared memory with broadcast LDS.128 (one wavefront per two entries), so the instruction stream of
+//     a pivot is ~NC DFMA + NC/2 LDS per warp and nothing else scales with the row count;
+//   * everything that is "per row" (the right-hand side, the entry in the entering column, the ratio test, the
+//     most-negative-slack search of phase 1) is one value PER LANE, so a ratio test over 32 rows is a handful of
+//     instructions followed by a redux-based warp argmin -- not a loop;
+//   * everything that is "per column" (pricing vectors ghat / g, the column -> constraint map) is kept
+//     lane-distributed (column j in lane j%32, slot j/32) and replicated in every warp, so pricing is also a
+//     handful of instructions + one warp argmin, identical in every warp, with no communication.
+// The only dynamically indexed register access is READING "my entry in the entering column k" (a warp-uniform
+// branch tree); the matching write is folded into the rank-1 update by patching the published pivot row.
+//
+// At (m,n) = (200,100): NC = 101 registers-pairs per thread, 4 warps per LP, 2 LPs resident per SM (the register
+// file is the limit: 2 x 128 x 255 registers), 404 warp-DFMAs per pivot = 202 clk of one SM's fp64 pipe.
+//
+// Stages per LP (same algorithm and tolerances as simplex_generic.cu):
+//   0. crash order by cosine score (A streamed once from HBM through the idle tableau registers)
+//   1. crash as an explicit inverse: Gauss-Jordan on the n x n block A_B0 (thread t owns row t), 1 barrier/pivot
+//   2. remaining rows enter through  P_N = -A_N D  (D rows broadcast from shared memory)
+//   3. phase 1 (most negative slack leaves, ratio test along the published row), phase 2 (Dantzig), 2 barriers/pivot
+//   4. x = xv - D sigma, slack = b - A x from the caller's A, labels = |slack| <= threshold
+// Instances the tile cannot hold or whose static crash basis is singular are flagged status = -1 and re-solved by
+// the generic kernel on the device (capi.cu); nothing ever falls back to the CPU.
+#include <cstdlib>
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace ddb {
+
+// ---- dynamic (warp-uniform) register index -> jump table -------------------------------------------------------
+#define DDB_R8(M, b) M(b + 0) M(b + 1) M(b + 2) M(b + 3) M(b + 4) M(b + 5) M(b + 6) M(b + 7)
+#define DDB_R128(M)                                                                                       \
+    DDB_R8(M, 0) DDB_R8(M, 8) DDB_R8(M, 16) DDB_R8(M, 24) DDB_R8(M, 32) DDB_R8(M, 40) DDB_R8(M, 48)       \
+    DDB_R8(M, 56) DDB_R8(M, 64) DDB_R8(M, 72) DDB_R8(M, 80) DDB_R8(M, 88) DDB_R8(M, 96) DDB_R8(M, 104)    \
+    DDB_R8(M, 112) DDB_R8(M, 120)
+
+template <int NC>
+__device__ __forceinline__ double reg_get(const double (&T)[NC], int k) {
+    static_assert(NC <= 128, "jump table covers 128 registers");
+    double v = 0.0;
+    switch (k) {
+#define DDB_CASE(I)                                    \
+    case (I):                                          \
+        if constexpr ((I) < NC) v = T[(I) < NC ? (I) : 0]; \
+        break;
+        DDB_R128(DDB_CASE)
+#undef DDB_CASE
+        default: break;
+    }
+    return v;
+}
+// Write at a warp-uniform dynamic index.  The asm volatile leaves keep the compiler from if-converting the switch
+// into a select per register (which costs 3 instructions per tableau column); what remains is a uniform branch tree.
+template <int NC>
+__device__ __forceinline__ void reg_set(double (&T)[NC], int k, double v) {
+    switch (k) {
+#define DDB_CASE(I)                                                                         \
+    case (I):                                                                               \
+        if constexpr ((I) < NC) asm volatile("mov.f64 %0, %1;" : "=d"(T[(I) < NC ? (I) : 0]) : "d"(v)); \
+        break;
+        DDB_R128(DDB_CASE)
+#undef DDB_CASE
+        default: break;
+    }
+}
+
+struct RowPub {               // what the pivot row's owner (warp) publishes beside the row itself
+    double p;                 // pivot entry (stored scale)
+    double il;                // 1 / lam of the pivot row before the pivot
+    int k;                    // entering column (-1: none -> infeasible / singular crash basis)
+    int var;                  // constraint whose slack was basic in the pivot row
+};
+
+struct RowHdr {               // one per warp: its candidate row
+    unsigned long long key;   // dkey(slack) in phase 1, dkey(ratio) in phase 2, KEY_INF = no candidate
+    int row;                  // candidate tile row (= thread index)
+    int pad;
+};
+
+// Pitch (in doubles) of the rows kept in shared memory: even (16-byte rows for LDS.128) with pitch/2 odd, so that
+// 8 lanes reading the same 16-byte column of 8 consecutive rows hit 8 different bank groups.
+__host__ __device__ constexpr int row_pitch(int NC) {
+    int pd = (NC + 1) & ~1;
+    if (((pd / 2) & 1) == 0) pd += 2;
+    return pd;
+}
+
+struct RowLayout {
+    size_t D, prow, pub, hdr, order, colvar0, pivcol, basic_tile, sval, sig, xbuf, gbuf, gnn, red, total;
+};
+__host__ __device__ inline size_t rr_align(size_t v) { return (v + 15) / 16 * 16; }
+__host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W) {
+    RowLayout L;
+    const int PD = row_pitch(NC);
+    const int CT = 32 * ((NC + 31) / 32);
+    size_t off = 0;
+    L.D = off;          off += rr_align((size_t)n * PD * 8);
+    L.prow = off;       off += rr_align((size_t)2 * PD * 8);
+    L.pub = off;        off += rr_align((size_t)2 * sizeof(RowPub));
+    L.hdr = off;        off += rr_align((size_t)W * sizeof(RowHdr));
+    L.order = off;      off += rr_align((size_t)m * 4);
+    L.colvar0 = off;    off += rr_align((size_t)n * 4);
+    L.pivcol = off;     off += rr_align((size_t)n * 4);
+    L.basic_tile = off; off += rr_align((size_t)m * 4);
+    L.sval = off;       off += rr_align((size_t)W * 32 * 8);
+    L.sig = off;        off += rr_align((size_t)n * 8);
+    L.xbuf = off;       off += rr_align((size_t)(n > CT ? n : CT) * 8);
+    L.gbuf = off;       off += rr_align((size_t)m * 8);
+    L.gnn = off;        off += rr_align((size_t)m * 8);
+    L.red = off;        off += rr_align((size_t)(3 * W + 4) * 4);
+    L.total = off;
+    return L;
+}
+
+template <int NC, int W, int MINB>
+__global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs a) {
+    constexpr int CS = (NC + 31) / 32;      // slots of the lane-distributed column vectors
+    constexpr int PD = row_pitch(NC);
+    constexpr int NT = W * 32;              // threads = tile rows
+    constexpr int RHS = NC - 1;             // register / column that holds the right-hand side
+    constexpr int RB = NC / CS;             // rows per register batch when T is used as a streaming buffer
+    static_assert(W <= 32, "one header per lane");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int m = a.m, n = a.n;
+    const RowLayout L = make_row_layout(m, n, NC, W);
+    double* Dsm = reinterpret_cast<double*>(smem_raw + L.D);
+    double* prow = reinterpret_cast<double*>(smem_raw + L.prow);
+    RowPub* pub = reinterpret_cast<RowPub*>(smem_raw + L.pub);
+    RowHdr* hdr = reinterpret_cast<RowHdr*>(smem_raw + L.hdr);
+    int* order = reinterpret_cast<int*>(smem_raw + L.order);
+    int* colvar0 = reinterpret_cast<int*>(smem_raw + L.colvar0);
+    int* pivcol = reinterpret_cast<int*>(smem_raw + L.pivcol);
+    int* basic_tile = reinterpret_cast<int*>(smem_raw + L.basic_tile);
+    double* sval = reinterpret_cast<double*>(smem_raw + L.sval);
+    double* sig = reinterpret_cast<double*>(smem_raw + L.sig);
+    double* xbuf = reinterpret_cast<double*>(smem_raw + L.xbuf);
+    double* gbuf = reinterpret_cast<double*>(smem_raw + L.gbuf);
+    double* gnn = reinterpret_cast<double*>(smem_raw + L.gnn);
+    int* red = reinterpret_cast<int*>(smem_raw + L.red);
+    __shared__ long long cur_lp;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // ---- register state -------------------------------------------------------------------------------------
+    double T[NC];            // my tableau row; T[RHS] is its right-hand side
+    double vec[CS];          // ghat (phase 1), replicated in every warp, lane-distributed by column
+    double gv[CS];           // g (true reduced costs), same distribution
+    int colvar[CS];          // constraint whose slack is nonbasic in my columns (-1: not a structural column)
+    int rowvar = -1;         // constraint whose slack is basic in my row
+    double lam = 1.0, ilam = 1.0;   // my row's lazy scale: true row = lam * T
+
+    // Rows are stored LAZILY NORMALISED: the true tableau row is lam * T (ilam = 1 / lam).  A pivot (r, k) never
+    // rescales the pivot row: with p = T_r[k] (stored), rp = 1/p, il = ilam_r (before the pivot)
+    //     rows i != r :  f = T_i[k] * rp;  T_i[c] -= f * T_r[c] (c != k);  T_i[k] = -f * il       (lam_i unchanged)
+    //     row r       :  T_r unchanged except T_r[k] = il;  lam_r = rp, ilam_r = p
+    //     costs       :  g[c] -= g_k rp T_r[c] (c != k);  g[k] = -g_k rp il
+    // so the owner just publishes its raw registers and every other thread runs one FMA per entry.
+    // rank-1 update of my row from the raw pivot row in shared memory (broadcast reads):  T[c] -= f * prow[c]
+    auto rank1 = [&](const double* pr, double f) {
+        const double nf = -f;
+        const double2* p2 = reinterpret_cast<const double2*>(pr);
+#pragma unroll
+        for (int c2 = 0; c2 < NC / 2; ++c2) {
+            const double2 v = p2[c2];
+            T[2 * c2] = fma(nf, v.x, T[2 * c2]);
+            T[2 * c2 + 1] = fma(nf, v.y, T[2 * c2 + 1]);
+        }
+        if constexpr (NC & 1) T[NC - 1] = fma(nf, pr[NC - 1], T[NC - 1]);
+    };
+    auto publish = [&](double* pr) {
+        double2* p2 = reinterpret_cast<double2*>(pr);
+#pragma unroll
+        for (int c2 = 0; c2 < NC / 2; ++c2) p2[c2] = make_double2(T[2 * c2], T[2 * c2 + 1]);
+        if constexpr (NC & 1) pr[NC - 1] = T[NC - 1];
+    };
+    // slot kq of a lane-distributed vector (kq is warp-uniform)
+    auto slot_get_d = [&](const double (&v)[CS], int kq) {
+        double r = v[0];
+#pragma unroll
+        for (int cs = 1; cs < CS; ++cs)
+            if (kq == cs) r = v[cs];
+        return r;
+    };
+    auto slot_get_i = [&](const int (&v)[CS], int kq) {
+        int r = v[0];
+#pragma unroll
+        for (int cs = 1; cs < CS; ++cs)
+            if (kq == cs) r = v[cs];
+        return r;
+    };
+    // T used as a streaming buffer: dot products of up to RB*W rows of A (from `base`) with a lane-distributed
+    // vector; all loads of a batch are in flight together.  out1[i] = a_i . v ; out2[i] = a_i . a_i (optional)
+    auto row_dots = [&](const double* Ag, const double (&vl)[CS], double* out1, double* out2) {
+        for (int base = 0; base < m; base += RB * W) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int i = base + r * W + warp;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    T[r * CS + cs] = (i < m && j < n) ? __ldg(Ag + (size_t)i * n + j) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int i = base + r * W + warp;
+                double dot = 0.0, nn = 0.0;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const double v = T[r * CS + cs];
+                    dot = fma(v, vl[cs], dot);
+                    nn = fma(v, v, nn);
+                }
+                dot = warp_sum(dot);
+                if (out2) nn = warp_sum(nn);
+                if (lane == 0 && i < m) {
+                    out1[i] = dot;
+                    if (out2) out2[i] = nn;
+                }
+            }
+        }
+    };
+
+    for (;;) {
+        if (tid == 0) cur_lp = (long long)atomicAdd(a.counter, 1ull);
+        __syncthreads();
+        const long long lp = cur_lp;
+        if (lp >= a.B) break;
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;
+
+        // ---- stage 0: crash order ---------------------------------------------------------------------------
+        {
+            double cl[CS];
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+                const int j = lane + 32 * cs;
+                cl[cs] = (j < n) ? __ldg(cg + j) : 0.0;
+            }
+            row_dots(Ag, cl, gbuf, gnn);
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += NT) {
+            const bool excl = mask && mask[i] == 0;
+            const double dot = gbuf[i], nn = gnn[i];
+            gnn[i] = excl ? kInf : (nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5);
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += NT) {
+            const double v = gnn[i];
+            int rank = 0;
+            for (int i2 = 0; i2 < m; ++i2) {
+                const double v2 = gnn[i2];
+                rank += (v2 < v) || (v2 == v && i2 < i);
+            }
+            order[rank] = i;
+            basic_tile[i] = -1;
+        }
+        int m_eff = m;
+        if (mask) {
+            m_eff = 0;
+            for (int i = 0; i < m; ++i) m_eff += (gnn[i] < kInf);   // uniform, only for reduced LPs
+        }
+        __syncthreads();
+        const int nN = m_eff - n;
+        bool need_generic = (nN < 0) || (nN > NT) || (n > NT) || (n > NC - 1);
+
+        int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
+        int status = ST_OPTIMAL;
+        int buf = 0;
+
+        if (!need_generic) {
+            // ---- stage 1: thread t < n loads row order[t] of [A | b]; Gauss-Jordan to the inverse --------------
+            {
+                const bool have = tid < n;
+                const int row = have ? order[tid] : 0;
+                const double* Ar = Ag + (size_t)row * n;
+                if ((n & 1) == 0 && (reinterpret_cast<size_t>(a.A) & 15) == 0) {
+                    const double2* Ar2 = reinterpret_cast<const double2*>(Ar);
+#pragma unroll
+                    for (int c2 = 0; c2 < (NC - 1) / 2; ++c2) {
+                        double2 v = make_double2(0.0, 0.0);
+                        if (have && 2 * c2 < n) v = __ldg(Ar2 + c2);
+                        T[2 * c2] = v.x;
+                        T[2 * c2 + 1] = v.y;
+                    }
+                    if constexpr (((NC - 1) & 1) != 0) T[NC - 2] = 0.0;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < NC - 1; ++c) T[c] = (have && c < n) ? __ldg(Ar + c) : 0.0;
+                }
+                T[RHS] = have ? __ldg(bg + row) : 0.0;
+                rowvar = have ? row : -1;
+                lam = 1.0;
+                ilam = 1.0;
+            }
+            unsigned freemask = 0;   // bit cs set: column (lane + 32 cs) is still a free x_j
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+                const int j = lane + 32 * cs;
+                if (j < n) freemask |= 1u << cs;
+                gv[cs] = (j < n) ? __ldg(cg + j) : 0.0;
+            }
+
+            for (int t = 0; t < n; ++t) {
+                double* pr = prow + buf * PD;
+                const bool own = (tid == t);
+                if (warp == (t >> 5)) {
+                    // the owner publishes its raw row; its warp finds the pivot column (largest |entry| among the
+                    // free columns; a row is a pivot row once in the crash, so its lam is still 1)
+                    if (own) publish(pr);
+                    __syncwarp();
+                    unsigned long long best = 0ull;
+                    int bq = 0;
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        const double v = (j < n) ? pr[j] : 0.0;
+                        const unsigned long long kk =
+                            (freemask >> cs & 1u) ? (unsigned long long)__double_as_longlong(fabs(v)) : 0ull;
+                        if (kk > best) { best = kk; bq = cs; }
+                    }
+                    unsigned long long kmin;
+                    const int kl = warp_argmin_key(~best, kmin);   // argmax through the complemented key
+                    const int kq = __shfl_sync(FULL, bq, kl);
+                    const int k = kl + 32 * kq;
+                    const double pabs = __longlong_as_double((long long)~kmin);
+                    if (lane == 0) {
+                        const double p = pr[k];
+                        pub[buf].p = p;
+                        pub[buf].k = (pabs >= kTolCrash) ? k : -1;
+                        pivcol[t] = k;
+                    }
+                }
+                __syncthreads();
+                const int k = pub[buf].k;
+                if (k < 0) { need_generic = true; break; }
+                const int kl = k & 31, kq = k >> 5;
+                const double p = pub[buf].p;
+                const double rp = fast_rcp(p);
+                const double e = reg_get<NC>(T, k);
+                const double f = own ? 0.0 : e * rp;
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? 1.0 : -f);
+                if (own) { lam = rp; ilam = p; }
+                // cost row
+                const double gk = __shfl_sync(FULL, slot_get_d(gv, kq), kl);
+                const double fg = gk * rp;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    const double plv = (j < n) ? pr[j] : 0.0;
+                    gv[cs] = fma(-fg, plv, gv[cs]);
+                    if (lane == kl && kq == cs) gv[cs] = -fg;
+                }
+                if (lane == kl) freemask &= ~(1u << kq);
+                buf ^= 1;
+                ++npiv_crash;
+            }
+        }
+
+        if (!need_generic) {
+            __syncthreads();
+            // dump D' (row of x_k stored at index k; column RHS holds the x-vertex) and the column -> constraint map
+            if (tid < n) {
+                const int k = pivcol[tid];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) T[c] *= lam;      // true rows of the inverse
+                publish(Dsm + (size_t)k * PD);
+                colvar0[k] = rowvar;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+                const int j = lane + 32 * cs;
+                colvar[cs] = (j < n) ? colvar0[j] : -1;
+                vec[cs] = (j < n) ? 1.0 : 0.0;
+            }
+
+            // ---- stage 2: my row of P_N = -A_N D, s_N = b_N - A_N xv -------------------------------------------
+            const bool live = tid < nN;
+            {
+                const int myrow = live ? order[n + tid] : 0;
+#pragma unroll
+                for (int c = 0; c < NC; ++c) T[c] = 0.0;
+                if (warp * 32 < nN) {
+                    const double* Ar = Ag + (size_t)myrow * n;
+                    double an[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) an[q] = (live && q < n) ? __ldg(Ar + q) : 0.0;
+                    for (int k0 = 0; k0 < n; k0 += 4) {
+                        double av[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            av[q] = an[q];
+                            an[q] = (live && k0 + 4 + q < n) ? __ldg(Ar + k0 + 4 + q) : 0.0;
+                        }
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (k0 + q < n) rank1(Dsm + (size_t)(k0 + q) * PD, av[q]);
+                    }
+                }
+                if (live) T[RHS] += __ldg(bg + myrow);
+                rowvar = live ? myrow : -1;
+                lam = 1.0;
+                ilam = 1.0;
+            }
+
+            // ---- stage 3a: phase 1 ----------------------------------------------------------------------------
+            for (;;) {
+                const double s = lam * T[RHS];
+                unsigned long long kmin;
+                const int ll = warp_argmin_key((live && s < -kTolFeas) ? dkey(s) : KEY_INF, kmin);
+                if (lane == 0) {
+                    hdr[warp].key = kmin;
+                    hdr[warp].row = warp * 32 + ll;
+                }
+                __syncthreads();
+                const int ww = warp_argmin_key((lane < W) ? hdr[lane].key : KEY_INF, kmin);
+                if (kmin == KEY_INF) break;                       // s >= 0 everywhere: phase 1 finished
+                if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const int r = hdr[ww].row;
+                double* pr = prow + buf * PD;
+                const bool own = (tid == r);
+                if (warp == (r >> 5)) {
+                    // owner publishes its raw row; its warp runs the ratio test along the true row lam_r * T_r:
+                    // min ghat_j / (-e_j) over e_j < -tol
+                    if (own) publish(pr);
+                    __syncwarp();
+                    const double lam_r = __shfl_sync(FULL, lam, r & 31);
+                    const double il_r = __shfl_sync(FULL, ilam, r & 31);
+                    double bn = 0.0, bd = 0.0;   // best numerator / denominator (bd == 0: none)
+                    int bq = 0;
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        const double e = (j < n) ? -lam_r * pr[j] : 0.0;
+                        if (colvar[cs] >= 0 && e > kTolPivot) {
+                            const double num = fmax(vec[cs], 0.0);
+                            if (bd == 0.0 || num * bd < bn * e) { bn = num; bd = e; bq = cs; }
+                        }
+                    }
+                    const double ratio = bn * fast_rcp(bd > 0.0 ? bd : 1.0);
+                    const int kl = warp_argmin_key((bd > 0.0) ? dkey(ratio) : KEY_INF, kmin);
+                    const int kq = __shfl_sync(FULL, bq, kl);
+                    const int var_r = __shfl_sync(FULL, rowvar, r & 31);
+                    if (lane == 0) {
+                        const int k = kl + 32 * kq;
+                        const bool none = (kmin == KEY_INF);
+                        const double p = none ? 1.0 : pr[k];
+                        pub[0].p = p;
+                        pub[0].il = il_r;
+                        pub[0].k = none ? -1 : k;
+                        pub[0].var = var_r;
+                    }
+                }
+                __syncthreads();
+                const int k = pub[0].k;
+                if (k < 0) { status = ST_INFEASIBLE; break; }
+                const int kl = k & 31, kq = k >> 5;
+                const double p = pub[0].p, il = pub[0].il;
+                const double rp = fast_rcp(p);
+                const int var_r = pub[0].var;
+                const double e = reg_get<NC>(T, k);
+                const double f = own ? 0.0 : e * rp;
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? il : -f * il);
+                if (own) { lam = rp; ilam = p; }
+                // pricing vectors and the column bookkeeping
+                const double vk = __shfl_sync(FULL, slot_get_d(vec, kq), kl);
+                const double gk = __shfl_sync(FULL, slot_get_d(gv, kq), kl);
+                const int cv = __shfl_sync(FULL, slot_get_i(colvar, kq), kl);
+                const double fv = vk * rp, fg = gk * rp;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    const double plv = (j < n) ? pr[j] : 0.0;
+                    vec[cs] = fma(-fv, plv, vec[cs]);
+                    gv[cs] = fma(-fg, plv, gv[cs]);
+                    if (lane == kl && kq == cs) {
+                        vec[cs] = -fv * il;
+                        gv[cs] = -fg * il;
+                        colvar[cs] = var_r;
+                    }
+                }
+                if (own) rowvar = cv;
+                buf ^= 1;
+                ++npiv_p1;
+            }
+            __syncthreads();
+
+            // ---- stage 3b: phase 2 ----------------------------------------------------------------------------
+            while (status == ST_OPTIMAL) {
+                // entering column: most negative g (identical decision in every warp)
+                double gmin = kInf;
+                int bq = 0;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs)
+                    if (colvar[cs] >= 0 && gv[cs] < gmin) { gmin = gv[cs]; bq = cs; }
+                unsigned long long kmin;
+                const int kl = warp_argmin_key(dkey(gmin), kmin);
+                if (kmin >= dkey(-kTolFeas)) break;                // optimal
+                const int kq = __shfl_sync(FULL, bq, kl);
+                const int k = kl + 32 * kq;
+                // ratio test: one row per lane
+                const double e = reg_get<NC>(T, k);
+                const double et = lam * e;                         // true entry / right-hand side of my row
+                const double sc = fmax(lam * T[RHS], 0.0);
+                const bool cand = live && et > kTolPivot;
+                const double ratio = sc * fast_rcp(cand ? et : 1.0);
+                const int ll = warp_argmin_key(cand ? dkey(ratio) : KEY_INF, kmin);
+                if (lane == 0) {
+                    hdr[warp].key = kmin;
+                    hdr[warp].row = warp * 32 + ll;
+                }
+                __syncthreads();
+                const int ww = warp_argmin_key((lane < W) ? hdr[lane].key : KEY_INF, kmin);
+                if (kmin == KEY_INF) { status = ST_UNBOUNDED; break; }
+                if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const int r = hdr[ww].row;
+                double* pr = prow + buf * PD;
+                const bool own = (tid == r);
+                if (own) {
+                    publish(pr);
+                    pub[0].p = e;
+                    pub[0].il = ilam;
+                    pub[0].var = rowvar;
+                }
+                __syncthreads();
+                const double p = pub[0].p, il = pub[0].il;
+                const double rp = fast_rcp(p);
+                const double f = own ? 0.0 : e * rp;
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? il : -f * il);
+                if (own) { lam = rp; ilam = p; }
+                const double gk = __shfl_sync(FULL, slot_get_d(gv, kq), kl);
+                const int cv = __shfl_sync(FULL, slot_get_i(colvar, kq), kl);
+                const double fg = gk * rp;
+                const int var_r = pub[0].var;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    const double plv = (j < n) ? pr[j] : 0.0;
+                    gv[cs] = fma(-fg, plv, gv[cs]);
+                    if (lane == kl && kq == cs) {
+                        gv[cs] = -fg * il;
+                        colvar[cs] = var_r;
+                    }
+                }
+                if (own) rowvar = cv;
+                buf ^= 1;
+                ++npiv_p2;
+            }
+        }
+
+        // ---- stage 4: x, objective, slacks, labels -----------------------------------------------------------------
+        __syncthreads();
+        uint8_t* lab = a.labels + (size_t)lp * m;
+        int nact = 0, nties = 0, nviol = 0;
+        if (need_generic) {
+            status = -1;   // re-solved by the generic kernel (capi.cu)
+        } else if (status == ST_OPTIMAL) {
+            // where does every constraint sit now?
+            if (tid < nN) {
+                sval[tid] = lam * T[RHS];
+                if (rowvar >= 0) basic_tile[rowvar] = tid;
+            }
+            __syncthreads();
+            for (int j = tid; j < n; j += NT) {
+                const int bt = basic_tile[colvar0[j]];
+                sig[j] = (bt >= 0) ? sval[bt] : 0.0;
+            }
+            __syncthreads();
+            {
+                double sl[CS];
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    sl[cs] = (j < n) ? sig[j] : 0.0;
+                }
+                for (int k = warp; k < n; k += W) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        if (j < n) acc = fma(Dsm[(size_t)k * PD + j], sl[cs], acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0) xbuf[k] = Dsm[(size_t)k * PD + RHS] - acc;
+                }
+            }
+            __syncthreads();
+            double xl[CS];
+#pragma unroll
+            for (int cs = 0; cs < CS; ++cs) {
+                const int j = lane + 32 * cs;
+                xl[cs] = (j < n) ? xbuf[j] : 0.0;
+            }
+            if (warp == 0) {
+                double acc = 0.0;
+#pragma unroll
+                for (int cs = 0; cs < CS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0 && a.obj) a.obj[lp] = acc;
+            }
+            if (a.x)
+                for (int j = tid; j < n; j += NT) a.x[(size_t)lp * n + j] = xbuf[j];
+            row_dots(Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x
+            __syncthreads();
+            for (int i = tid; i < m; i += NT) {
+                const double slack = __ldg(bg + i) - gbuf[i];
+                const double as = fabs(slack);
+                const int active = as <= a.thr;
+                lab[i] = (uint8_t)active;
+                nact += active;
+                int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
+                const bool excl = mask && mask[i] == 0;
+                if (!excl) tie |= (active != (basic_tile[i] < 0));
+                nties += tie;
+                nviol += (slack < -a.thr * 10.0);
+            }
+        }
+        if (!need_generic && status != ST_OPTIMAL) {
+            for (int i = tid; i < m; i += NT) lab[i] = 0;
+            if (a.x)
+                for (int j = tid; j < n; j += NT) a.x[(size_t)lp * n + j] = 0.0;
+            if (tid == 0 && a.obj) a.obj[lp] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        nact = __reduce_add_sync(FULL, nact);
+        nties = __reduce_add_sync(FULL, nties);
+        nviol = __reduce_add_sync(FULL, nviol);
+        __syncthreads();
+        if (lane == 0) {
+            red[warp * 3 + 0] = nact;
+            red[warp * 3 + 1] = nties;
+            red[warp * 3 + 2] = nviol;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t0 = 0, t1 = 0, t2 = 0;
+            for (int w = 0; w < W; ++w) {
+                t0 += red[w * 3 + 0];
+                t1 += red[w * 3 + 1];
+                t2 += red[w * 3 + 2];
+            }
+            a.status[lp] = status;
+            if (status == -1) atomicAdd(a.flag_count, 1);
+            if (status != -1) {
+                if (a.n_active) a.n_active[lp] = t0;
+                if (a.ties) a.ties[lp] = t1;
+                if (a.violations) a.violations[lp] = t2;
+                if (a.pivots) {
+                    int* pv = a.pivots + (size_t)lp * 4;
+                    pv[0] = npiv_crash;
+                    pv[1] = npiv_p1;
+                    pv[2] = npiv_p2;
+                    pv[3] = npiv_crash + npiv_p1 + npiv_p2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct RowVariant {
+    int NC, W, MINB;
+    cudaError_t (*launch)(const SolveArgs&, int, cudaStream_t);
+};
+
+template <int NC, int W, int MINB>
+cudaError_t launch_row_variant(const SolveArgs& a, int sm_count, cudaStream_t st) {
+    auto kern = simplex_rowreg_kernel<NC, W, MINB>;
+    const size_t smem = make_row_layout(a.m, a.n, NC, W).total;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    kern<<<(int)grid, W * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+// (columns incl. rhs, warps, min CTAs/SM).  Picked: smallest NC >= n + 1, then smallest W with 32 W >= max(n, m - n).
+const RowVariant kRowVariants[] = {
+    {8, 1, 32, launch_row_variant<8, 1, 32>},
+    {24, 1, 16, launch_row_variant<24, 1, 16>},
+    {24, 2, 8, launch_row_variant<24, 2, 8>},
+    {48, 2, 5, launch_row_variant<48, 2, 5>},
+    {48, 4, 3, launch_row_variant<48, 4, 3>},
+    {72, 4, 2, launch_row_variant<72, 4, 2>},
+    {101, 4, 2, launch_row_variant<101, 4, 2>},
+    {101, 8, 1, launch_row_variant<101, 8, 1>},
+};
+
+const RowVariant* pick_row_variant(int m, int n) {
+    const int rows = (m - n > n) ? (m - n) : n;
+    for (const RowVariant& v : kRowVariants)
+        if (n + 1 <= v.NC && rows <= 32 * v.W) return &v;
+    return nullptr;
+}
+}  // namespace
+
+bool rowreg_supported(int m, int n) { return m >= n && pick_row_variant(m, n) != nullptr; }
+
+cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st) {
+    const RowVariant* v = pick_row_variant(a.m, a.n);
+    if (!v) return cudaErrorInvalidValue;
+    return v->launch(a, sm_count, st);
+}
+
+}  // namespace ddb
