@@ -2,12 +2,19 @@
 the line table of the same cubin (nvdisasm -g -c).  Usage: ncu_by_line.py sass.csv kernel.dis [top]"""
 import csv, re, sys, collections
 sass_csv, dis, top = sys.argv[1], sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 40
-addr2line = {}; cur = None
+outer = len(sys.argv) > 4 and sys.argv[4] == 'outer'   # attribute to the outermost call site (needs nvdisasm -gi)
+addr2line = {}; cur = None; fresh = True
 for l in open(dis):
-    m = re.search(r'//## File ".*?([^/"]+)", line (\d+)', l)
-    if m: cur = '%s:%s' % (m.group(1), m.group(2)); continue
+    m = re.search(r'//## File ".*?([^/"]+)", line (\d+)(?: inlined at ".*?([^/"]+)", line (\d+))?', l)
+    if m:
+        inner = '%s:%s' % (m.group(1), m.group(2))
+        outr = '%s:%s' % (m.group(3), m.group(4)) if m.group(3) else inner
+        if outer: cur = outr
+        elif fresh: cur = inner
+        fresh = False
+        continue
     m = re.match(r'\s+/\*([0-9a-f]{4,})\*/', l)
-    if m: addr2line[int(m.group(1), 16)] = cur
+    if m: addr2line[int(m.group(1), 16)] = cur; fresh = True
 rows = list(csv.reader(open(sass_csv)))
 hi = [i for i, r in enumerate(rows) if r and r[0] == 'Address'][0]
 hdr = rows[hi]; ci = {n: i for i, n in enumerate(hdr)}
