@@ -37,6 +37,15 @@ def _peaks():
     return 6650.0, 'fallback (B200_PROFILING.md)'
 
 
+def _measured_traffic():
+    """DRAM bytes per LP of the simplex kernel from the committed ncu --set full capture (profiles/), or None."""
+    path = os.path.join(ROOT, 'profiles', 'ncu_traffic.json')
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
+
+
 def _onchip_peaks():
     path = os.path.join(ROOT, 'profiles', 'onchip_peaks.json')
     if os.path.exists(path):
@@ -291,12 +300,19 @@ def run_ours(args):
     hbm_peak, peak_src = _peaks()
     alg_bytes_per_lp = 8 * (M * N_VARS + M + N_VARS) + M + 8 * N_VARS + 8 + 4 + 16 + 4      # SURVEY 8(d), materialised instance
     achieved = alg_bytes_per_lp * B / kern_s / 1e9
+    tr = _measured_traffic()
+    traffic = tr['dram_bytes_per_lp'] * B if tr and tr.get('m') == M and tr.get('n') == N_VARS else None
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak,
-                'traffic': None, 'peak_source': peak_src, 'kernel': 'simplex (plan %d)' % ctx.solve_plan(M, N_VARS),
+                'traffic': traffic, 'traffic_source': (tr or {}).get('source'),
+                'peak_source': peak_src, 'kernel': 'simplex (plan %d)' % ctx.solve_plan(M, N_VARS),
                 'algorithmic_bytes_per_lp': alg_bytes_per_lp,
                 'note': 'tableau is on-chip for this shape: the binding rooflines are fp64 FMA issue / shared-memory bandwidth, see roofline_onchip'}
-    # on-chip work actually done: crash pivot t updates (m-1) rows, phase-1/2 pivots (m-n-1) rows of n+1 entries
-    flop = 2.0 * (N_VARS + 1) * (piv[:, 0] * (M - 1) + (piv[:, 1] + piv[:, 2]) * (M - N_VARS - 1))
+    # on-chip work of the algorithm: a crash pivot updates the n rows of the inverse, the
+    # remaining m-n rows enter through an (m-n) x n x (n+1) product, a phase-1/2 pivot updates m-n rows; n+1 entries
+    # per row, 2 flop per entry
+    did_gemm = (piv[:, 0] == N_VARS).astype(np.float64)
+    flop = 2.0 * (N_VARS + 1) * (piv[:, 0] * N_VARS + did_gemm * (M - N_VARS) * N_VARS
+                                 + (piv[:, 1] + piv[:, 2]) * (M - N_VARS))
     onchip = {'fp64_flop_per_launch': float(flop.sum()), 'achieved_tflops': float(flop.sum()) / kern_s / 1e12,
               'tableau_bytes_per_launch': float(flop.sum()) * 8.0, 'achieved_tableau_tbs': float(flop.sum()) * 8.0 / kern_s / 1e12,
               'mean_pivots': {'crash': float(piv[:, 0].mean()), 'phase1': float(piv[:, 1].mean()), 'phase2': float(piv[:, 2].mean())}}
@@ -313,11 +329,15 @@ def run_ours(args):
     match = None
     if world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
-        count = args.cpu_sample if args.cpu_sample else max(cores * 16, 128)
-        sA, sb, sc_ = A[:count].cpu().numpy(), b[:count].cpu().numpy(), c[:count].cpu().numpy()
         pool = mp.get_context('fork').Pool(cores)
         try:
-            cpu_solve_timed(sA[: cores * 2], sb[: cores * 2], sc_[: cores * 2], pool, cores)
+            # pilot (also pays the pool start-up and imports), then a sample sized for ~12 s of CPU wall time
+            pilot = max(cores * 4, 32)
+            pA, pb, pc = A[:pilot].cpu().numpy(), b[:pilot].cpu().numpy(), c[:pilot].cpu().numpy()
+            cpu_solve_timed(pA, pb, pc, pool, cores)
+            dt0, _ = cpu_solve_timed(pA, pb, pc, pool, cores)
+            count = args.cpu_sample if args.cpu_sample else int(min(B, max(cores * 16, 12.0 * pilot / dt0)))
+            sA, sb, sc_ = A[:count].cpu().numpy(), b[:count].cpu().numpy(), c[:count].cpu().numpy()
             dt, flat = cpu_solve_timed(sA, sb, sc_, pool, cores)
         finally:
             pool.close(); pool.join()

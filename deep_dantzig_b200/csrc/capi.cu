@@ -16,6 +16,8 @@ cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, i
 bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
+bool tile2d_supported(int m, int n);
+cudaError_t launch_simplex_tile2d(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowreg_supported(int m, int n);
 cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
 struct S2vArgs {
@@ -165,7 +167,7 @@ extern "C" int ddb_device_info(ddb_ctx* ctx, int* sm_count, int* cc_major, int* 
 extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static int auto_plan(const ddb_ctx* ctx, int m, int n) {
-    if (ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
+    if (ddb::tile2d_supported(m, n) || ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
     if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
     return 2;
 }
@@ -175,16 +177,20 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
     if (m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_plan: m=%d n=%d", m, n);
     if (n > 512) return fail(DDB_EUNSUPPORTED, "ddb_solve_plan: n=%d > 512 is not supported yet", n);
     int plan = ctx->forced_plan >= 0 ? ctx->forced_plan : auto_plan(ctx, m, n);
-    if (plan == 0 && !ddb::rowreg_supported(m, n) && !ddb::regtile_supported(m, n))
+    if (plan == 0 && !ddb::tile2d_supported(m, n) && !ddb::rowreg_supported(m, n) && !ddb::regtile_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "register-tiled kernel does not cover m=%d n=%d", m, n);
     if (plan == 1 && (int64_t)ddb::generic_smem_bytes(m, n, true) > ctx->smem_optin)
         return fail(DDB_EUNSUPPORTED, "shared-memory tableau does not fit for m=%d n=%d", m, n);
+    if (plan == 3 && !ddb::tile2d_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "2-D register-tile kernel does not cover m=%d n=%d", m, n);
+    if (plan == 4 && !ddb::regtile_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "warp-tiled register kernel does not cover m=%d n=%d", m, n);
     return plan;
 }
 
 extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
     if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
-    if (plan < -1 || plan > 2) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
+    if (plan < -1 || plan > 4) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
     ctx->forced_plan = plan;
     return DDB_OK;
 }
@@ -268,11 +274,13 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
     a.only_flagged = 0;
     CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
 
-    if (plan == 0) {
-        // plan 0 has two register-resident kernels: row-per-thread (preferred) and warp-tiled (wider shapes)
-        static const bool force_tiled = [] { const char* e = getenv("DDB_PLAN0_TILED"); return e && e[0] == '1'; }();
-        const bool use_row = ddb::rowreg_supported(m, n) && !(force_tiled && ddb::regtile_supported(m, n));
-        const size_t need = use_row ? 0 : ddb::regtile_scratch_bytes(m, n, ctx->sm_count);
+    if (plan == 0 || plan == 3 || plan == 4) {
+        // Register-resident kernels: row-per-thread (plan 0 default), 2-D tile (plan 3), warp-tiled (plan 4, and the
+        // fallback of plan 0 for shapes the row kernel does not cover).
+        int which = ddb::rowreg_supported(m, n) ? 1 : (ddb::tile2d_supported(m, n) ? 0 : 2);
+        if (plan == 3) which = 0;
+        if (plan == 4) which = 2;
+        const size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count) : 0;
         if (need) {
             if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
             if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
@@ -280,7 +288,9 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
             if (rc) return rc;
             a.gtab = (double*)ctx->scratch.p;
         }
-        if (use_row)
+        if (which == 0)
+            CUDA_TRY(ddb::launch_simplex_tile2d(a, ctx->sm_count, st));
+        else if (which == 1)
             CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
         else
             CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));

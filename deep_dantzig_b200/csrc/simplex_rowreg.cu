@@ -7,24 +7,27 @@
 //   * everything that is "per row" (the right-hand side, the entry in the entering column, the ratio test, the
 //     most-negative-slack search of phase 1) is one value PER LANE, so a ratio test over 32 rows is a handful of
 //     instructions followed by a redux-based warp argmin -- not a loop;
-//   * everything that is "per column" (pricing vectors ghat / g, the column -> constraint map) is kept
-//     lane-distributed (column j in lane j%32, slot j/32) and replicated in every warp, so pricing is also a
-//     handful of instructions + one warp argmin, identical in every warp, with no communication.
-// The only dynamically indexed register accesses are "my entry in the entering column k" (read) and "the new
-// column k" (write): warp-uniform branch trees (reg_get / reg_set below).
+//   * everything that is "per column" (pricing vectors ghat / g, the column -> constraint map) lives in shared
+//     memory, one copy per CTA, and is maintained by the warp that owns the pivot row: while it holds the
+//     published row it updates the cost vectors lane-distributed (column j in lane j%32) and prices the NEXT
+//     entering column, so the other warps never touch a cost vector.
+// The only dynamically indexed register accesses are reading "my entry in the entering column k" and writing the
+// new column k: warp-uniform branch trees (reg_get / reg_set below).
 //
-// One barrier per pivot: before the barrier EVERY warp speculatively publishes its own best candidate row and
-// prices the cost vector that would result if that candidate won (per-warp copies of g in shared memory); after
-// the barrier all warps pick the same winner from W small headers and go straight into the rank-1 update.
+// Rows are stored lazily normalised (true row = lam * stored row), so a pivot never rescales the pivot row: its
+// owner publishes its raw registers and every other thread runs one FMA per entry.
 //
-// At (m,n) = (200,100): NC = 101 registers-pairs per thread, 4 warps per LP, 2 LPs resident per SM (the register
-// file is the limit: 2 x 128 x 255 registers), 404 warp-DFMAs per pivot = 202 clk of one SM's fp64 pipe.
+// At (m,n) = (200,100): NC = 101 register pairs per thread, 4 warps per LP, 2 LPs resident per SM (the register
+// file is the limit: 2 x 128 x 255 registers).  Measured bound of the update (tools/rank1_bench.cu): a broadcast
+// operand from shared memory costs 4 clk per warp-double of load/store write-back, the fp64 FMA only ~1.6 clk, so
+// this layout is operand-delivery-bound (814 clk per pivot per warp with two LPs per SM); simplex_tile2d.cu is
+// the 2-D register-tile variant that removes that bound (R + C operands per R * C FMAs).
 //
 // Stages per LP (same algorithm and tolerances as simplex_generic.cu):
 //   0. crash order by cosine score (A streamed once from HBM through the idle tableau registers)
-//   1. crash as an explicit inverse: Gauss-Jordan on the n x n block A_B0 (thread t owns row t)
+//   1. crash as an explicit inverse: Gauss-Jordan on the n x n block A_B0 (thread t owns row t), 1 barrier/pivot
 //   2. remaining rows enter through  P_N = -A_N D  (D rows broadcast from shared memory)
-//   3. phase 1 (most negative slack leaves, ratio test along the published row), phase 2 (Dantzig)
+//   3. phase 1 (most negative slack leaves, ratio test along the published row), phase 2 (Dantzig), 2 barriers/pivot
 //   4. x = xv - D sigma, slack = b - A x from the caller's A, labels = |slack| <= threshold
 // Instances the tile cannot hold or whose static crash basis is singular are flagged status = -1 and re-solved by
 // the generic kernel on the device (capi.cu); nothing ever falls back to the CPU.
@@ -35,21 +38,7 @@
 
 namespace ddb {
 
-// Optional per-section cycle accounting of the phase-2 loop (debug builds only: -DDDB_TIMING; results in a.gtab).
-#ifdef DDB_TIMING
-#define TSTAMP(i)                                   \
-    do {                                            \
-        const long long _t = clock64();             \
-        tacc[i] += _t - tlast;                      \
-        tlast = _t;                                 \
-    } while (0)
-#else
-#define TSTAMP(i) do { } while (0)
-#endif
-
-// ---- dynamic (warp-uniform) register index -> uniform branch tree ----------------------------------------------
-// The asm volatile leaves keep the compiler from if-converting the switch into a select per register (3
-// instructions per tableau column) and from copying registers around at the merge points.
+// ---- dynamic (warp-uniform) register index -> jump table -------------------------------------------------------
 #define DDB_R8(M, b) M(b + 0) M(b + 1) M(b + 2) M(b + 3) M(b + 4) M(b + 5) M(b + 6) M(b + 7)
 #define DDB_R128(M)                                                                                       \
     DDB_R8(M, 0) DDB_R8(M, 8) DDB_R8(M, 16) DDB_R8(M, 24) DDB_R8(M, 32) DDB_R8(M, 40) DDB_R8(M, 48)       \
@@ -58,12 +47,12 @@ namespace ddb {
 
 template <int NC>
 __device__ __forceinline__ double reg_get(const double (&T)[NC], int k) {
-    static_assert(NC <= 128, "the switch covers 128 registers");
+    static_assert(NC <= 128, "jump table covers 128 registers");
     double v = 0.0;
     switch (k) {
-#define DDB_CASE(I)                                                                         \
-    case (I):                                                                               \
-        if constexpr ((I) < NC) asm volatile("mov.f64 %0, %1;" : "=d"(v) : "d"(T[(I) < NC ? (I) : 0])); \
+#define DDB_CASE(I)                                    \
+    case (I):                                          \
+        if constexpr ((I) < NC) v = T[(I) < NC ? (I) : 0]; \
         break;
         DDB_R128(DDB_CASE)
 #undef DDB_CASE
@@ -71,6 +60,8 @@ __device__ __forceinline__ double reg_get(const double (&T)[NC], int k) {
     }
     return v;
 }
+// Write at a warp-uniform dynamic index.  The asm volatile leaves keep the compiler from if-converting the switch
+// into a select per register (which costs 3 instructions per tableau column); what remains is a uniform branch tree.
 template <int NC>
 __device__ __forceinline__ void reg_set(double (&T)[NC], int k, double v) {
     switch (k) {
@@ -84,12 +75,16 @@ __device__ __forceinline__ void reg_set(double (&T)[NC], int k, double v) {
     }
 }
 
-struct RowCand {              // one per (buffer, warp): that warp's candidate pivot row
+struct RowPub {               // what the pivot row's owner (warp) publishes beside the row itself
     double p;                 // pivot entry (stored scale)
-    double il;                // 1 / lam of the candidate row
-    int row;                  // tile row (= thread index)
-    int k;                    // crash / phase 1: entering column (-1: none); phase 2: NEXT entering column (-1: optimal)
-    int var;                  // constraint whose slack is basic in the candidate row
+    double il;                // 1 / lam of the pivot row before the pivot
+    int k;                    // entering column (-1: none -> infeasible / singular crash basis)
+    int var;                  // constraint whose slack was basic in the pivot row
+};
+
+struct RowHdr {               // one per warp: its candidate row
+    unsigned long long key;   // dkey(slack) in phase 1, dkey(ratio) in phase 2, KEY_INF = no candidate
+    int row;                  // candidate tile row (= thread index)
     int pad;
 };
 
@@ -102,13 +97,7 @@ __host__ __device__ constexpr int row_pitch(int NC) {
 }
 
 struct RowLayout {
-    // persistent per LP
-    size_t D, order, colvar0, pivcol, basic_tile, cvsm;
-    // pivot loops (crash, phase 1, phase 2) -- aliased with the stage 0 / stage 4 scratch below
-    size_t prow, cand, keys, gbufs, ghbufs;
-    // stage 0 / stage 4 scratch
-    size_t gbuf, gnn, sval, sig, xbuf, red;
-    size_t total;
+    size_t D, prow, pub, hdr, gsm, ghsm, cvsm, order, colvar0, pivcol, basic_tile, sval, sig, xbuf, gbuf, gnn, red, total;
 };
 __host__ __device__ inline size_t rr_align(size_t v) { return (v + 15) / 16 * 16; }
 __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W) {
@@ -117,58 +106,53 @@ __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W
     const int CT = 32 * ((NC + 31) / 32);
     size_t off = 0;
     L.D = off;          off += rr_align((size_t)n * PD * 8);
+    L.prow = off;       off += rr_align((size_t)2 * PD * 8);
+    L.pub = off;        off += rr_align((size_t)2 * sizeof(RowPub));
+    L.hdr = off;        off += rr_align((size_t)W * sizeof(RowHdr));
+    L.gsm = off;        off += rr_align((size_t)CT * 8);
+    L.ghsm = off;       off += rr_align((size_t)CT * 8);
+    L.cvsm = off;       off += rr_align((size_t)CT * 4);
     L.order = off;      off += rr_align((size_t)m * 4);
     L.colvar0 = off;    off += rr_align((size_t)n * 4);
     L.pivcol = off;     off += rr_align((size_t)n * 4);
     L.basic_tile = off; off += rr_align((size_t)m * 4);
-    L.cvsm = off;       off += rr_align((size_t)CT * 4);
-    const size_t u0 = off;
-    L.prow = off;       off += rr_align((size_t)2 * W * PD * 8);
-    L.cand = off;       off += rr_align((size_t)2 * W * sizeof(RowCand));
-    L.keys = off;       off += rr_align((size_t)2 * W * 8);
-    L.gbufs = off;      off += rr_align((size_t)2 * W * CT * 8);
-    L.ghbufs = off;     off += rr_align((size_t)2 * W * CT * 8);
-    const size_t u1 = off;
-    off = u0;
-    L.gbuf = off;       off += rr_align((size_t)m * 8);
-    L.gnn = off;        off += rr_align((size_t)m * 8);
     L.sval = off;       off += rr_align((size_t)W * 32 * 8);
     L.sig = off;        off += rr_align((size_t)n * 8);
     L.xbuf = off;       off += rr_align((size_t)(n > CT ? n : CT) * 8);
+    L.gbuf = off;       off += rr_align((size_t)m * 8);
+    L.gnn = off;        off += rr_align((size_t)m * 8);
     L.red = off;        off += rr_align((size_t)(3 * W + 4) * 4);
-    L.total = off > u1 ? off : u1;
+    L.total = off;
     return L;
 }
 
 template <int NC, int W, int MINB>
 __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs a) {
     constexpr int CS = (NC + 31) / 32;      // slots of the lane-distributed column vectors
-    constexpr int CT = 32 * CS;
     constexpr int PD = row_pitch(NC);
     constexpr int NT = W * 32;              // threads = tile rows
     constexpr int RHS = NC - 1;             // register / column that holds the right-hand side
     constexpr int RB = NC / CS;             // rows per register batch when T is used as a streaming buffer
-    constexpr int NCH = (NC + 7) / 8;       // 8-column chunks of a row
     static_assert(W <= 32, "one header per lane");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = a.m, n = a.n;
     const RowLayout L = make_row_layout(m, n, NC, W);
     double* Dsm = reinterpret_cast<double*>(smem_raw + L.D);
+    double* prow = reinterpret_cast<double*>(smem_raw + L.prow);
+    RowPub* pub = reinterpret_cast<RowPub*>(smem_raw + L.pub);
+    RowHdr* hdr = reinterpret_cast<RowHdr*>(smem_raw + L.hdr);
+    double* gsm = reinterpret_cast<double*>(smem_raw + L.gsm);     // g: true reduced costs, one copy per CTA
+    double* ghsm = reinterpret_cast<double*>(smem_raw + L.ghsm);   // ghat: artificial costs of phase 1
+    int* cvsm = reinterpret_cast<int*>(smem_raw + L.cvsm);         // column -> constraint whose slack is nonbasic
     int* order = reinterpret_cast<int*>(smem_raw + L.order);
     int* colvar0 = reinterpret_cast<int*>(smem_raw + L.colvar0);
     int* pivcol = reinterpret_cast<int*>(smem_raw + L.pivcol);
     int* basic_tile = reinterpret_cast<int*>(smem_raw + L.basic_tile);
-    int* cvsm = reinterpret_cast<int*>(smem_raw + L.cvsm);          // column -> constraint whose slack is nonbasic
-    double* prow = reinterpret_cast<double*>(smem_raw + L.prow);    // [2][W][PD] candidate pivot rows
-    RowCand* cand = reinterpret_cast<RowCand*>(smem_raw + L.cand);  // [2][W]
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(smem_raw + L.keys);   // [2][W]
-    double* gbufs = reinterpret_cast<double*>(smem_raw + L.gbufs);    // [2][W][CT] g (true reduced costs) candidates
-    double* ghbufs = reinterpret_cast<double*>(smem_raw + L.ghbufs);  // [2][W][CT] ghat (phase-1 costs) candidates
-    double* gbuf = reinterpret_cast<double*>(smem_raw + L.gbuf);
-    double* gnn = reinterpret_cast<double*>(smem_raw + L.gnn);
     double* sval = reinterpret_cast<double*>(smem_raw + L.sval);
     double* sig = reinterpret_cast<double*>(smem_raw + L.sig);
     double* xbuf = reinterpret_cast<double*>(smem_raw + L.xbuf);
+    double* gbuf = reinterpret_cast<double*>(smem_raw + L.gbuf);
+    double* gnn = reinterpret_cast<double*>(smem_raw + L.gnn);
     int* red = reinterpret_cast<int*>(smem_raw + L.red);
     __shared__ long long cur_lp;
 
@@ -186,8 +170,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
     //     row r       :  T_r unchanged except T_r[k] = il;  lam_r = rp, ilam_r = p
     //     costs       :  g[c] -= g_k rp T_r[c] (c != k);  g[k] = -g_k rp il
     // so the owner just publishes its raw registers and every other thread runs one FMA per entry.
-
-    // plain rank-1 update of my row from a row in shared memory (broadcast reads):  T[c] -= f * pr[c]
+    // rank-1 update of my row from the raw pivot row in shared memory (broadcast reads):  T[c] -= f * prow[c]
     auto rank1 = [&](const double* pr, double f) {
         const double nf = -f;
         const double2* p2 = reinterpret_cast<const double2*>(pr);
@@ -199,35 +182,11 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         }
         if constexpr (NC & 1) T[NC - 1] = fma(nf, pr[NC - 1], T[NC - 1]);
     };
-    // rank-1 update, then write column kset (T[kset] = newval) and read the updated column kget (warp-uniform
-    // indices, -1 = none): two uniform branch trees around the pure-FMA loop.
-    auto rank1_fused = [&](const double* pr, double f, int kset, double newval, int kget, double& eget) {
-        rank1(pr, f);
-        if (kset >= 0) reg_set<NC>(T, kset, newval);
-        if (kget >= 0) eget = reg_get<NC>(T, kget);
-    };
-    auto get_col = [&](int k) -> double { return reg_get<NC>(T, k); };
     auto publish = [&](double* pr) {
         double2* p2 = reinterpret_cast<double2*>(pr);
 #pragma unroll
         for (int c2 = 0; c2 < NC / 2; ++c2) p2[c2] = make_double2(T[2 * c2], T[2 * c2 + 1]);
         if constexpr (NC & 1) pr[NC - 1] = T[NC - 1];
-    };
-    // winner among the W candidate keys of buffer nb (lowest warp on ties); kmin = its key
-    auto pick_winner = [&](int nb, unsigned long long& kmin) -> int {
-        if constexpr (W <= 4) {
-            const unsigned long long* kk = keys + nb * W;
-            int ww = 0;
-            kmin = kk[0];
-#pragma unroll
-            for (int w = 1; w < W; ++w) {
-                const unsigned long long kw = kk[w];
-                if (kw < kmin) { kmin = kw; ww = w; }
-            }
-            return ww;
-        } else {
-            return warp_argmin_key((lane < W) ? keys[nb * W + lane] : KEY_INF, kmin);
-        }
     };
     // T used as a streaming buffer: dot products of up to RB*W rows of A (from `base`) with a lane-distributed
     // vector; all loads of a batch are in flight together.  out1[i] = a_i . v ; out2[i] = a_i . a_i (optional)
@@ -310,7 +269,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
 
         int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
         int status = ST_OPTIMAL;
-        int par = 0, gw = 0;     // the current cost vectors are gbufs / ghbufs [par][gw]
+        int buf = 0;
 
         if (!need_generic) {
             // ---- stage 1: thread t < n loads row order[t] of [A | b]; Gauss-Jordan to the inverse --------------
@@ -337,31 +296,31 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                 lam = 1.0;
                 ilam = 1.0;
             }
-            for (int j = tid; j < CT; j += NT) {
-                gbufs[j] = (j < n) ? __ldg(cg + j) : 0.0;       // [0][0]
-                cvsm[j] = (j < n) ? -1 : -2;                     // -1: still a free x_j (crash), -2: not a column
+            // column vectors live in shared memory (one copy per CTA, maintained by the pivot row's warp)
+            for (int j = tid; j < 32 * CS; j += NT) {
+                gsm[j] = (j < n) ? __ldg(cg + j) : 0.0;
+                ghsm[j] = (j < n) ? 1.0 : 0.0;
+                cvsm[j] = (j < n) ? -1 : -2;          // -1: still a free x_j (crash), -2: not a column
             }
             __syncthreads();
 
             for (int t = 0; t < n; ++t) {
-                const int nb = t & 1;
-                double* pr = prow + (size_t)(nb * W) * PD;
-                RowCand* cd = cand + nb * W;
+                double* pr = prow + buf * PD;
                 const bool own = (tid == t);
                 if (warp == (t >> 5)) {
                     // the owner publishes its raw row; its warp finds the pivot column (largest |entry| among the
                     // free columns; a row is a pivot row once in the crash, so its lam is still 1) and updates g
                     if (own) publish(pr);
                     __syncwarp();
-                    double rv[CS];
+                    double pl[CS];
                     unsigned long long best = 0ull;
                     int bq = 0;
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) {
                         const int j = lane + 32 * cs;
-                        rv[cs] = (j < n) ? pr[j] : 0.0;
+                        pl[cs] = (j < n) ? pr[j] : 0.0;
                         const unsigned long long kk =
-                            (cvsm[j] == -1) ? (unsigned long long)__double_as_longlong(fabs(rv[cs])) : 0ull;
+                            (cvsm[j] == -1) ? (unsigned long long)__double_as_longlong(fabs(pl[cs])) : 0ull;
                         if (kk > best) { best = kk; bq = cs; }
                     }
                     unsigned long long kmin;
@@ -369,31 +328,31 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                     const int k = kl + 32 * __shfl_sync(FULL, bq, kl);
                     const double pabs = __longlong_as_double((long long)~kmin);
                     const double p = pr[k];
-                    const double fg = gbufs[k] * fast_rcp(p);
+                    const double fg = gsm[k] * fast_rcp(p);
                     __syncwarp();
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) {
                         const int j = lane + 32 * cs;
-                        const double g = fma(-fg, rv[cs], gbufs[j]);
-                        gbufs[j] = (j == k) ? -fg : g;
+                        if (j < n) gsm[j] = (j == k) ? -fg : fma(-fg, pl[cs], gsm[j]);
                     }
                     if (lane == 0) {
-                        cd->p = p;
-                        cd->k = (pabs >= kTolCrash) ? k : -1;
+                        pub[buf].p = p;
+                        pub[buf].k = (pabs >= kTolCrash) ? k : -1;
                         pivcol[t] = k;
                         cvsm[k] = 0;                  // no longer free
                     }
                 }
                 __syncthreads();
-                const int k = cd->k;
+                const int k = pub[buf].k;
                 if (k < 0) { need_generic = true; break; }
-                const double p = cd->p;
+                const double p = pub[buf].p;
                 const double rp = fast_rcp(p);
-                const double e = get_col(k);
+                const double e = reg_get<NC>(T, k);
                 const double f = own ? 0.0 : e * rp;
-                double dummy;
-                rank1_fused(pr, f, k, own ? 1.0 : -f, -1, dummy);
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? 1.0 : -f);
                 if (own) { lam = rp; ilam = p; }
+                buf ^= 1;
                 ++npiv_crash;
             }
         }
@@ -409,7 +368,6 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                 colvar0[k] = rowvar;
                 cvsm[k] = rowvar;
             }
-            for (int j = tid; j < CT; j += NT) ghbufs[j] = (j < n) ? 1.0 : 0.0;     // [0][0]: artificial costs
             __syncthreads();
 
             // ---- stage 2: my row of P_N = -A_N D, s_N = b_N - A_N xv -------------------------------------------
@@ -442,199 +400,163 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             }
 
             // ---- stage 3a: phase 1 (most negative slack leaves; ratio test along its row) -------------------
-            // Every warp publishes its own most-negative row, runs the ratio test along it and writes the cost
-            // vectors that pivot would produce into its private candidate buffers; after the barrier the winner
-            // (most negative slack over all warps) is adopted by everybody.
             for (;;) {
-                const int nb = par ^ 1;
-                const double* gcur = gbufs + (size_t)(par * W + gw) * CT;
-                const double* ghcur = ghbufs + (size_t)(par * W + gw) * CT;
                 const double s = lam * T[RHS];
                 unsigned long long kmin;
                 const int ll = warp_argmin_key((live && s < -kTolFeas) ? dkey(s) : KEY_INF, kmin);
-                if (kmin != KEY_INF) {
-                    double* prw = prow + (size_t)(nb * W + warp) * PD;
-                    if (lane == ll) publish(prw);
+                if (lane == 0) {
+                    hdr[warp].key = kmin;
+                    hdr[warp].row = warp * 32 + ll;
+                }
+                __syncthreads();
+                const int ww = warp_argmin_key((lane < W) ? hdr[lane].key : KEY_INF, kmin);
+                if (kmin == KEY_INF) break;                       // s >= 0 everywhere: phase 1 finished
+                if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const int r = hdr[ww].row;
+                double* pr = prow + buf * PD;
+                const bool own = (tid == r);
+                if (warp == (r >> 5)) {
+                    // owner publishes its raw row; its warp runs the ratio test along the true row lam_r * T_r
+                    // (min ghat_j / (-e_j) over e_j < -tol) and updates ghat, g and the column map
+                    if (own) publish(pr);
                     __syncwarp();
-                    const double lam_r = __shfl_sync(FULL, lam, ll);
-                    const double il = __shfl_sync(FULL, ilam, ll);
-                    const int var_r = __shfl_sync(FULL, rowvar, ll);
-                    double rv[CS], gh[CS];
+                    const double lam_r = __shfl_sync(FULL, lam, r & 31);
+                    const double il = __shfl_sync(FULL, ilam, r & 31);
+                    const int var_r = __shfl_sync(FULL, rowvar, r & 31);
+                    double pl[CS], gh[CS];
                     double bn = 0.0, bd = 0.0;   // best numerator / denominator (bd == 0: none)
                     int bq = 0;
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) {
                         const int j = lane + 32 * cs;
-                        rv[cs] = (j < n) ? prw[j] : 0.0;
-                        gh[cs] = ghcur[j];
-                        const double e = -lam_r * rv[cs];       // true entry of the candidate row
-                        if (e > kTolPivot) {
+                        pl[cs] = (j < n) ? pr[j] : 0.0;
+                        gh[cs] = ghsm[j];
+                        const double e = -lam_r * pl[cs];
+                        if (j < n && e > kTolPivot) {
                             const double num = fmax(gh[cs], 0.0);
                             if (bd == 0.0 || num * bd < bn * e) { bn = num; bd = e; bq = cs; }
                         }
                     }
                     const double ratio = bn * fast_rcp(bd > 0.0 ? bd : 1.0);
-                    unsigned long long kmin2;
-                    const int kl = warp_argmin_key((bd > 0.0) ? dkey(ratio) : KEY_INF, kmin2);
-                    const bool none = (kmin2 == KEY_INF);
+                    const int kl = warp_argmin_key((bd > 0.0) ? dkey(ratio) : KEY_INF, kmin);
+                    const bool none = (kmin == KEY_INF);
                     const int k = none ? 0 : kl + 32 * __shfl_sync(FULL, bq, kl);
-                    const double p = none ? 1.0 : prw[k];
+                    const double p = none ? 1.0 : pr[k];
                     const double rp = fast_rcp(p);
-                    const double fv = ghcur[k] * rp, fg = gcur[k] * rp;
-                    double* gnext = gbufs + (size_t)(nb * W + warp) * CT;
-                    double* ghnext = ghbufs + (size_t)(nb * W + warp) * CT;
+                    const double fv = ghsm[k] * rp, fg = gsm[k] * rp;
+                    const int cv = cvsm[k];
+                    __syncwarp();
+                    if (!none) {
 #pragma unroll
-                    for (int cs = 0; cs < CS; ++cs) {
-                        const int j = lane + 32 * cs;
-                        const double h = fma(-fv, rv[cs], gh[cs]);
-                        const double g = fma(-fg, rv[cs], gcur[j]);
-                        ghnext[j] = (j == k) ? -fv * il : h;
-                        gnext[j] = (j == k) ? -fg * il : g;
+                        for (int cs = 0; cs < CS; ++cs) {
+                            const int j = lane + 32 * cs;
+                            if (j < n) {
+                                ghsm[j] = (j == k) ? -fv * il : fma(-fv, pl[cs], gh[cs]);
+                                gsm[j] = (j == k) ? -fg * il : fma(-fg, pl[cs], gsm[j]);
+                            }
+                        }
                     }
                     if (lane == 0) {
-                        RowCand* cd = cand + nb * W + warp;
-                        cd->p = p;
-                        cd->il = il;
-                        cd->row = warp * 32 + ll;
-                        cd->k = none ? -1 : k;
-                        cd->var = var_r;
+                        pub[0].p = p;
+                        pub[0].il = il;
+                        pub[0].k = none ? -1 : k;
+                        pub[0].var = cv;              // becomes basic in the pivot row
+                        if (!none) cvsm[k] = var_r;   // becomes nonbasic in column k
                     }
                 }
-                if (lane == 0) keys[nb * W + warp] = kmin;
                 __syncthreads();
-                const int ww = pick_winner(nb, kmin);
-                if (kmin == KEY_INF) break;                       // s >= 0 everywhere: phase 1 finished
-                if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
-                const RowCand* cd = cand + nb * W + ww;
-                const int k = cd->k;
+                const int k = pub[0].k;
                 if (k < 0) { status = ST_INFEASIBLE; break; }
-                const double p = cd->p, il = cd->il;
-                const bool own = (tid == cd->row);
+                const double p = pub[0].p, il = pub[0].il;
                 const double rp = fast_rcp(p);
-                const double e = get_col(k);
+                const double e = reg_get<NC>(T, k);
                 const double f = own ? 0.0 : e * rp;
-                double dummy;
-                rank1_fused(prow + (size_t)(nb * W + ww) * PD, f, k, own ? il : -f * il, -1, dummy);
-                if (own) {
-                    lam = rp;
-                    ilam = p;
-                    const int cv = cvsm[k];       // becomes basic in my row
-                    cvsm[k] = rowvar;             // my old slack becomes nonbasic in column k
-                    rowvar = cv;
-                }
-                par = nb;
-                gw = ww;
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? il : -f * il);
+                if (own) { lam = rp; ilam = p; rowvar = pub[0].var; }
+                buf ^= 1;
                 ++npiv_p1;
             }
             __syncthreads();
 
             // ---- stage 3b: phase 2 (Dantzig) ---------------------------------------------------------------
-            // Same scheme; a candidate also carries the NEXT entering column (priced on the cost vector its pivot
-            // would produce), and the rank-1 update extracts my entry in that column on the way.
+            // The pivot row's warp prices the NEXT entering column while it holds the row, so the other warps never
+            // touch the cost vector.  First column: every warp computes it (read-only).
             int k = -1;
-            double e = 0.0;
             if (status == ST_OPTIMAL) {
-                const double* gcur = gbufs + (size_t)(par * W + gw) * CT;
                 double gmin = kInf;
                 int bq = 0;
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) {
                     const int j = lane + 32 * cs;
-                    const double g = gcur[j];
+                    const double g = gsm[j];
                     if (j < n && g < gmin) { gmin = g; bq = cs; }
                 }
                 unsigned long long kmin;
                 const int kl = warp_argmin_key(dkey(gmin), kmin);
                 if (kmin < dkey(-kTolFeas)) k = kl + 32 * __shfl_sync(FULL, bq, kl);
-                if (k >= 0) e = get_col(k);
             }
-#ifdef DDB_TIMING
-            long long tacc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-            long long tlast = clock64();
-#endif
             while (status == ST_OPTIMAL && k >= 0) {
-                TSTAMP(7);
-                const int nb = par ^ 1;
-                const double* gcur = gbufs + (size_t)(par * W + gw) * CT;
                 // ratio test: one row per lane
+                const double e = reg_get<NC>(T, k);
                 const double et = lam * e;                         // true entry / right-hand side of my row
                 const double sc = fmax(lam * T[RHS], 0.0);
-                const bool ok = live && et > kTolPivot;
-                const double ratio = sc * fast_rcp(ok ? et : 1.0);
+                const bool cand = live && et > kTolPivot;
+                const double ratio = sc * fast_rcp(cand ? et : 1.0);
                 unsigned long long kmin;
-                const int ll = warp_argmin_key(ok ? dkey(ratio) : KEY_INF, kmin);
-                TSTAMP(0);                                         // ratio test + warp argmin
-                if (kmin != KEY_INF) {
-                    double* prw = prow + (size_t)(nb * W + warp) * PD;
-                    if (lane == ll) publish(prw);
+                const int ll = warp_argmin_key(cand ? dkey(ratio) : KEY_INF, kmin);
+                if (lane == 0) {
+                    hdr[warp].key = kmin;
+                    hdr[warp].row = warp * 32 + ll;
+                }
+                __syncthreads();
+                const int ww = warp_argmin_key((lane < W) ? hdr[lane].key : KEY_INF, kmin);
+                if (kmin == KEY_INF) { status = ST_UNBOUNDED; break; }
+                if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const int r = hdr[ww].row;
+                double* pr = prow + buf * PD;
+                const bool own = (tid == r);
+                if (warp == (r >> 5)) {
+                    if (own) publish(pr);
                     __syncwarp();
-                    TSTAMP(1);                                     // publish
-                    const double il = __shfl_sync(FULL, ilam, ll);
-                    const int var_r = __shfl_sync(FULL, rowvar, ll);
-                    const double p = prw[k];
-                    const double fg = gcur[k] * fast_rcp(p);
-                    double* gnext = gbufs + (size_t)(nb * W + warp) * CT;
+                    const double il = __shfl_sync(FULL, ilam, r & 31);
+                    const int var_r = __shfl_sync(FULL, rowvar, r & 31);
+                    const double p = pr[k];
+                    const double fg = gsm[k] * fast_rcp(p);
+                    const int cv = cvsm[k];
+                    __syncwarp();
                     double gmin = kInf;
                     int bq = 0;
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) {
                         const int j = lane + 32 * cs;
-                        const double rvj = (j < n) ? prw[j] : 0.0;
-                        double g = fma(-fg, rvj, gcur[j]);
-                        if (j == k) g = -fg * il;
-                        gnext[j] = g;
-                        if (j < n && g < gmin) { gmin = g; bq = cs; }
+                        if (j < n) {
+                            const double g = (j == k) ? -fg * il : fma(-fg, pr[j], gsm[j]);
+                            gsm[j] = g;
+                            if (g < gmin) { gmin = g; bq = cs; }
+                        }
                     }
-                    unsigned long long kmin2;
-                    const int kl = warp_argmin_key(dkey(gmin), kmin2);
-                    const int knext = (kmin2 < dkey(-kTolFeas)) ? kl + 32 * __shfl_sync(FULL, bq, kl) : -1;
+                    const int kl = warp_argmin_key(dkey(gmin), kmin);
+                    const int knext = (kmin < dkey(-kTolFeas)) ? kl + 32 * __shfl_sync(FULL, bq, kl) : -1;
                     if (lane == 0) {
-                        RowCand* cd = cand + nb * W + warp;
-                        cd->p = p;
-                        cd->il = il;
-                        cd->row = warp * 32 + ll;
-                        cd->k = knext;
-                        cd->var = var_r;
+                        pub[0].p = p;
+                        pub[0].il = il;
+                        pub[0].k = knext;
+                        pub[0].var = cv;
+                        cvsm[k] = var_r;
                     }
-                    TSTAMP(2);                                     // speculative pricing
                 }
-                if (lane == 0) keys[nb * W + warp] = kmin;
                 __syncthreads();
-                const int ww = pick_winner(nb, kmin);
-                TSTAMP(3);                                         // barrier + winner
-                if (kmin == KEY_INF) { status = ST_UNBOUNDED; break; }
-                if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
-                const RowCand* cd = cand + nb * W + ww;
-                const double p = cd->p, il = cd->il;
-                const int knext = cd->k;
-                const bool own = (tid == cd->row);
+                const double p = pub[0].p, il = pub[0].il;
                 const double rp = fast_rcp(p);
                 const double f = own ? 0.0 : e * rp;
-                double enext = 0.0;
-                TSTAMP(4);                                         // header, rcp
-                rank1_fused(prow + (size_t)(nb * W + ww) * PD, f, k, own ? il : -f * il, knext, enext);
-                TSTAMP(5);                                         // rank-1 update
-                if (own) {
-                    lam = rp;
-                    ilam = p;
-                    const int cv = cvsm[k];
-                    cvsm[k] = rowvar;
-                    rowvar = cv;
-                }
-                par = nb;
-                gw = ww;
-                k = knext;
-                e = enext;
+                rank1(pr, f);
+                reg_set<NC>(T, k, own ? il : -f * il);
+                if (own) { lam = rp; ilam = p; rowvar = pub[0].var; }
+                k = pub[0].k;
+                buf ^= 1;
                 ++npiv_p2;
-                TSTAMP(6);                                         // bookkeeping
             }
-#ifdef DDB_TIMING
-            if (a.gtab && lane == 0) {
-                double* o = a.gtab + ((size_t)lp * W + warp) * 16;
-                for (int q = 0; q < 14; ++q) o[q] = (double)tacc[q];
-                o[14] = (double)npiv_p2;
-            }
-#endif
         }
 
         // ---- stage 4: x, objective, slacks, labels -----------------------------------------------------------------

@@ -54,10 +54,12 @@ int ddb_destroy(ddb_ctx *ctx);
 /* sm_count, compute capability, opt-in shared memory per block (bytes) of the context's device. */
 int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, int64_t *smem_optin);
 
-/* Which kernel family ddb_solve_label_* will use for an (m, n) shape: 0 = register-tiled (tableau in the
- * register file), 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau; <0 = error. */
+/* Which kernel family ddb_solve_label_* will use for an (m, n) shape: 0 = tableau in the register file
+ * (row-per-thread kernel, falling back to the other register kernels for shapes it does not cover),
+ * 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau; <0 = error. */
 int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
-/* Force a kernel family for testing (-1 = automatic). */
+/* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 3 = 2-D register-tile kernel,
+ * 4 = warp-tiled register kernel (both are alternatives of plan 0 kept for A/B measurements). */
 int ddb_set_solve_plan(ddb_ctx *ctx, int plan);
 
 /*

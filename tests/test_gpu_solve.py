@@ -231,13 +231,15 @@ def test_full_size_properties(cuda_device):
     frac_unb = (st == 5).mean()
     assert abs(frac_unb - 0.472) < 0.02, frac_unb              # Wendel: 2^-m sum_{k<n} C(m,k) at m = 2n -> ~0.472
     ok = st == 2
-    assert (na[ok] == n).all() and (na[~ok] == 0).all()        # non-degenerate: exactly n active rows
-    # ties (an inactive slack inside [1e-8, 1e-6]) are rare but legitimate at this scale: counted, reported, bounded
-    n_tie = int((r['ties'].cpu().numpy() > 0).sum())
+    # ties (a slack inside [1e-8, 1e-6], or a thresholded label that disagrees with the final basis -- an
+    # ill-conditioned vertex) are rare but legitimate at this scale: counted, reported, bounded, never hidden
+    tie = r['ties'].cpu().numpy() > 0
+    n_tie = int(tie.sum())
     print('instances with a reported tie: %d of %d' % (n_tie, B))
     assert n_tie <= B // 1000
+    assert (na[ok & ~tie] == n).all() and (na[~ok] == 0).all()   # non-degenerate: exactly n active rows
     # KKT certificate on the device data, independent of the solver: primal feasibility and objective consistency
-    okt = torch.from_numpy(ok).cuda()
+    okt = torch.from_numpy(ok & ~tie).cuda()
     A, b, c, x = r['A'][okt], r['b'][okt], r['c'][okt], r['x'][okt]
     slack = b - torch.bmm(A, x.unsqueeze(2)).squeeze(2)
     assert slack.min().item() >= -1e-7
@@ -251,7 +253,8 @@ def test_full_size_properties(cuda_device):
     # linearity: scaling the objective scales the optimum, labels unchanged; row permutation permutes labels
     r2 = solver.solve_label(r['A'][:512], r['b'][:512], (r['c'][:512] * 3.0).contiguous())
     assert (r2['labels'] == lab[:512]).all()
-    assert torch.allclose(r2['obj'][ok[:512]], 3.0 * r['obj'][:512][ok[:512]], rtol=1e-9, atol=0)
+    okh = torch.from_numpy(ok[:512]).cuda()
+    assert torch.allclose(r2['obj'][okh], 3.0 * r['obj'][:512][okh], rtol=1e-9, atol=0)
     perm = torch.randperm(m, device='cuda')
     r3 = solver.solve_label(r['A'][:512][:, perm].contiguous(), r['b'][:512][:, perm].contiguous(), r['c'][:512])
     assert (r3['labels'] == lab[:512][:, perm]).all()
@@ -296,16 +299,18 @@ def test_dropin_dataset_and_linprog(cuda_device):
     assert len(ph) == 32 and ph[0]['lp']['A'].shape == (50, 20)
 
 
+@pytest.mark.parametrize('plan0', [0, 3, 4])
 @pytest.mark.parametrize('m,n,N', [(10, 5, 300), (50, 20, 300), (100, 50, 100), (200, 100, 200)])
-def test_register_tiled_and_generic_kernels_agree(cuda_device, m, n, N):
-    """plan 0 (tableau in registers) and plan 1 (tableau in shared memory) implement the same algorithm."""
+def test_register_resident_and_generic_kernels_agree(cuda_device, m, n, N, plan0):
+    """The three register-resident kernels (0: row per thread, 3: 2-D register tile, 4: warp-tiled) and plan 1
+    (tableau in shared memory) implement the same algorithm: same statuses, labels and pivot path."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
     assert ctx.solve_plan(m, n) == 0
     A, b, c = _numpy_batch(m, n, [17 + 3 * i for i in range(N)])
     dA, db, dc = _dev(A, b, c)
     try:
-        ctx.set_solve_plan(0)
+        ctx.set_solve_plan(plan0)
         r0 = _to_np(solver.solve_label(dA, db, dc))
         ctx.set_solve_plan(1)
         r1 = _to_np(solver.solve_label(dA, db, dc))
@@ -314,7 +319,7 @@ def test_register_tiled_and_generic_kernels_agree(cuda_device, m, n, N):
     assert (r0['status'] == r1['status']).all()
     assert (r0['labels'] == r1['labels']).all()
     assert (r0['n_active'] == r1['n_active']).all()
-    assert (r0['pivots'][:, 0] == r1['pivots'][:, 0]).all()
+    assert (r0['pivots'] == r1['pivots']).all()
     ok = r0['status'] == 2
     assert np.abs(r0['x'][ok] - r1['x'][ok]).max() <= 1e-9 * np.abs(r1['x'][ok]).max()
     assert np.abs(r0['obj'][ok] - r1['obj'][ok]).max() <= 1e-9 * np.abs(r1['obj'][ok]).max()
