@@ -97,7 +97,7 @@ __host__ __device__ constexpr int row_pitch(int NC) {
 }
 
 struct RowLayout {
-    size_t D, prow, pub, hdr, gsm, ghsm, cvsm, order, colvar0, pivcol, basic_tile, sval, sig, xbuf, gbuf, gnn, red, total;
+    size_t D, prow, pub, hdr, part, gsm, ghsm, cvsm, order, colvar0, pivcol, basic_tile, sval, sig, xbuf, gbuf, gnn, red, total;
 };
 __host__ __device__ inline size_t rr_align(size_t v) { return (v + 15) / 16 * 16; }
 __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W) {
@@ -109,7 +109,8 @@ __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W
     L.prow = off;       off += rr_align((size_t)2 * PD * 8);
     L.pub = off;        off += rr_align((size_t)2 * sizeof(RowPub));
     L.hdr = off;        off += rr_align((size_t)W * sizeof(RowHdr));
-    L.gsm = off;        off += rr_align((size_t)CT * 8);
+    L.part = off;       off += rr_align((size_t)W * sizeof(RowHdr));
+    L.gsm = off;        off += rr_align((size_t)2 * CT * 8);
     L.ghsm = off;       off += rr_align((size_t)CT * 8);
     L.cvsm = off;       off += rr_align((size_t)CT * 4);
     L.order = off;      off += rr_align((size_t)m * 4);
@@ -129,6 +130,7 @@ __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W
 template <int NC, int W, int MINB>
 __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs a) {
     constexpr int CS = (NC + 31) / 32;      // slots of the lane-distributed column vectors
+    constexpr int CT = 32 * CS;
     constexpr int PD = row_pitch(NC);
     constexpr int NT = W * 32;              // threads = tile rows
     constexpr int RHS = NC - 1;             // register / column that holds the right-hand side
@@ -141,7 +143,8 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
     double* prow = reinterpret_cast<double*>(smem_raw + L.prow);
     RowPub* pub = reinterpret_cast<RowPub*>(smem_raw + L.pub);
     RowHdr* hdr = reinterpret_cast<RowHdr*>(smem_raw + L.hdr);
-    double* gsm = reinterpret_cast<double*>(smem_raw + L.gsm);     // g: true reduced costs, one copy per CTA
+    RowHdr* part = reinterpret_cast<RowHdr*>(smem_raw + L.part);    // phase 2: per-warp partial pricing result
+    double* gsm = reinterpret_cast<double*>(smem_raw + L.gsm);     // g: true reduced costs ([2][CT], phase 2 double-buffers)
     double* ghsm = reinterpret_cast<double*>(smem_raw + L.ghsm);   // ghat: artificial costs of phase 1
     int* cvsm = reinterpret_cast<int*>(smem_raw + L.cvsm);         // column -> constraint whose slack is nonbasic
     int* order = reinterpret_cast<int*>(smem_raw + L.order);
@@ -480,9 +483,12 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             __syncthreads();
 
             // ---- stage 3b: phase 2 (Dantzig) ---------------------------------------------------------------
-            // The pivot row's warp prices the NEXT entering column while it holds the row, so the other warps never
-            // touch the cost vector.  First column: every warp computes it (read-only).
+            // Three short barriers per pivot: (A) candidates -> winner row, (B) the owner lane has published its raw
+            // row, (C) rank-1 update done and the next entering column priced.  Pricing is spread over the warps
+            // (warp w updates / scans the columns of slot w of a double-buffered cost vector) so that the only
+            // serial section of a pivot is the owner lane's 51 stores.
             int k = -1;
+            int gpar = 0;                 // current cost vector = gsm + gpar * CT
             if (status == ST_OPTIMAL) {
                 double gmin = kInf;
                 int bq = 0;
@@ -509,51 +515,59 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                     hdr[warp].key = kmin;
                     hdr[warp].row = warp * 32 + ll;
                 }
-                __syncthreads();
+                __syncthreads();                                   // (A)
                 const int ww = warp_argmin_key((lane < W) ? hdr[lane].key : KEY_INF, kmin);
                 if (kmin == KEY_INF) { status = ST_UNBOUNDED; break; }
                 if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
                 const int r = hdr[ww].row;
                 double* pr = prow + buf * PD;
                 const bool own = (tid == r);
-                if (warp == (r >> 5)) {
-                    if (own) publish(pr);
-                    __syncwarp();
-                    const double il = __shfl_sync(FULL, ilam, r & 31);
-                    const int var_r = __shfl_sync(FULL, rowvar, r & 31);
-                    const double p = pr[k];
-                    const double fg = gsm[k] * fast_rcp(p);
-                    const int cv = cvsm[k];
-                    __syncwarp();
+                double rp_own = 0.0;
+                if (own) {
+                    publish(pr);
+                    pub[0].p = e;                                  // my entry in column k is the pivot
+                    pub[0].il = ilam;
+                    const int cv = cvsm[k];                        // becomes basic in my row
+                    cvsm[k] = rowvar;                              // my old slack becomes nonbasic in column k
+                    rowvar = cv;
+                    rp_own = 1.0;
+                }
+                __syncthreads();                                   // (B)
+                const double p = pub[0].p, il = pub[0].il;
+                const double rp = fast_rcp(p);
+                {
+                    // my warp's share of the pricing: g' = g - (g_k / p) row, g'_k = -g_k / (p lam_r)
+                    const double* gcur = gsm + gpar * CT;
+                    double* gnext = gsm + (gpar ^ 1) * CT;
+                    const double fg = gcur[k] * rp;
                     double gmin = kInf;
-                    int bq = 0;
+                    int bj = 0;
 #pragma unroll
                     for (int cs = 0; cs < CS; ++cs) {
-                        const int j = lane + 32 * cs;
-                        if (j < n) {
-                            const double g = (j == k) ? -fg * il : fma(-fg, pr[j], gsm[j]);
-                            gsm[j] = g;
-                            if (g < gmin) { gmin = g; bq = cs; }
+                        if ((cs % W) == warp) {
+                            const int j = lane + 32 * cs;
+                            if (j < n) {
+                                const double g = (j == k) ? -fg * il : fma(-fg, pr[j], gcur[j]);
+                                gnext[j] = g;
+                                if (g < gmin) { gmin = g; bj = j; }
+                            }
                         }
                     }
                     const int kl = warp_argmin_key(dkey(gmin), kmin);
-                    const int knext = (kmin < dkey(-kTolFeas)) ? kl + 32 * __shfl_sync(FULL, bq, kl) : -1;
+                    const int bjw = __shfl_sync(FULL, bj, kl);
                     if (lane == 0) {
-                        pub[0].p = p;
-                        pub[0].il = il;
-                        pub[0].k = knext;
-                        pub[0].var = cv;
-                        cvsm[k] = var_r;
+                        part[warp].key = kmin;
+                        part[warp].row = bjw;
                     }
                 }
-                __syncthreads();
-                const double p = pub[0].p, il = pub[0].il;
-                const double rp = fast_rcp(p);
                 const double f = own ? 0.0 : e * rp;
                 rank1(pr, f);
                 reg_set<NC>(T, k, own ? il : -f * il);
-                if (own) { lam = rp; ilam = p; rowvar = pub[0].var; }
-                k = pub[0].k;
+                if (rp_own != 0.0) { lam = rp; ilam = p; }
+                __syncthreads();                                   // (C)
+                const int w2 = warp_argmin_key((lane < W) ? part[lane].key : KEY_INF, kmin);
+                k = (kmin < dkey(-kTolFeas)) ? part[w2].row : -1;
+                gpar ^= 1;
                 buf ^= 1;
                 ++npiv_p2;
             }
