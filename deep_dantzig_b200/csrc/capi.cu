@@ -32,7 +32,13 @@ struct S2vArgs {
     float* probs;
     int* error_flag;
     int store_A;
+    const float* gram;
+    int gram_pitch;
 };
+bool s2v_gram_tc_supported(int m, int n);
+size_t s2v_gram_out_floats(int m);
+cudaError_t launch_s2v_gram_tc(long long B, int m, int n, const double* A, const double* b, const double* c, float* out,
+                               int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_forward(const S2vArgs& a, int sm_count, long long smem_optin, cudaStream_t st, const char** why);
 }  // namespace ddb
 
@@ -78,6 +84,7 @@ struct ddb_ctx {
     cudaEvent_t scratch_free = nullptr;
     bool scratch_in_use = false;
     DevBuf genA, genb, genc;   // fused generate->solve chunk buffers
+    DevBuf gram;               // classifier: per-instance Gram row sums from the tensor-core kernel
     Slot slots[kSlots];
     int forced_plan = -1;
     int64_t launches = 0;
@@ -149,6 +156,7 @@ extern "C" int ddb_destroy(ddb_ctx* ctx) {
     release(ctx->genA);
     release(ctx->genb);
     release(ctx->genc);
+    release(ctx->gram);
     if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
     if (ctx->counters) cudaFree(ctx->counters);
     delete ctx;
@@ -442,6 +450,20 @@ extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, in
     a.graph = graph; a.B = B; a.m = m; a.n = n; a.p = p; a.T = T;
     a.A = A; a.b = b; a.c = c; a.params = params; a.logp = logp; a.probs = probs;
     a.error_flag = err; a.store_A = 0;
+    a.gram = nullptr; a.gram_pitch = 0;
+    // complete variant: the Gram product W = G G^T (the only dense contraction of the forward) runs on the tensor cores
+    // (tcgen05 kind::tf32, 3xTF32) when m + 1 <= 256; larger shapes keep the fused CUDA-core Gram inside the forward
+    static const bool no_tc = [] { const char* e = getenv("DDB_S2V_NO_TC"); return e && e[0] == '1'; }();
+    if (graph == 0 && !no_tc && ddb::s2v_gram_tc_supported(m, n)) {
+        const size_t need = (size_t)B * ddb::s2v_gram_out_floats(m) * sizeof(float);
+        if (need > ctx->gram.cap) CUDA_TRY(cudaStreamSynchronize(st));
+        int rc = ensure(ctx->gram, need);
+        if (rc) return rc;
+        CUDA_TRY(ddb::launch_s2v_gram_tc(B, m, n, A, b, c, (float*)ctx->gram.p, ctx->sm_count, st));
+        ctx->launches += 1;
+        a.gram = (const float*)ctx->gram.p;
+        a.gram_pitch = (int)(ddb::s2v_gram_out_floats(m) / 3);
+    }
     const char* why = "";
     cudaError_t e = ddb::launch_s2v_forward(a, ctx->sm_count, ctx->smem_optin, st, &why);
     if (e != cudaSuccess) {

@@ -30,6 +30,8 @@ struct S2vArgs {
     float* probs;              // [B, m, 2] (nullable)
     int* error_flag;           // set to 1 if a sparse instance did not fit the shared-memory plan
     int store_A;               // bipartite: normalised A kept in shared memory (general adjacency supported)
+    const float* gram;         // complete: [B][3][gram_pitch] Wp, Wn, wc from the tensor-core Gram kernel (nullable)
+    int gram_pitch;
 };
 
 __host__ __device__ inline int pad4(int v) { return (v + 3) & ~3; }
@@ -420,56 +422,68 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
-        // ---- G = [normalize([A | b]) ; [c, 0]]  (normalisation in fp64 as the reference does, s2v.py:145) ----------------
-        for (int i = warp; i < m; i += nw) {
-            const double bi = bg[i];
-            double ss = 0.0;
-            for (int j = lane; j < n; j += 32) {
-                const double x = Ag[(size_t)i * n + j];
-                ss = fma(x, x, ss);
+        if (a.gram) {
+            // Wp, Wn, wc were produced by the tcgen05 Gram kernel (s2v_gram_tc.cu): G never has to be built here
+            const float* gr = a.gram + (size_t)lp * 3 * a.gram_pitch;
+            for (int i = tid; i < M1; i += nt) {
+                Wp[i] = __ldg(gr + i);
+                Wn[i] = __ldg(gr + a.gram_pitch + i);
+                wc[i] = __ldg(gr + 2 * a.gram_pitch + i);
             }
-            ss = warp_sum(ss) + bi * bi;
-            const double inv = 1.0 / fmax(sqrt(ss), 1e-12);
-            for (int j = lane; j < n; j += 32) G[i * PG + j] = (float)(Ag[(size_t)i * n + j] * inv);
-            if (lane == 0) G[i * PG + n] = (float)(bi * inv);
-        }
-        for (int j = tid; j <= n; j += nt) G[m * PG + j] = (j < n) ? (float)cg[j] : 0.f;
-        for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
-        __syncthreads();
+            for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
+            __syncthreads();
+        } else {
+            // ---- G = [normalize([A | b]) ; [c, 0]]  (normalisation in fp64 as the reference does, s2v.py:145) ----------------
+            for (int i = warp; i < m; i += nw) {
+                const double bi = bg[i];
+                double ss = 0.0;
+                for (int j = lane; j < n; j += 32) {
+                    const double x = Ag[(size_t)i * n + j];
+                    ss = fma(x, x, ss);
+                }
+                ss = warp_sum(ss) + bi * bi;
+                const double inv = 1.0 / fmax(sqrt(ss), 1e-12);
+                for (int j = lane; j < n; j += 32) G[i * PG + j] = (float)(Ag[(size_t)i * n + j] * inv);
+                if (lane == 0) G[i * PG + n] = (float)(bi * inv);
+            }
+            for (int j = tid; j <= n; j += nt) G[m * PG + j] = (j < n) ? (float)cg[j] : 0.f;
+            for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
+            __syncthreads();
 
-        // ---- fused Gram + relu row sums: W_ij = <G_i, G_j>, never stored ----------------------------------------------------
-        // each warp takes 4 rows at a time; lanes walk the columns j (conflict-free: odd pitch)
-        for (int i0 = warp * 4; i0 < M1; i0 += nw * 4) {
-            float sp[4] = {0.f, 0.f, 0.f, 0.f}, sn[4] = {0.f, 0.f, 0.f, 0.f}, wl[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int j = lane; j < M1; j += 32) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-                const float* gj = G + j * PG;
-                for (int k = 0; k <= n; ++k) {
-                    const float x = gj[k];
-#pragma unroll
+            // ---- fused Gram + relu row sums: W_ij = <G_i, G_j>, never stored ----------------------------------------------------
+            // each warp takes 4 rows at a time; lanes walk the columns j (conflict-free: odd pitch)
+            for (int i0 = warp * 4; i0 < M1; i0 += nw * 4) {
+                float sp[4] = {0.f, 0.f, 0.f, 0.f}, sn[4] = {0.f, 0.f, 0.f, 0.f}, wl[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int j = lane; j < M1; j += 32) {
+                    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                    const float* gj = G + j * PG;
+                    for (int k = 0; k <= n; ++k) {
+                        const float x = gj[k];
+    #pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int i = (i0 + u < M1) ? i0 + u : m;
+                            acc[u] = fmaf(G[i * PG + k], x, acc[u]);
+                        }
+                    }
+    #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        const int i = (i0 + u < M1) ? i0 + u : m;
-                        acc[u] = fmaf(G[i * PG + k], x, acc[u]);
+                        const int i = i0 + u;
+                        if (i < M1 && j != i) {
+                            if (j < m) { sp[u] += fmaxf(acc[u], 0.f); sn[u] += fmaxf(-acc[u], 0.f); }
+                            else wl[u] = acc[u];                      // column m: against the cost node
+                        }
                     }
                 }
-#pragma unroll
+    #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int i = i0 + u;
-                    if (i < M1 && j != i) {
-                        if (j < m) { sp[u] += fmaxf(acc[u], 0.f); sn[u] += fmaxf(-acc[u], 0.f); }
-                        else wl[u] = acc[u];                      // column m: against the cost node
+                    const float a0 = warp_sumf(sp[u]), a1 = warp_sumf(sn[u]), a2 = warp_sumf(wl[u]);
+                    if (lane == 0 && i0 + u < M1) {
+                        Wp[i0 + u] = a0; Wn[i0 + u] = a1; wc[i0 + u] = a2;
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const float a0 = warp_sumf(sp[u]), a1 = warp_sumf(sn[u]), a2 = warp_sumf(wl[u]);
-                if (lane == 0 && i0 + u < M1) {
-                    Wp[i0 + u] = a0; Wn[i0 + u] = a1; wc[i0 + u] = a2;
-                }
-            }
+            __syncthreads();
         }
-        __syncthreads();
         // cost-node statistics: sums of relu(+-W[m][j]) over rows j < m  (W is symmetric: W[:m, m] == W[m, :m])
         if (warp == 0) {
             float sp = 0.f, sn = 0.f;
