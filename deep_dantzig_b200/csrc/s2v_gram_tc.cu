@@ -80,7 +80,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
 struct GramLayout {
     int RG;            // 8-row groups per plane
     int PLB;           // plane pitch in bytes
-    size_t hi, lo, inv, bar, slot, total;
+    size_t hi, lo, stage, inv, bar, slot, total;   // hi / lo of stage 0; stage = byte offset between the two stages
 };
 __host__ __device__ inline GramLayout gram_layout(int m) {
     GramLayout L;
@@ -91,10 +91,13 @@ __host__ __device__ inline GramLayout gram_layout(int m) {
     size_t off = 0;
     L.hi = off;   off += (size_t)NPL * L.PLB;
     L.lo = off;   off += (size_t)NPL * L.PLB;
+    off = (off + 127) / 128 * 128;
+    L.stage = off;
+    off *= 2;                                  // second stage: produce chunk k+1 while the tensor core reads chunk k
     off = (off + 15) / 16 * 16;
     L.inv = off;  off += (size_t)(M1 + 16) * 4;
     off = (off + 15) / 16 * 16;
-    L.bar = off;  off += 16;
+    L.bar = off;  off += 32;
     L.slot = off; off += 16;
     L.total = off;
     return L;
@@ -124,13 +127,15 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
     }
     if (tid == 0) {
         mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
         fence_mbar_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot;
-    uint32_t parity = 0;
+    uint32_t par0 = 0, par1 = 0;          // phase parity of the two stage barriers
+    bool pend0 = false, pend1 = false;    // stage has MMAs in flight that have not been waited for
 
     // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = NN
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -146,9 +151,15 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
         // epilogue and A is read exactly once.
         for (int kc = 0; kc < nkc; ++kc) {
             const int kabs = kc * KC + lane;
+            const int stg = kc & 1;
+            // the MMAs that read this stage two chunks ago must have finished before it is overwritten
+            if (stg == 0 && pend0) { mbar_wait(bar, par0); par0 ^= 1; pend0 = false; }
+            if (stg == 1 && pend1) { mbar_wait(bar + 1, par1); par1 ^= 1; pend1 = false; }
+            unsigned char* hs = hi + (size_t)stg * L.stage;
+            unsigned char* ls = lo + (size_t)stg * L.stage;
             // ---- produce the chunk: rows of G' -> (hi, lo) tf32 in the canonical UMMA layout -------------------------------
             const uint32_t coff = (uint32_t)(lane >> 2) * L.PLB + (lane & 3) * 4;
-#pragma unroll 8
+#pragma unroll 16
             for (int r = warp; r < rows_pl; r += GT / 32) {
                 double v = 0.0;
                 if (r < m) {
@@ -161,33 +172,36 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
                 const uint32_t h = to_tf32(g);
                 const uint32_t l = to_tf32(g - __uint_as_float(h));
                 const uint32_t off = coff + (uint32_t)(r >> 3) * 128 + (r & 7) * 16;
-                *reinterpret_cast<uint32_t*>(hi + off) = h;
-                *reinterpret_cast<uint32_t*>(lo + off) = l;
+                *reinterpret_cast<uint32_t*>(hs + off) = h;
+                *reinterpret_cast<uint32_t*>(ls + off) = l;
             }
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
                 tc_fence_after();
+                const uint32_t hb = hi_s + (uint32_t)(stg * L.stage), lb = lo_s + (uint32_t)(stg * L.stage);
 #pragma unroll 1
                 for (int mt = 0; mt < MT; ++mt) {
                     const uint32_t d = tmem_base + (uint32_t)(mt * NN);
 #pragma unroll 1
                     for (int s = 0; s < KC / 8; ++s) {
                         const uint32_t ko = (uint32_t)(2 * s) * L.PLB;
-                        const uint64_t a_hi = smem_desc(hi_s + ko + mt * 2048, L.PLB, 128);
-                        const uint64_t a_lo = smem_desc(lo_s + ko + mt * 2048, L.PLB, 128);
-                        const uint64_t b_hi = smem_desc(hi_s + ko, L.PLB, 128);
-                        const uint64_t b_lo = smem_desc(lo_s + ko, L.PLB, 128);
+                        const uint64_t a_hi = smem_desc(hb + ko + mt * 2048, L.PLB, 128);
+                        const uint64_t a_lo = smem_desc(lb + ko + mt * 2048, L.PLB, 128);
+                        const uint64_t b_hi = smem_desc(hb + ko, L.PLB, 128);
+                        const uint64_t b_lo = smem_desc(lb + ko, L.PLB, 128);
                         umma_tf32(d, a_hi, b_hi, idesc, (kc | s) != 0);
                         umma_tf32(d, a_hi, b_lo, idesc, 1);
                         umma_tf32(d, a_lo, b_hi, idesc, 1);
                     }
                 }
-                umma_commit(bar);
+                umma_commit(bar + stg);
             }
-            mbar_wait(bar, parity);                      // the MMAs have consumed the chunk (and, last chunk, D is complete)
-            parity ^= 1;
+            if (stg == 0) pend0 = true; else pend1 = true;
         }
+        // all MMAs of this instance have to be complete before the accumulators are read
+        if (pend0) { mbar_wait(bar, par0); par0 ^= 1; pend0 = false; }
+        if (pend1) { mbar_wait(bar + 1, par1); par1 ^= 1; pend1 = false; }
         tc_fence_after();
 
         // ---- epilogue (warps 0-3: thread t owns accumulator row t of each tile) ------------------------------------------
