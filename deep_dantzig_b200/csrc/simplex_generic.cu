@@ -15,8 +15,9 @@
 // order of the cosine score a_i.c/|a_i| (rows most opposed to c first), column = largest |entry|;
 // (2) phase 1: dual-simplex-type pivots with artificial costs ghat = 1 until s >= 0;
 // (3) phase 2: Dantzig primal simplex until g >= 0; ties everywhere broken by lowest variable index (Bland);
-// (4) x from the rows frozen at the end of the crash, slack = b - A x recomputed from the caller's A,
-//     labels = |slack| <= threshold exactly as gurobi_lp.py:435-443.
+// (4) x from the rows frozen at the end of the crash, one step of iterative refinement on the final active set when
+//     its residual is not negligible, slack = b - A x recomputed from the caller's A, labels = |slack| <= threshold
+//     exactly as gurobi_lp.py:435-443.
 #include "common.cuh"
 
 namespace ddb {
@@ -418,6 +419,54 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
                 }
             }
             __syncthreads();
+            // ---- one step of iterative refinement on the final active set -------------------------------------------------
+            // rho_j = slack of the active (nonbasic) constraint of column j at the computed x, from the caller's A, b; it
+            // should be 0.  When it is not (an ill-conditioned vertex: the errors of a few hundred pivots amplified),
+            // move the nonbasic slacks from rho to 0 through the tableau:  d sigma = +sum_j P_wj rho_j for a crash
+            // constraint that is basic in row w, d sigma = -rho_k for one that is nonbasic in column k, and
+            // x -= D d sigma.  The corrected slacks are accurate to second order.
+            {
+                double* rho = gh;     // the phase-1 cost vector is dead by now
+                double* dsig = g;     // so is g
+                double rmax = 0.0;
+                for (int j = warp; j < n; j += nw) {
+                    const int q = colvar[j];
+                    double acc = 0.0;
+                    if (q >= 0)
+                        for (int c2 = lane; c2 < n; c2 += 32) acc = fma(Ag[(size_t)q * n + c2], xbuf[c2], acc);
+                    acc = warp_sum(acc);
+                    const double r = (q >= 0) ? bg[q] - acc : 0.0;
+                    if (lane == 0) rho[j] = r;
+                    rmax = fmax(rmax, fabs(r));
+                }
+                if (__syncthreads_or(rmax > a.thr * 0.01)) {
+                    for (int j0 = warp; j0 < n; j0 += nw) {
+                        const int q0 = colvar0[j0];
+                        double d = 0.0;
+                        if (q0 >= 0) {
+                            const int w = where[q0];
+                            if (w >= 0) {
+                                for (int j = lane; j < n; j += 32) d = fma(P[(size_t)w * n + j], rho[j], d);
+                                d = warp_sum(d);
+                            } else {
+                                d = -rho[-w - 1];
+                            }
+                        }
+                        if (lane == 0) sig[j0] = d;
+                    }
+                    __syncthreads();
+                    for (int i = warp; i < m; i += nw) {
+                        if (rowstate[i] == ROW_CRASHED) {
+                            double acc = 0.0;
+                            for (int j = lane; j < n; j += 32) acc = fma(P[(size_t)i * n + j], sig[j], acc);
+                            acc = warp_sum(acc);
+                            if (lane == 0) xbuf[rowfree[i]] -= acc;
+                        }
+                    }
+                    __syncthreads();
+                }
+                (void)dsig;
+            }
             if (warp == 0) {
                 double acc = 0.0;
                 for (int j = lane; j < n; j += 32) acc = fma(cg[j], xbuf[j], acc);

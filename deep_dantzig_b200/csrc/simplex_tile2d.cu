@@ -667,7 +667,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_tile2d_kernel(SolveArgs 
         __syncthreads();
         TSTAGE(4);                                             // phase 2
         uint8_t* lab = a.labels + (size_t)lp * m;
-        int nact = 0, nties = 0, nviol = 0;
+        int nact = 0, nties = 0, nviol = 0, nref = 0;
         if (need_generic) {
             status = -1;   // re-solved by the generic kernel (capi.cu)
         } else if (status == ST_OPTIMAL) {
@@ -732,8 +732,13 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_tile2d_kernel(SolveArgs 
                 if (!excl) tie |= (active != (basic_tile[i] < 0));
                 nties += tie;
                 nviol += (slack < -a.thr * 10.0);
+                nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);   // active row with a visible residual
             }
         }
+        // An optimal instance whose active rows do not have (numerically) zero slack at the computed x -- an
+        // ill-conditioned vertex -- is handed to the generic kernel, which holds the tableau in memory and can run a
+        // step of iterative refinement on the final active set (simplex_generic.cu).
+        if (__syncthreads_or(nref > 0) && status == ST_OPTIMAL) status = -1;
         if (!need_generic && status != ST_OPTIMAL) {
             for (int i = tid; i < m; i += NT) lab[i] = 0;
             if (a.x)
