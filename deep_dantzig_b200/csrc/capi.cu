@@ -40,6 +40,21 @@ size_t s2v_gram_out_floats(int m);
 cudaError_t launch_s2v_gram_tc(long long B, int m, int n, const double* A, const double* b, const double* c, float* out,
                                int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_forward(const S2vArgs& a, int sm_count, long long smem_optin, cudaStream_t st, const char** why);
+struct S2vGradArgs {
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;
+    const uint8_t* labels;
+    float w0, w1;
+    float* grad;
+    double* loss;
+    int* error_flag;
+};
+cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_count, long long smem_optin, cudaStream_t st,
+                                      const char** why);
 }  // namespace ddb
 
 static thread_local char g_err[512] = "";
@@ -469,6 +484,39 @@ extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, in
     if (e != cudaSuccess) {
         if (why[0]) return fail(DDB_EUNSUPPORTED, "%s (m=%d n=%d p=%d)", why, m, n, p);
         return fail(DDB_ECUDA, "s2v forward launch: %s", cudaGetErrorString(e));
+    }
+    ctx->launches += 1;
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// classifier loss + gradient (training step of the reference: src/ml/train.py:59-66, criterion src/benchmark.py:70-75)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
+                                     const double* b, const double* c, const float* params, const uint8_t* labels,
+                                     float w0, float w1, float* grad, double* loss, int32_t* not_dense, void* stream) {
+    if (!ctx || !A || !b || !c || !params || !labels || !grad || !loss || !not_dense)
+        return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: NULL argument");
+    if (graph != 1)
+        return fail(DDB_EUNSUPPORTED, "ddb_s2v_loss_grad_dev: only the bipartite variant (graph 1) has a device backward");
+    if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
+        return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: B=%lld m=%d n=%d p=%d T=%d", (long long)B, m, n, p, T);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npar = ddb_s2v_param_count(graph, p);
+    CUDA_TRY(cudaMemsetAsync(grad, 0, sizeof(float) * (size_t)npar, st));
+    CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
+    CUDA_TRY(cudaMemsetAsync(not_dense, 0, sizeof(int32_t), st));
+    if (B == 0) return DDB_OK;
+    ddb::S2vGradArgs a;
+    a.B = B; a.m = m; a.n = n; a.p = p; a.T = T;
+    a.A = A; a.b = b; a.c = c; a.params = params; a.labels = labels; a.w0 = w0; a.w1 = w1;
+    a.grad = grad; a.loss = loss; a.error_flag = not_dense;
+    const char* why = "";
+    cudaError_t e = ddb::launch_s2v_bipartite_grad(a, npar, ctx->sm_count, ctx->smem_optin, st, &why);
+    if (e != cudaSuccess) {
+        if (why[0]) return fail(DDB_EUNSUPPORTED, "%s (m=%d n=%d p=%d T=%d)", why, m, n, p, T);
+        return fail(DDB_ECUDA, "s2v backward launch: %s", cudaGetErrorString(e));
     }
     ctx->launches += 1;
     return DDB_OK;

@@ -1,0 +1,468 @@
+// Batched loss + gradient of the reference classifier, bipartite variant on dense instances: one CTA per LP instance,
+// fp32, forward recomputed in shared memory, backward by hand, gradients summed over the batch.
+//
+// Replaces the inner loop of train_net (reference src/ml/train.py:59-66: zero_grad; for every instance
+// loss = criterion(model(x), y); loss.backward(); optimizer.step()) with its criterion
+// NLLLoss(weight=[w0, w1], size_average=False) (src/benchmark.py:70-75) for a whole batch: the summed loss and the
+// accumulated gradient of every parameter, in the flat state_dict order of include/ddb200.h (4).
+//
+// Forward = s2v_bipartite_kernel (s2v_forward.cu; s2v.py:253-323, 218-251, quirk B9 kept).  What makes the backward
+// cheap on the reference's dense random LPs (adj all ones): the messages a node receives are group means, so the
+// gradient that flows back through a round is the SAME vector for every constraint node (d mean_c / m) and for every
+// variable node (d mean_v / n); only the last round needs a per-node gradient (through t7).  Per round the kernel keeps
+// one p-bit activity mask per node and the two input means, nothing else.
+//   head:   scores_i = t8 . [relu(u6) ; relu(t7 mu_i) ; c_feats_i],  u6 = t6c mean_c + t6v mean_v
+//   round:  mu_q = relu(base_q + (q < n ? t2c mean_c : t2v mean_v)),  base_q = t0 + t1 . feats_q + w3 . relu-sums_q
+//   w3cp = t3c relu(t4c), w3cn = t3c relu(-t4c) (same for v): their gradients are accumulated as p-vectors and pushed
+//   through t3 / t4 once per CTA.
+#include "common.cuh"
+
+namespace ddb {
+
+struct S2vGradArgs {
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;
+    const uint8_t* labels;     // [B, m] 0 / 1
+    float w0, w1;              // class weights of the NLL loss
+    float* grad;               // [param_count], accumulated with atomics (zeroed by the caller)
+    double* loss;              // scalar, accumulated with atomics (zeroed by the caller)
+    int* error_flag;           // set to 1 when an instance is not dense (general adjacency is not handled here)
+};
+
+namespace {
+
+__host__ __device__ inline int bpad4(int v) { return (v + 3) & ~3; }
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+// y[k] = sum_l W[k][l] x[l], W row-major p x p in global memory; one warp per output
+__device__ __forceinline__ void matvec_g(const float* __restrict__ W, int p, const float* x, float* y, int warp, int lane, int nw) {
+    for (int k = warp; k < p; k += nw) {
+        float acc = 0.f;
+        for (int l = lane; l < p; l += 32) acc = fmaf(__ldg(W + k * p + l), x[l], acc);
+        acc = wsum(acc);
+        if (lane == 0) y[k] = acc;
+    }
+}
+// y[l] = sum_k W[k][l] x[k]  (transposed product), one warp per output
+__device__ __forceinline__ void matvec_gT(const float* __restrict__ W, int p, const float* x, float* y, int warp, int lane, int nw) {
+    for (int l = warp; l < p; l += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < p; k += 32) acc = fmaf(__ldg(W + k * p + l), x[k], acc);
+        acc = wsum(acc);
+        if (lane == 0) y[l] = acc;
+    }
+}
+
+struct GradLayout {          // offsets in floats
+    size_t t7T, t7N, mu, zr, dmu, gacc, mask, vecs, total;
+};
+__host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, int npar) {
+    const int PP = bpad4(p), NP = m + n;
+    GradLayout L;
+    size_t off = 0;
+    L.t7T = off;  off += (size_t)p * PP;
+    L.t7N = off;  off += (size_t)p * PP;
+    L.mu = off;   off += (size_t)p * NP;
+    L.zr = off;   off += (size_t)p * m;
+    L.dmu = off;  off += (size_t)p * m;
+    L.gacc = off; off += (size_t)((npar + 3) & ~3);
+    off = (off + 1) & ~(size_t)1;
+    L.mask = off; off += (size_t)2 * T * NP;                       // one 64-bit mask per (round, node)
+    L.vecs = off;
+    off += (size_t)8 * m + 5 * n + (size_t)(24 + 2 * T) * PP + 64;
+    L.total = off;
+    return L;
+}
+
+__global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, int npar) {
+    extern __shared__ __align__(16) float sm[];
+    const int m = a.m, n = a.n, p = a.p, T = a.T, PP = bpad4(p), NP = m + n;
+    const GradLayout L = grad_layout(m, n, p, T, npar);
+    float* t7T = sm + L.t7T;                  // t7T[l][k] = t7[k][l]
+    float* t7N = sm + L.t7N;                  // t7N[k][l] = t7[k][l]
+    float* mu = sm + L.mu;                    // [p][NP] embeddings of the current round
+    float* zr = sm + L.zr;                    // [p][m] relu(t7 mu_i), later d z
+    float* dmu = sm + L.dmu;                  // [p][m] gradient wrt the last round's constraint embeddings
+    float* gacc = sm + L.gacc;                // per-CTA gradient accumulator, flat parameter order
+    unsigned long long* mask = reinterpret_cast<unsigned long long*>(sm + L.mask);   // [T][NP]
+    float* v = sm + L.vecs;
+    float* rb = v;     v += m;    float* cosv = v;  v += m;    float* Sp = v;   v += m;    float* Sn = v;  v += m;
+    float* ds0 = v;    v += m;    float* ds1 = v;   v += m;    float* lossn = v; v += m;   float* spare = v; v += m;
+    float* cj = v;     v += n;    float* Cp = v;    v += n;    float* Cn = v;   v += n;    float* ccnt = v; v += 2 * n;
+    float* w3cp = v;   v += PP;   float* w3cn = v;  v += PP;   float* w3vp = v; v += PP;   float* w3vn = v; v += PP;
+    float* meanc = v;  v += PP;   float* meanv = v; v += PP;   float* yv = v;   v += PP;   float* yc = v;   v += PP;
+    float* u6pre = v;  v += PP;   float* u6r = v;   v += PP;   float* du6 = v;  v += PP;   float* tmp1 = v; v += PP;
+    float* tmp2 = v;   v += PP;   float* dmc = v;   v += PP;   float* dmv = v;  v += PP;   float* da = v;   v += PP;
+    float* db2 = v;    v += PP;   float* r4 = v;    v += 4 * PP;
+    float* gw3 = v;    v += 4 * PP;            // per-CTA accumulators of d w3cp, d w3cn, d w3vp, d w3vn
+    float* mcs = v;    v += (size_t)T * PP;    // input mean_c of every round
+    float* mvs = v;    v += (size_t)T * PP;    // input mean_v of every round
+    int* iflag = reinterpret_cast<int*>(v);
+    (void)spare;
+
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const float* P = a.params;
+    const float* t0 = P;   P += p;        const int o_t0 = 0;
+    const float* t1c = P;  P += 4 * p;    const int o_t1c = o_t0 + p;
+    const float* t1v = P;  P += p;        const int o_t1v = o_t1c + 4 * p;
+    const float* t2c = P;  P += p * p;    const int o_t2c = o_t1v + p;
+    const float* t2v = P;  P += p * p;    const int o_t2v = o_t2c + p * p;
+    const float* t3c = P;  P += p * p;    const int o_t3c = o_t2v + p * p;
+    const float* t3v = P;  P += p * p;    const int o_t3v = o_t3c + p * p;
+    const float* t4c = P;  P += p;        const int o_t4c = o_t3v + p * p;
+    const float* t4v = P;  P += p;        const int o_t4v = o_t4c + p;
+    const float* t6c = P;  P += p * p;    const int o_t6c = o_t4v + p;
+    const float* t6v = P;  P += p * p;    const int o_t6v = o_t6c + p * p;
+    const float* t7 = P;   P += p * p;    const int o_t7 = o_t6v + p * p;
+    const float* t8 = P;                  const int o_t8 = o_t7 + p * p;
+    const int W8 = 2 * p + 4;
+
+    for (int e = tid; e < p * PP; e += nt) {
+        const int r = e / PP, q = e - r * PP;
+        t7T[e] = (q < p) ? __ldg(t7 + q * p + r) : 0.f;
+        t7N[e] = (q < p) ? __ldg(t7 + r * p + q) : 0.f;
+    }
+    for (int e = tid; e < npar; e += nt) gacc[e] = 0.f;
+    for (int e = tid; e < 4 * PP; e += nt) gw3[e] = 0.f;
+    for (int l = tid; l < p; l += nt) {
+        r4[l] = fmaxf(__ldg(t4c + l), 0.f);
+        r4[PP + l] = fmaxf(-__ldg(t4c + l), 0.f);
+        r4[2 * PP + l] = fmaxf(__ldg(t4v + l), 0.f);
+        r4[3 * PP + l] = fmaxf(-__ldg(t4v + l), 0.f);
+    }
+    __syncthreads();
+    matvec_g(t3c, p, r4, w3cp, warp, lane, nw);
+    matvec_g(t3c, p, r4 + PP, w3cn, warp, lane, nw);
+    matvec_g(t3v, p, r4 + 2 * PP, w3vp, warp, lane, nw);
+    matvec_g(t3v, p, r4 + 3 * PP, w3vn, warp, lane, nw);
+    __syncthreads();
+    double loss_cta = 0.0;
+
+    for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        const uint8_t* yl = a.labels + (size_t)lp * m;
+        for (int j = tid; j < n; j += nt) {
+            cj[j] = (float)cg[j];
+            Cp[j] = 0.f; Cn[j] = 0.f; ccnt[j] = 0.f;
+        }
+        if (tid == 0) *iflag = 0;
+        __syncthreads();
+        // ---- pass over A (as the forward kernel): row normalisation, cosines, relu row / column sums -------------------
+        for (int i = warp; i < m; i += nw) {
+            const float bi = (float)bg[i];
+            float ss = 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const float x = (float)Ag[(size_t)i * n + j];
+                ss = fmaf(x, x, ss);
+            }
+            ss = wsum(ss) + bi * bi;
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+            float cs = 0.f, sp = 0.f, sn = 0.f, cnt = 0.f;
+            for (int j = lane; j < n; j += 32) {
+                const float x = (float)Ag[(size_t)i * n + j] * inv;
+                cs = fmaf(x, cj[j], cs);
+                sp += fmaxf(x, 0.f);
+                sn += fmaxf(-x, 0.f);
+                cnt += (x != 0.f) ? 1.f : 0.f;
+                atomicAdd(&Cp[j], fmaxf(x, 0.f));
+                atomicAdd(&Cn[j], fmaxf(-x, 0.f));
+            }
+            cs = wsum(cs); sp = wsum(sp); sn = wsum(sn); cnt = wsum(cnt);
+            if (lane == 0) {
+                rb[i] = bi * inv; cosv[i] = cs; Sp[i] = sp; Sn[i] = sn;
+                if (cnt != (float)n) *iflag = 1;
+            }
+        }
+        for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
+        __syncthreads();
+        if (*iflag) {                     // sparse instance: not handled by this kernel (uniform decision)
+            if (tid == 0) *a.error_flag = 1;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- forward rounds, keeping the activity masks and the input means of every round -----------------------------
+        for (int t = 0; t < T; ++t) {
+            for (int l = warp; l < p; l += nw) {
+                float sc = 0.f, svv = 0.f;
+                for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
+                for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
+                sc = wsum(sc); svv = wsum(svv);
+                if (lane == 0) {
+                    meanc[l] = sc / (float)m; meanv[l] = svv / (float)n;
+                    mcs[t * PP + l] = meanc[l]; mvs[t * PP + l] = meanv[l];
+                }
+            }
+            __syncthreads();
+            matvec_g(t2c, p, meanc, yv, warp, lane, nw);
+            matvec_g(t2v, p, meanv, yc, warp, lane, nw);
+            __syncthreads();
+            for (int q = tid; q < NP; q += nt) {
+                unsigned long long bits = 0ull;
+                for (int l = 0; l < p; ++l) {
+                    float val = __ldg(t0 + l);
+                    if (q < m) {
+                        val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
+                        val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
+                    } else {
+                        const int j = q - m;
+                        val += __ldg(t1v + l) * cj[j] + w3vp[l] * Cp[j] + w3vn[l] * Cn[j];
+                    }
+                    val += (q < n) ? yv[l] : yc[l];
+                    if (val > 0.f) bits |= 1ull << l;
+                    mu[l * NP + q] = fmaxf(val, 0.f);
+                }
+                mask[(size_t)t * NP + q] = bits;
+            }
+            __syncthreads();
+        }
+
+        // ---- head forward: scores, loss, d scores ---------------------------------------------------------------------------
+        for (int l = warp; l < p; l += nw) {
+            float sc = 0.f, svv = 0.f;
+            for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
+            for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
+            sc = wsum(sc); svv = wsum(svv);
+            if (lane == 0) { meanc[l] = sc / (float)m; meanv[l] = svv / (float)n; }
+        }
+        __syncthreads();
+        matvec_g(t6c, p, meanc, tmp1, warp, lane, nw);
+        matvec_g(t6v, p, meanv, tmp2, warp, lane, nw);
+        __syncthreads();
+        for (int l = tid; l < p; l += nt) {
+            u6pre[l] = tmp1[l] + tmp2[l];
+            u6r[l] = fmaxf(u6pre[l], 0.f);
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += nt) {
+            float s0 = 0.f, s1 = 0.f;
+            for (int l = 0; l < p; ++l) {
+                s0 = fmaf(__ldg(t8 + l), u6r[l], s0);
+                s1 = fmaf(__ldg(t8 + W8 + l), u6r[l], s1);
+            }
+            for (int kb = 0; kb < PP; kb += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int l = 0; l < p; ++l) {
+                    const float x = mu[l * NP + i];
+                    const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
+                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                }
+                const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (kb + u < p) {
+                        zr[(kb + u) * m + i] = r[u];
+                        s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
+                        s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
+                    }
+                }
+            }
+            const float f1 = rb[i], f3 = cosv[i];
+            s0 += __ldg(t8 + 2 * p) + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 3) * f3;
+            s1 += __ldg(t8 + W8 + 2 * p) + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 3) * f3;
+            const float mx = fmaxf(s0, s1);
+            const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
+            const float p0 = expf(s0 - lse), p1 = expf(s1 - lse);
+            const int y = yl[i] ? 1 : 0;
+            const float w = y ? a.w1 : a.w0;
+            lossn[i] = -w * (y ? (s1 - lse) : (s0 - lse));
+            ds0[i] = w * (p0 - (y == 0 ? 1.f : 0.f));
+            ds1[i] = w * (p1 - (y == 1 ? 1.f : 0.f));
+        }
+        __syncthreads();
+
+        // ---- head backward ------------------------------------------------------------------------------------------------------
+        // S_c = sum_i ds_c[i];  loss
+        if (warp == 0) {
+            float s0 = 0.f, s1 = 0.f, ls = 0.f;
+            for (int i = lane; i < m; i += 32) { s0 += ds0[i]; s1 += ds1[i]; ls += lossn[i]; }
+            s0 = wsum(s0); s1 = wsum(s1); ls = wsum(ls);
+            if (lane == 0) { tmp1[0] = s0; tmp1[1] = s1; loss_cta += (double)ls; }
+        }
+        __syncthreads();
+        {
+            const float S0 = tmp1[0], S1 = tmp1[1];
+            // d t8: u6 block, c_feats block
+            for (int l = tid; l < p; l += nt) {
+                gacc[o_t8 + l] += S0 * u6r[l];
+                gacc[o_t8 + W8 + l] += S1 * u6r[l];
+                const float g = __ldg(t8 + l) * S0 + __ldg(t8 + W8 + l) * S1;
+                du6[l] = (u6pre[l] > 0.f) ? g : 0.f;
+            }
+            if (warp == 1) {
+                float f1a = 0.f, f1b = 0.f, f3a = 0.f, f3b = 0.f;
+                for (int i = lane; i < m; i += 32) {
+                    f1a += ds0[i] * rb[i]; f1b += ds1[i] * rb[i];
+                    f3a += ds0[i] * cosv[i]; f3b += ds1[i] * cosv[i];
+                }
+                f1a = wsum(f1a); f1b = wsum(f1b); f3a = wsum(f3a); f3b = wsum(f3b);
+                if (lane == 0) {
+                    gacc[o_t8 + 2 * p] += S0;          gacc[o_t8 + W8 + 2 * p] += S1;
+                    gacc[o_t8 + 2 * p + 1] += f1a;     gacc[o_t8 + W8 + 2 * p + 1] += f1b;
+                    gacc[o_t8 + 2 * p + 3] += f3a;     gacc[o_t8 + W8 + 2 * p + 3] += f3b;
+                }
+            }
+        }
+        // d t8 (z block) and d z in place of zr
+        for (int k = warp; k < p; k += nw) {
+            float g0 = 0.f, g1 = 0.f;
+            const float w0k = __ldg(t8 + p + k), w1k = __ldg(t8 + W8 + p + k);
+            for (int i = lane; i < m; i += 32) {
+                const float z = zr[k * m + i];
+                g0 = fmaf(ds0[i], z, g0);
+                g1 = fmaf(ds1[i], z, g1);
+                zr[k * m + i] = (z > 0.f) ? (w0k * ds0[i] + w1k * ds1[i]) : 0.f;
+            }
+            g0 = wsum(g0); g1 = wsum(g1);
+            if (lane == 0) { gacc[o_t8 + p + k] += g0; gacc[o_t8 + W8 + p + k] += g1; }
+        }
+        __syncthreads();
+        // d t6c, d t6v;  t6c^T du6, t6v^T du6
+        for (int e = tid; e < p * p; e += nt) {
+            const int k = e / p, l = e - k * p;
+            gacc[o_t6c + e] += du6[k] * meanc[l];
+            gacc[o_t6v + e] += du6[k] * meanv[l];
+        }
+        matvec_gT(t6c, p, du6, tmp1, warp, lane, nw);     // tmp1 = t6c^T du6
+        matvec_gT(t6v, p, du6, tmp2, warp, lane, nw);     // tmp2 = t6v^T du6
+        // d t7[k][l] = sum_i dz[k][i] mu[l][i]
+        for (int e = tid; e < p * p; e += nt) {
+            const int k = e / p, l = e - k * p;
+            float acc = 0.f;
+            for (int i = 0; i < m; ++i) acc = fmaf(zr[k * m + i], mu[l * NP + i], acc);
+            gacc[o_t7 + e] += acc;
+        }
+        __syncthreads();
+        // d mu_c (last round) = t7^T dz + t6c^T du6 / m
+        for (int i = tid; i < m; i += nt) {
+            for (int lb = 0; lb < PP; lb += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                for (int k = 0; k < p; ++k) {
+                    const float x = zr[k * m + i];
+                    const float4 w = *reinterpret_cast<const float4*>(t7N + k * PP + lb);
+                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                }
+                const float r[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (lb + u < p) dmu[(lb + u) * m + i] = r[u] + tmp1[lb + u] / (float)m;
+            }
+        }
+        for (int l = tid; l < p; l += nt) dmv[l] = tmp2[l] / (float)n;      // same for every variable node
+        __syncthreads();
+
+        // ---- rounds backward ---------------------------------------------------------------------------------------------------
+        for (int t = T - 1; t >= 0; --t) {
+            const bool last = (t == T - 1);
+            // one warp per embedding coordinate l: the linear reductions of d pre[l][:] over the nodes
+            for (int l = warp; l < p; l += nw) {
+                float s_all = 0.f, s_t1c1 = 0.f, s_t1c3 = 0.f, s_c = 0.f, s_sp = 0.f, s_sn = 0.f;
+                float s_t1v = 0.f, s_cp = 0.f, s_cn = 0.f, s_a = 0.f, s_b = 0.f;
+                const float gc = last ? 0.f : dmc[l], gv = dmv[l];
+                for (int q = lane; q < NP; q += 32) {
+                    const bool on = (mask[(size_t)t * NP + q] >> l) & 1ull;
+                    float d = 0.f;
+                    if (on) d = (q < m) ? (last ? dmu[l * m + q] : gc) : gv;
+                    s_all += d;
+                    if (q < m) {
+                        s_c += d; s_t1c1 = fmaf(d, rb[q], s_t1c1); s_t1c3 = fmaf(d, cosv[q], s_t1c3);
+                        s_sp = fmaf(d, Sp[q], s_sp); s_sn = fmaf(d, Sn[q], s_sn);
+                    } else {
+                        const int j = q - m;
+                        s_t1v = fmaf(d, cj[j], s_t1v); s_cp = fmaf(d, Cp[j], s_cp); s_cn = fmaf(d, Cn[j], s_cn);
+                    }
+                    if (q < n) s_a += d; else s_b += d;
+                }
+                s_all = wsum(s_all); s_c = wsum(s_c); s_t1c1 = wsum(s_t1c1); s_t1c3 = wsum(s_t1c3);
+                s_sp = wsum(s_sp); s_sn = wsum(s_sn); s_t1v = wsum(s_t1v); s_cp = wsum(s_cp); s_cn = wsum(s_cn);
+                s_a = wsum(s_a); s_b = wsum(s_b);
+                if (lane == 0) {
+                    gacc[o_t0 + l] += s_all;
+                    gacc[o_t1c + 4 * l] += s_c;
+                    gacc[o_t1c + 4 * l + 1] += s_t1c1;
+                    gacc[o_t1c + 4 * l + 3] += s_t1c3;
+                    gacc[o_t1v + l] += s_t1v;
+                    gw3[l] += s_sp; gw3[PP + l] += s_sn; gw3[2 * PP + l] += s_cp; gw3[3 * PP + l] += s_cn;
+                    da[l] = s_a; db2[l] = s_b;
+                }
+            }
+            __syncthreads();
+            // d t2c += da (x) mean_c(t), d t2v += db2 (x) mean_v(t); gradient of the input means
+            for (int e = tid; e < p * p; e += nt) {
+                const int k = e / p, l = e - k * p;
+                gacc[o_t2c + e] += da[k] * mcs[t * PP + l];
+                gacc[o_t2v + e] += db2[k] * mvs[t * PP + l];
+            }
+            matvec_gT(t2c, p, da, tmp1, warp, lane, nw);
+            matvec_gT(t2v, p, db2, tmp2, warp, lane, nw);
+            __syncthreads();
+            for (int l = tid; l < p; l += nt) {
+                dmc[l] = tmp1[l] / (float)m;
+                dmv[l] = tmp2[l] / (float)n;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- per CTA: push d w3 through t3 / t4, then add the accumulator to the global gradient --------------------------------
+    __syncthreads();
+    for (int e = tid; e < p * p; e += nt) {
+        const int k = e / p, l = e - k * p;
+        gacc[o_t3c + e] += gw3[k] * r4[l] + gw3[PP + k] * r4[PP + l];
+        gacc[o_t3v + e] += gw3[2 * PP + k] * r4[2 * PP + l] + gw3[3 * PP + k] * r4[3 * PP + l];
+    }
+    matvec_gT(t3c, p, gw3, tmp1, warp, lane, nw);
+    matvec_gT(t3c, p, gw3 + PP, tmp2, warp, lane, nw);
+    __syncthreads();
+    for (int l = tid; l < p; l += nt) {
+        const float tv = __ldg(t4c + l);
+        gacc[o_t4c + l] += (tv > 0.f ? tmp1[l] : 0.f) - (tv < 0.f ? tmp2[l] : 0.f);
+    }
+    __syncthreads();
+    matvec_gT(t3v, p, gw3 + 2 * PP, tmp1, warp, lane, nw);
+    matvec_gT(t3v, p, gw3 + 3 * PP, tmp2, warp, lane, nw);
+    __syncthreads();
+    for (int l = tid; l < p; l += nt) {
+        const float tv = __ldg(t4v + l);
+        gacc[o_t4v + l] += (tv > 0.f ? tmp1[l] : 0.f) - (tv < 0.f ? tmp2[l] : 0.f);
+    }
+    __syncthreads();
+    for (int e = tid; e < npar; e += nt) {
+        const float g = gacc[e];
+        if (g != 0.f) atomicAdd(a.grad + e, g);
+    }
+    if (tid == 0) atomicAdd(a.loss, loss_cta);
+}
+
+}  // namespace
+
+size_t s2v_grad_smem_bytes(int m, int n, int p, int T, int npar) { return grad_layout(m, n, p, T, npar).total * 4; }
+
+cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_count, long long smem_optin, cudaStream_t st,
+                                      const char** why) {
+    *why = "";
+    if (a.p > 64) { *why = "classifier backward: p > 64 is not supported (one 64-bit activity mask per node)"; return cudaErrorInvalidValue; }
+    const size_t smem = s2v_grad_smem_bytes(a.m, a.n, a.p, a.T, npar);
+    if ((long long)smem > smem_optin) { *why = "classifier backward: embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
+    cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_bipartite_grad_kernel, 256, smem);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
+    if (grid > a.B) grid = a.B;
+    s2v_bipartite_grad_kernel<<<(int)grid, 256, smem, st>>>(a, npar);
+    return cudaGetLastError();
+}
+
+}  // namespace ddb

@@ -101,6 +101,47 @@ class Model(nn.Module):
         self.probs = probs
         return logp
 
+    def device_backward_supported(self, A):
+        """The hand-written backward (csrc/s2v_backward.cu) covers the reference's default model -- bipartite graph, dense
+        instances, p <= 64; everything else trains through ``forward_batch_torch`` + autograd."""
+        return self.graph == 'bipartite' and self.p <= 64 and A.is_cuda and not self.force_torch
+
+    def loss_and_grad_batch(self, A, b, c, labels, weight):
+        """One training step's loss and gradient on the device: ``ddb_s2v_loss_grad_dev``.  Replaces the reference's
+        per-instance ``loss = criterion(model(x), y); loss.backward()`` accumulation (train.py:59-65) with
+        ``criterion = NLLLoss(weight, size_average=False)`` (benchmark.py:70-75).  labels [B,m] (0/1), weight = [w0, w1].
+        ACCUMULATES into ``param.grad`` like ``backward()`` does and returns the summed loss (0-dim fp64 tensor on the device)."""
+        if not (A.is_cuda and b.is_cuda and c.is_cuda):
+            raise _lib.DdbError('the classifier backward kernel needs CUDA tensors; there is no CPU fallback')
+        B, m, n = A.shape
+        dev = A.device
+        A, b, c = A.double().contiguous(), b.double().contiguous(), c.double().contiguous()
+        y = labels.to(device=dev, dtype=torch.uint8).contiguous()
+        params = self.flat_params().to(dev)
+        ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+        grad = torch.empty(params.numel(), dtype=torch.float32, device=dev)
+        loss = torch.empty((), dtype=torch.float64, device=dev)
+        flag = torch.empty(1, dtype=torch.int32, device=dev)
+        vp = lambda t: C.c_void_p(t.data_ptr())
+        rc = ctx.lib.ddb_s2v_loss_grad_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
+                                           vp(params), vp(y), float(weight[0]), float(weight[1]), vp(grad), vp(loss), vp(flag),
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        _lib.check(rc, 'ddb_s2v_loss_grad_dev')
+        self._last_grad_flag = flag
+        off = 0
+        for k in self._names:
+            q = getattr(self, k)
+            g = grad[off:off + q.numel()].view_as(q)
+            off += q.numel()
+            if q.requires_grad:
+                q.grad = g.clone() if q.grad is None else q.grad.add_(g)
+        return loss
+
+    def last_batch_was_dense(self):
+        """False if the last ``loss_and_grad_batch`` met an instance with a zero coefficient (its result is then invalid);
+        reading it synchronises with the device."""
+        return int(self._last_grad_flag.item()) == 0
+
     def forward_batch_torch(self, A, b, c):
         """Differentiable batched restatement (same arithmetic, relu-sum identity, quirks B9/B10)."""
         if self.graph == 'complete':

@@ -34,9 +34,13 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
         for data in trainloader:
             A, b, c, y = _to_device(data, dev)
             optimizer.zero_grad()
-            fx = model.forward_batch(A, b, c)                         # [B,m,2] log-probs
-            loss = criterion(fx.reshape(-1, 2), y.reshape(-1))        # summed over the batch (benchmark.py:75)
-            loss.backward()
+            if _device_backward_ok(model, criterion, A):
+                # hand-written loss + gradient kernel (csrc/s2v_backward.cu): one launch per batch
+                loss = model.loss_and_grad_batch(A, b, c, y, [float(criterion.weight[0]), float(criterion.weight[1])])
+            else:
+                fx = model.forward_batch(A, b, c)                         # [B,m,2] log-probs
+                loss = criterion(fx.reshape(-1, 2), y.reshape(-1))        # summed over the batch (benchmark.py:75)
+                loss.backward()
             parallel.allreduce_gradients(model)                       # no-op on one rank
             optimizer.step()
             running_loss += float(loss.detach())
@@ -47,6 +51,14 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
         metrics['train'].append(performance(trainloader, model, criterion, p_train))
         metrics['test'].append(performance(testloader, model, criterion, p_train))
     return metrics
+
+
+def _device_backward_ok(model, criterion, A):
+    """The device backward implements the reference's criterion (weighted NLL, summed: benchmark.py:70-75) for the
+    bipartite model on dense instances; anything else goes through autograd."""
+    return (hasattr(model, 'device_backward_supported') and model.device_backward_supported(A)
+            and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum'
+            and criterion.weight is not None and criterion.ignore_index < 0 and bool((A != 0).all()))
 
 
 def _probs_and_labels(loader, model):

@@ -130,6 +130,22 @@ int ddb_s2v_forward_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p,
                         const double *A, const double *b, const double *c, const float *params,
                         float *logp, float *probs, void *stream);
 
+/*
+ * (5) CLASSIFIER LOSS + GRADIENT -- replaces the per-instance accumulation loop of train_net
+ * (src/ml/train.py:59-66: for every instance  loss = criterion(model(x), y); loss.backward()) with its criterion
+ * NLLLoss(weight=[w0, w1], size_average=False) (src/benchmark.py:70-75) for a batch of B instances of one shape.
+ * labels[B,m] u8 (0/1) are the active-constraint labels of (2).  Outputs (device, overwritten):
+ *   grad[ddb_s2v_param_count(graph, p)] = d loss / d params in the flat order of (4), summed over the batch;
+ *   loss = summed weighted negative log-likelihood (fp64 accumulation of fp32 terms);
+ *   not_dense = 1 if an instance has a zero in A (the kernel covers the reference's dense random LPs; such an
+ *   instance contributes nothing and the caller must treat the call as failed).
+ * graph 1 ('bipartite', the reference's default, benchmark.py:166) only; p <= 64.
+ */
+int ddb_s2v_loss_grad_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p, int T,
+                          const double *A, const double *b, const double *c, const float *params,
+                          const uint8_t *labels, float w0, float w1,
+                          float *grad, double *loss, int32_t *not_dense, void *stream);
+
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 int64_t ddb_launch_count(ddb_ctx *ctx);
 

@@ -80,3 +80,39 @@ def test_gradients_equal_reference_accumulation():
         crit(lp, y[k]).backward()
     g_ref = torch.cat([q.grad.reshape(-1) for q in model.parameters()])
     assert torch.allclose(g_batch, g_ref, rtol=1e-4, atol=1e-5)
+
+
+def _grad_cases(golden_dir, graph):
+    g = np.load(os.path.join(golden_dir, 's2v_grad_%s.npz' % graph))
+    for ci in range(6):
+        pre = 'case%d_' % ci
+        dims = [int(v) for v in g[pre + 'dims']]
+        P = {k[len(pre + 'param_'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + 'param_')}
+        G = {k[len(pre + 'grad_'):]: g[k] for k in g.files if k.startswith(pre + 'grad_')}
+        yield dims, P, G, g[pre + 'A'], g[pre + 'b'], g[pre + 'c'], g[pre + 'y'], float(g[pre + 'loss']), g['weight']
+
+
+def grads_close(got, want, scale):
+    """fp32 gradients summed over m * batch nodes: 2e-4 of the largest reference entry, absolute."""
+    return np.abs(got - want).max() <= 2e-4 * scale + 1e-6
+
+
+@pytest.mark.parametrize('graph', ['complete', 'bipartite'])
+def test_batched_autograd_matches_reference_gradients(golden_dir, graph):
+    """The batched differentiable path reproduces loss and gradients of the UNMODIFIED reference model trained the
+    reference's way (tests/golden/make_s2v_grad_golden.py)."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    for dims, P, G, A, b, c, y, loss, w in _grad_cases(golden_dir, graph):
+        model = Model(graph, dims[2], dims[3], verbose_init=False)
+        model.load_state_dict(P)
+        crit = torch.nn.NLLLoss(weight=torch.from_numpy(w), reduction='sum')
+        lp = model.forward_batch_torch(torch.from_numpy(A), torch.from_numpy(b), torch.from_numpy(c))
+        l = crit(lp.reshape(-1, 2), torch.from_numpy(y.astype(np.int64)).reshape(-1))
+        l.backward()
+        assert abs(float(l) - loss) <= 1e-4 * abs(loss), dims
+        scale = max(np.abs(v).max() for v in G.values())
+        for k, q in model.named_parameters():
+            if k == 't3rc':                  # unused by the reference (quirk B10): no gradient on either side
+                assert q.grad is None or float(q.grad.abs().max()) == 0.0
+                continue
+            assert grads_close(q.grad.numpy(), G[k], scale), (graph, dims, k)

@@ -116,3 +116,62 @@ def test_drivers_end_to_end(cuda_device, tmp_path):
     sw = sweep_ratio_density(n=20, ratios=(1.5, 3.0), densities=(1.0, 0.3), per_cell=300, chunk=128)
     assert all(v['instances'] == 300 and v['optimal'] + v['unbounded'] + v['other'] == 300 for v in sw.values())
     assert sw[(3.0, 1.0)]['optimal'] > sw[(1.5, 1.0)]['optimal']        # more rows -> fewer unbounded instances (Wendel)
+
+
+def _grad_cases(golden_dir, graph):
+    g = np.load(os.path.join(golden_dir, 's2v_grad_%s.npz' % graph))
+    for ci in range(6):
+        pre = 'case%d_' % ci
+        dims = [int(v) for v in g[pre + 'dims']]
+        P = {k[len(pre + 'param_'):]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + 'param_')}
+        G = {k[len(pre + 'grad_'):]: g[k] for k in g.files if k.startswith(pre + 'grad_')}
+        yield dims, P, G, g[pre + 'A'], g[pre + 'b'], g[pre + 'c'], g[pre + 'y'], float(g[pre + 'loss']), g['weight']
+
+
+def test_backward_kernel_matches_reference_gradients(cuda_device, golden_dir):
+    """ddb_s2v_loss_grad_dev against loss + gradients of the UNMODIFIED reference model accumulated the reference's way
+    (tests/golden/make_s2v_grad_golden.py).  fp32: 2e-4 of the largest gradient entry."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    for dims, P, G, A, b, c, y, loss, w in _grad_cases(golden_dir, 'bipartite'):
+        model = Model('bipartite', dims[2], dims[3], on_cuda=True, verbose_init=False)
+        model.load_state_dict(P)
+        model.zero_grad()
+        l = model.loss_and_grad_batch(torch.from_numpy(A).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(c).cuda(),
+                                      torch.from_numpy(y).cuda(), [float(w[0]), float(w[1])])
+        assert model.last_batch_was_dense()
+        assert abs(float(l) - loss) <= 1e-4 * abs(loss), dims
+        scale = max(np.abs(v).max() for v in G.values())
+        for k, q in model.named_parameters():
+            assert np.abs(q.grad.cpu().numpy() - G[k]).max() <= 2e-4 * scale + 1e-6, (dims, k)
+
+
+@pytest.mark.parametrize('m,n,p,T,B', [(200, 100, 40, 3, 600), (50, 20, 12, 4, 1000), (37, 19, 13, 1, 77), (120, 60, 48, 2, 300)])
+def test_backward_kernel_vs_autograd_large_batch(cuda_device, m, n, p, T, B):
+    """Same loss and gradient as autograd through the batched torch restatement, on solver-produced labels."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import solver
+    torch.manual_seed(11)
+    model = Model('bipartite', p, T, on_cuda=True, verbose_init=False)
+    A, b, c = solver.generate(9, 0, B, m, n)
+    y = solver.solve_label(A, b, c)['labels']
+    w = [0.3, 0.7]
+    model.zero_grad()
+    l_dev = model.loss_and_grad_batch(A, b, c, y, w)
+    assert model.last_batch_was_dense()
+    g_dev = torch.cat([q.grad.reshape(-1) for q in model.parameters()]).clone()
+    model.zero_grad()
+    crit = torch.nn.NLLLoss(weight=torch.tensor(w, device='cuda'), reduction='sum')
+    l_ref = crit(model.forward_batch_torch(A, b, c).reshape(-1, 2), y.long().reshape(-1))
+    l_ref.backward()
+    g_ref = torch.cat([q.grad.reshape(-1) for q in model.parameters()])
+    assert abs(float(l_dev) - float(l_ref)) <= 2e-4 * abs(float(l_ref))
+    assert float((g_dev - g_ref).abs().max()) <= 5e-4 * float(g_ref.abs().max()) + 1e-5
+
+
+def test_backward_kernel_flags_sparse_instances(cuda_device):
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import solver
+    model = Model('bipartite', 8, 2, on_cuda=True, verbose_init=False)
+    A, b, c = solver.generate(6, 0, 8, 40, 20, density=0.5)
+    model.loss_and_grad_batch(A, b, c, torch.zeros(8, 40, dtype=torch.uint8, device='cuda'), [0.5, 0.5])
+    assert not model.last_batch_was_dense()
