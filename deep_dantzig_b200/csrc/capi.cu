@@ -53,6 +53,8 @@ struct S2vGradArgs {
     double* loss;
     int* error_flag;
 };
+cudaError_t launch_s2v_metrics(long long N, const float* logp, const float* probs, const uint8_t* labels, float thresh,
+                               float w0, float w1, double* out, unsigned int* minbits, int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_count, long long smem_optin, cudaStream_t st,
                                       const char** why);
 }  // namespace ddb
@@ -519,5 +521,21 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
         return fail(DDB_ECUDA, "s2v backward launch: %s", cudaGetErrorString(e));
     }
     ctx->launches += 1;
+    return DDB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// classifier evaluation metrics (src/ml/train.py:118-150, 174-246; src/ml/test.py:10-54)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int ddb_s2v_metrics_dev(ddb_ctx* ctx, int64_t N, const float* logp, const float* probs, const uint8_t* labels,
+                                   float thresh, float w0, float w1, double* out, void* stream) {
+    if (!ctx || !probs || !labels || !out) return fail(DDB_EINVAL, "ddb_s2v_metrics_dev: NULL argument");
+    if (N < 0) return fail(DDB_EINVAL, "ddb_s2v_metrics_dev: N=%lld", (long long)N);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    const int slot = ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
+    unsigned int* minbits = reinterpret_cast<unsigned int*>(ctx->counters + 3 * slot);
+    CUDA_TRY(ddb::launch_s2v_metrics(N, logp, probs, labels, thresh, w0, w1, out, minbits, ctx->sm_count, (cudaStream_t)stream));
+    ctx->launches += 2;
     return DDB_OK;
 }

@@ -6,13 +6,14 @@ What changes: a DataLoader batch is ONE batched forward/backward (``Model.forwar
 single-instance calls; the summed loss gives the same gradient as the reference's accumulation (:60-66).  Under
 torch.distributed every rank trains on its shard of the batch and gradients are summed with one flat all-reduce.
 Batches are dicts as produced by ``ml.utils.collate_randomlp``."""
+import ctypes as C
 import time
 
 import numpy as np
 import torch
 from sklearn.metrics import roc_curve
 
-from .. import parallel
+from .. import _lib, parallel
 
 
 def _to_device(batch, dev):
@@ -77,8 +78,47 @@ def _probs_and_labels(loader, model):
     return torch.cat(ys).numpy(), torch.cat(ps).numpy()
 
 
+def _on_device(model):
+    return _model_device(model).type == 'cuda' and not getattr(model, 'force_torch', False)
+
+
+def device_metrics(model, loader, criterion=None, prob_thresh=0.5):
+    """One evaluation pass entirely on the device: batched forward kernel + ``ddb_s2v_metrics_dev`` per batch, a single
+    8-double read-back at the end.  Returns [tp, fp, tn, fn, min positive prob, weighted NLL sum, #pos, #neg]."""
+    dev = _model_device(model)
+    ctx = _lib.context(dev.index if dev.index is not None else torch.cuda.current_device())
+    w = criterion.weight if (criterion is not None and getattr(criterion, 'weight', None) is not None) else None
+    w0, w1 = (float(w[0]), float(w[1])) if w is not None else (1.0, 1.0)
+    acc = torch.zeros(8, dtype=torch.float64, device=dev)
+    acc[4] = float('inf')
+    out = torch.empty(8, dtype=torch.float64, device=dev)
+    was_training = model.training
+    model.eval()
+    with torch.no_grad():
+        for data in loader:
+            A, b, c, y = _to_device(data, dev)
+            logp = model.forward_batch_cuda(A, b, c)
+            y8 = y.to(torch.uint8).contiguous()
+            rc = ctx.lib.ddb_s2v_metrics_dev(ctx.handle, y8.numel(), C.c_void_p(logp.data_ptr()),
+                                             C.c_void_p(model.probs.data_ptr()), C.c_void_p(y8.data_ptr()),
+                                             float(prob_thresh), w0, w1, C.c_void_p(out.data_ptr()),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            _lib.check(rc, 'ddb_s2v_metrics_dev')
+            mn = torch.minimum(acc[4], out[4])
+            acc += out
+            acc[4] = mn
+    if was_training:
+        model.train()
+    return acc.cpu().numpy()
+
+
 def recall_one_threshold(loader, model):
-    """train.py:118-150: threshold of the first ROC point whose TPR is 1.0 (keeps every active constraint)."""
+    """train.py:118-150: threshold of the first ROC point whose TPR is 1.0 (keeps every active constraint).  sklearn's
+    ROC thresholds are the scores themselves, so that point is the smallest predicted probability of a positive -- which
+    is what the device pass returns."""
+    if _on_device(model):
+        r = device_metrics(model, loader)
+        return float(r[4]) if (r[6] > 0 and r[7] > 0) else 0.5
     y_true, y_prob = _probs_and_labels(loader, model)
     if (y_true == 1).sum() == 0 or (y_true == 0).sum() == 0:
         return 0.5
@@ -95,6 +135,9 @@ def get_prob_recall_one(loader, model):
 
 def performance(loader, model, criterion, prob_thresh=0.5):
     """train.py:174-246 (metric names and formulas unchanged)."""
+    if _on_device(model) and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum':
+        r = device_metrics(model, loader, criterion, prob_thresh)
+        return _metrics_dict(r[5], int(r[0]), int(r[1]), int(r[2]), int(r[3]))
     dev = _model_device(model)
     was_training = model.training
     model.eval()
@@ -110,7 +153,91 @@ def performance(loader, model, criterion, prob_thresh=0.5):
             tns += int(((y == 0) & ~pred).sum()); fns += int(((y == 1) & ~pred).sum())
     if was_training:
         model.train()
+    return _metrics_dict(total_loss, tps, fps, tns, fns)
+
+
+def _metrics_dict(total_loss, tps, fps, tns, fns):
     tot = max(tps + fps + tns + fns, 1)
-    return {'total_loss': total_loss, 'accuracy': (tps + tns) / tot, 'precision': tps / max(tps + fps, 1),
+    return {'total_loss': float(total_loss), 'accuracy': (tps + tns) / tot, 'precision': tps / max(tps + fps, 1),
             'recall': tps / max(tps + fns, 1), 'y_pos': (tps + fns) / tot, 'y_neg': (fps + tns) / tot,
             'pred_pos': (tps + fps) / tot, 'pred_neg': (tns + fns) / tot}
+
+
+def train_on_device_stream(model, optimizer, m, n, steps, batch_per_rank, key=0, weight=(0.5, 0.5), density=1.0,
+                           threshold=None, overlap=True):
+    """BASELINE.json config 5: data-parallel classifier training fed by on-GPU LP generation.
+
+    Every step, every rank (one process per GPU) runs the whole hot path on its own shard, nothing touches the host:
+      1. fused Philox generate -> solve -> label for instances [(step * W + rank) * B, ... + B) of stream `key`
+         (``ddb_generate_solve_label_dev``; the Philox counter is the global instance index, so the data seen by the job
+         does not depend on the number of ranks);
+      2. loss + gradient of the batch in one launch (``ddb_s2v_loss_grad_dev``: the reference's accumulation loop
+         train.py:59-65 with the criterion of benchmark.py:70-75; non-optimal instances carry all-zero labels exactly as
+         randomlp_dataset.py:96-102 stores them);
+      3. ONE flat all-reduce of the gradient (NCCL over NVLink; 4.6-47 KB, latency-bound) and the optimizer step.
+    With ``overlap`` the next step's generate+solve is enqueued on a side stream before the all-reduce, so the collective
+    and the classifier kernels hide behind the solver (double-buffered instance tensors).
+    Returns {'loss': per-step global mean loss per constraint node, 'lps': LPs consumed by the whole job,
+             'seconds': device-timed duration (max over ranks), 'lps_per_sec': ...}."""
+    from .. import solver
+    dev = _model_device(model)
+    if dev.type != 'cuda':
+        raise _lib.DdbError('train_on_device_stream runs on the GPU only; there is no CPU fallback')
+    rank, W = parallel.world()
+    B = int(batch_per_rank)
+    thr = _lib.DEFAULT_THRESHOLD if threshold is None else threshold
+    parallel.broadcast_parameters(model)
+    main = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev) if overlap else main
+    bufs = [solver._alloc_outputs(B, m, n, dev) for _ in range(2)]
+    for bf in bufs:
+        bf['A'] = torch.empty(B, m, n, dtype=torch.float64, device=dev)
+        bf['b'] = torch.empty(B, m, dtype=torch.float64, device=dev)
+        bf['c'] = torch.empty(B, n, dtype=torch.float64, device=dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def produce(step):
+        bf = bufs[step % 2]
+        with torch.cuda.stream(side):
+            if step >= 2:
+                side.wait_event(consumed[step % 2])
+            solver.generate_solve_label(key, (step * W + rank) * B, B, m, n, density=density, threshold=thr, device=dev,
+                                        out=bf, instances=(bf['A'], bf['b'], bf['c']))
+            ready[step % 2].record(side)
+
+    losses = torch.zeros(steps, dtype=torch.float64, device=dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if W > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize(dev)
+    t0.record(main)
+    produce(0)
+    for step in range(steps):
+        bf = bufs[step % 2]
+        main.wait_event(ready[step % 2])
+        if overlap and step + 1 < steps:
+            produce(step + 1)
+        optimizer.zero_grad()
+        loss = model.loss_and_grad_batch(bf['A'], bf['b'], bf['c'], bf['labels'], weight)
+        consumed[step % 2].record(main)
+        if W > 1:
+            flat = torch.cat([q.grad.reshape(-1) for q in model.parameters()] + [loss.reshape(1).float()])
+            torch.distributed.all_reduce(flat)
+            off = 0
+            for q in model.parameters():
+                q.grad.copy_(flat[off:off + q.numel()].view_as(q.grad))
+                off += q.numel()
+            loss = flat[off].double()
+        optimizer.step()
+        losses[step] = loss / float(W * B * m)
+        if not overlap and step + 1 < steps:
+            produce(step + 1)
+    t1.record(main)
+    torch.cuda.synchronize(dev)
+    secs = torch.tensor([t0.elapsed_time(t1) / 1e3], dtype=torch.float64, device=dev)
+    if W > 1:
+        torch.distributed.all_reduce(secs, op=torch.distributed.ReduceOp.MAX)
+    secs = float(secs.item())
+    total = steps * W * B
+    return {'loss': losses.cpu().numpy(), 'lps': total, 'seconds': secs, 'lps_per_sec': total / secs}

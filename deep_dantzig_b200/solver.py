@@ -116,13 +116,20 @@ def generate(key, first_instance, B, m, n, density=1.0, device=0, want_x0=False)
 
 
 def generate_solve_label(key, first_instance, B, m, n, density=1.0, threshold=DEFAULT_THRESHOLD, device=0,
-                         keep_instances=False, out=None):
-    """Fused generate -> solve -> label; instances are only materialised for the caller when keep_instances."""
+                         keep_instances=False, out=None, instances=None):
+    """Fused generate -> solve -> label; instances are only materialised for the caller when keep_instances (fresh
+    tensors) or when `instances` = (A, b, c) preallocated CUDA tensors are given."""
     _require_cuda()
     dev = torch.device('cuda', device) if not isinstance(device, torch.device) else device
     res = out if out is not None else _alloc_outputs(B, m, n, dev)
     A = b = c = None
-    if keep_instances:
+    if instances is not None:
+        A, b, c = instances
+        for t, shp in ((A, (B, m, n)), (b, (B, m)), (c, (B, n))):
+            if not (t.is_cuda and t.dtype == torch.float64 and t.is_contiguous() and tuple(t.shape) == shp):
+                raise ValueError('instances must be contiguous float64 CUDA tensors A[B,m,n], b[B,m], c[B,n]')
+        keep_instances = True
+    elif keep_instances:
         A = torch.empty(B, m, n, dtype=torch.float64, device=dev)
         b = torch.empty(B, m, dtype=torch.float64, device=dev)
         c = torch.empty(B, n, dtype=torch.float64, device=dev)

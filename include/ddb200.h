@@ -146,6 +146,18 @@ int ddb_s2v_loss_grad_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int 
                           const uint8_t *labels, float w0, float w1,
                           float *grad, double *loss, int32_t *not_dense, void *stream);
 
+/*
+ * (6) CLASSIFIER EVALUATION METRICS -- replaces the host side of the per-epoch evaluation: the recall-1 threshold
+ * taken from sklearn's roc_curve (src/ml/train.py:118-150; the first ROC threshold with TPR == 1.0 is the smallest
+ * predicted probability of a positive) and the confusion-matrix loop of performance() (train.py:174-246) /
+ * get_accuracy (src/ml/test.py:10-54).  One streaming pass over N = B*m constraint nodes.
+ * Inputs : probs[N,2] (Model.probs), logp[N,2] (nullable: loss is 0 without it), labels[N] u8, thresh, class weights.
+ * Output : out[8] fp64 on the device = { tp, fp, tn, fn  (predicted positive <=> probs[:,1] >= thresh),
+ *          min over positives of probs[:,1] (+inf if none), weighted NLL sum, #positives, #negatives }.
+ */
+int ddb_s2v_metrics_dev(ddb_ctx *ctx, int64_t N, const float *logp, const float *probs, const uint8_t *labels,
+                        float thresh, float w0, float w1, double *out, void *stream);
+
 /* Number of kernels this library has launched on the context since creation (bench.py's gpu_launches). */
 int64_t ddb_launch_count(ddb_ctx *ctx);
 

@@ -175,3 +175,65 @@ def test_backward_kernel_flags_sparse_instances(cuda_device):
     A, b, c = solver.generate(6, 0, 8, 40, 20, density=0.5)
     model.loss_and_grad_batch(A, b, c, torch.zeros(8, 40, dtype=torch.uint8, device='cuda'), [0.5, 0.5])
     assert not model.last_batch_was_dense()
+
+
+def test_device_metrics_match_sklearn_and_torch(cuda_device):
+    """ddb_s2v_metrics_dev: recall-1 threshold == sklearn's ROC rule (train.py:138-140), confusion counts and weighted
+    NLL == the torch formulas of performance() (train.py:174-246)."""
+    from sklearn.metrics import roc_curve
+    from torch.utils.data import DataLoader, TensorDataset
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml import train as tr
+    from deep_dantzig_b200 import solver
+    torch.manual_seed(2)
+    model = Model('bipartite', 12, 3, on_cuda=True, verbose_init=False)
+    A, b, c = solver.generate(3, 0, 300, 50, 20)
+    y = solver.solve_label(A, b, c)['labels'].long()
+    loader = [{'A': A[k:k + 64], 'b': b[k:k + 64], 'c': c[k:k + 64], 'y': y[k:k + 64]} for k in range(0, 300, 64)]
+    crit = torch.nn.NLLLoss(weight=torch.tensor([0.6, 0.4], device='cuda'), reduction='sum')
+    thr = tr.recall_one_threshold(loader, model)
+    with torch.no_grad():
+        logp = model.forward_batch(A, b, c)
+    probs = model.probs[..., 1].reshape(-1).cpu().numpy()
+    yt = y.reshape(-1).cpu().numpy()
+    fpr, tpr, ths = roc_curve(yt, probs, pos_label=1)
+    assert thr == float(ths[np.where(tpr == 1.0)[0][0]]) == float(probs[yt == 1].min())
+    got = tr.performance(loader, model, crit, thr)
+    pred = probs >= np.float32(thr)
+    tp, fp = int((pred & (yt == 1)).sum()), int((pred & (yt == 0)).sum())
+    tn, fn = int((~pred & (yt == 0)).sum()), int((~pred & (yt == 1)).sum())
+    assert got['recall'] == 1.0 and fn == 0
+    assert abs(got['accuracy'] - (tp + tn) / yt.size) < 1e-12 and abs(got['precision'] - tp / (tp + fp)) < 1e-12
+    assert abs(got['pred_pos'] - (tp + fp) / yt.size) < 1e-12 and abs(got['y_pos'] - (tp + fn) / yt.size) < 1e-12
+    want_loss = float(crit(logp.reshape(-1, 2), y.reshape(-1)))
+    assert abs(got['total_loss'] - want_loss) <= 1e-5 * abs(want_loss)
+
+
+def test_streaming_training_and_reduced_solve(cuda_device):
+    """Config 5 on one rank (on-GPU generation feeds the loss+gradient kernel, loss goes down) followed by config 4
+    (classifier prunes rows at the recall-1 threshold, reduced LP solved and certified; results equal the full solve)."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml import train as tr
+    from deep_dantzig_b200 import reduced, solver
+    torch.manual_seed(0)
+    model = Model('bipartite', 12, 2, on_cuda=True, verbose_init=False)
+    opt = torch.optim.SGD(model.parameters(), lr=2e-5, momentum=0.9)
+    m, n = 60, 20
+    first = None
+    for overlap in (True, False):
+        hist = tr.train_on_device_stream(model, opt, m, n, steps=60, batch_per_rank=256, key=77, weight=(0.35, 0.65), overlap=overlap)
+        assert hist['lps'] == 60 * 256 and np.isfinite(hist['loss']).all()
+        first = hist['loss'][:5].mean() if first is None else first
+    print('streaming training: loss per node %.4f -> %.4f' % (first, hist['loss'][-10:].mean()))
+    assert hist['loss'][-10:].mean() < first
+    A, b, c = solver.generate(78, 0, 2000, m, n)
+    y = solver.solve_label(A, b, c)['labels'].long()
+    loader = [{'A': A, 'b': b, 'c': c, 'y': y}]
+    thr = tr.recall_one_threshold(loader, model)
+    t = reduced.timing_forward_pass(model, A, b, c, thr)
+    assert t['status_match'] == 2000 and t['label_match'] == 2000 and t['max_rel_x_diff'] <= 1e-9
+    assert t['certified_frac_of_optimal'] == 1.0                  # recall-1 threshold on these very instances
+    assert t['rows_kept_frac'] < 1.0
+    # a threshold that drops active rows is caught by the certificate and repaired by the full re-solve
+    t2 = reduced.timing_forward_pass(model, A, b, c, min(0.999, thr + 0.25))
+    assert t2['status_match'] == 2000 and t2['label_match'] == 2000 and t2['certified_frac_of_optimal'] < 1.0
