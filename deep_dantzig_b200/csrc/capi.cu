@@ -20,6 +20,8 @@ bool tile2d_supported(int m, int n);
 cudaError_t launch_simplex_tile2d(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowreg_supported(int m, int n);
 cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
+bool rowpipe_supported(int m, int n);
+cudaError_t launch_simplex_rowpipe(const SolveArgs& a, int sm_count, cudaStream_t st);
 struct S2vArgs {
     int graph;
     long long B;
@@ -210,12 +212,14 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
         return fail(DDB_EUNSUPPORTED, "2-D register-tile kernel does not cover m=%d n=%d", m, n);
     if (plan == 4 && !ddb::regtile_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "warp-tiled register kernel does not cover m=%d n=%d", m, n);
+    if (plan == 5 && !ddb::rowpipe_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "software-pipelined row-per-thread kernel does not cover m=%d n=%d", m, n);
     return plan;
 }
 
 extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
     if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
-    if (plan < -1 || plan > 4) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
+    if (plan < -1 || plan > 5) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
     ctx->forced_plan = plan;
     return DDB_OK;
 }
@@ -299,12 +303,14 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
     a.only_flagged = 0;
     CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
 
-    if (plan == 0 || plan == 3 || plan == 4) {
-        // Register-resident kernels: row-per-thread (plan 0 default), 2-D tile (plan 3), warp-tiled (plan 4, and the
-        // fallback of plan 0 for shapes the row kernel does not cover).
+    if (plan == 0 || plan == 3 || plan == 4 || plan == 5) {
+        // Register-resident kernels: row-per-thread (plan 0 default), its software-pipelined variant (plan 5, measured
+        // slower: DESIGN.md), 2-D tile (plan 3), warp-tiled (plan 4, and the fallback of plan 0 for shapes the row
+        // kernels do not cover).
         int which = ddb::rowreg_supported(m, n) ? 1 : (ddb::tile2d_supported(m, n) ? 0 : 2);
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
+        if (plan == 5) which = 3;
         const size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count) : 0;
         if (need) {
             if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
@@ -317,6 +323,8 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
             CUDA_TRY(ddb::launch_simplex_tile2d(a, ctx->sm_count, st));
         else if (which == 1)
             CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
+        else if (which == 3)
+            CUDA_TRY(ddb::launch_simplex_rowpipe(a, ctx->sm_count, st));
         else
             CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
         if (need) {

@@ -36,6 +36,20 @@
 
 #include "common.cuh"
 
+// dev-only stage accounting (tools/rowreg_timing.cu builds with -DDDB_TIMING; never defined in the library build)
+#ifdef DDB_TIMING
+#define DDB_TSTAMP(i)                          \
+    do {                                       \
+        if (tid == 0) {                        \
+            const long long t_ = clock64();    \
+            tacc[i] += (double)(t_ - tlast);   \
+            tlast = t_;                        \
+        }                                      \
+    } while (0)
+#else
+#define DDB_TSTAMP(i)
+#endif
+
 namespace ddb {
 
 // ---- dynamic (warp-uniform) register index -> jump table -------------------------------------------------------
@@ -233,6 +247,10 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
         const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;
+#ifdef DDB_TIMING
+        double tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long tlast = clock64();
+#endif
 
         // ---- stage 0: crash order ---------------------------------------------------------------------------
         {
@@ -274,6 +292,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         int status = ST_OPTIMAL;
         int buf = 0;
 
+        DDB_TSTAMP(0);
         if (!need_generic) {
             // ---- stage 1: thread t < n loads row order[t] of [A | b]; Gauss-Jordan to the inverse --------------
             {
@@ -360,6 +379,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             }
         }
 
+        DDB_TSTAMP(1);
         if (!need_generic) {
             __syncthreads();
             // dump D' (row of x_k stored at index k; column RHS holds the x-vertex) and the column -> constraint map
@@ -402,6 +422,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                 ilam = 1.0;
             }
 
+            DDB_TSTAMP(2);
             // ---- stage 3a: phase 1 (most negative slack leaves; ratio test along its row) -------------------
             for (;;) {
                 const double s = lam * T[RHS];
@@ -482,6 +503,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             }
             __syncthreads();
 
+            DDB_TSTAMP(3);
             // ---- stage 3b: phase 2 (Dantzig) ---------------------------------------------------------------
             // Three short barriers per pivot: (A) candidates -> winner row, (B) the owner lane has published its raw
             // row, (C) rank-1 update done and the next entering column priced.  Pricing is spread over the warps
@@ -573,6 +595,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             }
         }
 
+        DDB_TSTAMP(4);
         // ---- stage 4: x, objective, slacks, labels -----------------------------------------------------------------
         __syncthreads();
         uint8_t* lab = a.labels + (size_t)lp * m;
@@ -664,6 +687,11 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             red[warp * 3 + 2] = nviol;
         }
         __syncthreads();
+        DDB_TSTAMP(5);
+#ifdef DDB_TIMING
+        if (tid == 0)
+            for (int q = 0; q < 8; ++q) a.gtab[(size_t)lp * 8 + q] = tacc[q];
+#endif
         if (tid == 0) {
             int t0 = 0, t1 = 0, t2 = 0;
             for (int w = 0; w < W; ++w) {

@@ -59,7 +59,8 @@ int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, i
  * 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau; <0 = error. */
 int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
 /* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 3 = 2-D register-tile kernel,
- * 4 = warp-tiled register kernel (both are alternatives of plan 0 kept for A/B measurements). */
+ * 4 = warp-tiled register kernel, 5 = row-per-thread kernel with software-pipelined pivots (alternatives of
+ * plan 0 kept for A/B measurements). */
 int ddb_set_solve_plan(ddb_ctx *ctx, int plan);
 
 /*

@@ -302,7 +302,7 @@ def test_dropin_dataset_and_linprog(cuda_device):
     assert len(ph) == 32 and ph[0]['lp']['A'].shape == (50, 20)
 
 
-@pytest.mark.parametrize('plan0', [0, 3, 4])
+@pytest.mark.parametrize('plan0', [0, 3, 4, 5])
 @pytest.mark.parametrize('m,n,N', [(10, 5, 300), (50, 20, 300), (100, 50, 100), (200, 100, 200)])
 def test_register_resident_and_generic_kernels_agree(cuda_device, m, n, N, plan0):
     """The three register-resident kernels (0: row per thread, 3: 2-D register tile, 4: warp-tiled) and plan 1
