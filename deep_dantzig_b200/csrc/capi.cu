@@ -22,26 +22,13 @@ bool rowreg_supported(int m, int n);
 cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowpipe_supported(int m, int n);
 cudaError_t launch_simplex_rowpipe(const SolveArgs& a, int sm_count, cudaStream_t st);
-struct S2vArgs {
-    int graph;
-    long long B;
-    int m, n, p, T;
-    const double* A;
-    const double* b;
-    const double* c;
-    const float* params;
-    float* logp;
-    float* probs;
-    int* error_flag;
-    int store_A;
-    const float* gram;
-    int gram_pitch;
-};
 bool s2v_gram_tc_supported(int m, int n);
 size_t s2v_gram_out_floats(int m);
 cudaError_t launch_s2v_gram_tc(long long B, int m, int n, const double* A, const double* b, const double* c, float* out,
                                int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_forward(const S2vArgs& a, int sm_count, long long smem_optin, cudaStream_t st, const char** why);
+bool s2v_bipartite_dense_supported(int m, int n, int p, const void* A, long long smem_optin);
+cudaError_t launch_s2v_bipartite_dense(const S2vArgs& a, int sm_count, cudaStream_t st);
 struct S2vGradArgs {
     long long B;
     int m, n, p, T;
@@ -104,6 +91,7 @@ struct ddb_ctx {
     bool scratch_in_use = false;
     DevBuf genA, genb, genc;   // fused generate->solve chunk buffers
     DevBuf gram;               // classifier: per-instance Gram row sums from the tensor-core kernel
+    DevBuf s2vflag;            // classifier: per-instance "has a zero coefficient" flags of the dense bipartite kernel
     Slot slots[kSlots];
     int forced_plan = -1;
     int64_t launches = 0;
@@ -176,6 +164,7 @@ extern "C" int ddb_destroy(ddb_ctx* ctx) {
     release(ctx->genb);
     release(ctx->genc);
     release(ctx->gram);
+    release(ctx->s2vflag);
     if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
     if (ctx->counters) cudaFree(ctx->counters);
     delete ctx;
@@ -476,6 +465,23 @@ extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, in
     a.A = A; a.b = b; a.c = c; a.params = params; a.logp = logp; a.probs = probs;
     a.error_flag = err; a.store_A = 0;
     a.gram = nullptr; a.gram_pitch = 0;
+    a.inst_flag = nullptr; a.flag_count = nullptr; a.only_flagged = 0;
+    // bipartite variant: dense instances (the reference's distribution) go through the HBM-streaming kernel; it flags
+    // instances with zero coefficients and the general kernel below then processes exactly those
+    static const bool no_dense = [] { const char* e = getenv("DDB_S2V_NO_DENSE"); return e && e[0] == '1'; }();
+    if (graph == 1 && !no_dense && ddb::s2v_bipartite_dense_supported(m, n, p, A, ctx->smem_optin)) {
+        const size_t need = (size_t)B * sizeof(int);
+        if (need > ctx->s2vflag.cap) CUDA_TRY(cudaStreamSynchronize(st));
+        int rc = ensure(ctx->s2vflag, need);
+        if (rc) return rc;
+        a.inst_flag = (int*)ctx->s2vflag.p;
+        a.flag_count = err + 1;
+        CUDA_TRY(cudaMemsetAsync(a.inst_flag, 0, need, st));
+        CUDA_TRY(cudaMemsetAsync(a.flag_count, 0, sizeof(int), st));
+        CUDA_TRY(ddb::launch_s2v_bipartite_dense(a, ctx->sm_count, st));
+        ctx->launches += 1;
+        a.only_flagged = 1;
+    }
     // complete variant: the Gram product W = G G^T (the only dense contraction of the forward) runs on the tensor cores
     // (tcgen05 kind::tf32, 3xTF32) when m + 1 <= 256; larger shapes keep the fused CUDA-core Gram inside the forward
     static const bool no_tc = [] { const char* e = getenv("DDB_S2V_NO_TC"); return e && e[0] == '1'; }();

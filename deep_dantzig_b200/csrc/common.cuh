@@ -39,6 +39,27 @@ struct SolveArgs {
     int* flag_count;           // number of instances plan 0 flagged for the generic kernel
 };
 
+// Arguments of the classifier forward kernels (s2v_forward.cu, s2v_bipartite_dense.cu).
+struct S2vArgs {
+    int graph;                 // 0 complete, 1 bipartite
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;       // flat, reference state_dict order (oracle/classifier.py: *_PARAMS)
+    float* logp;               // [B, m, 2]
+    float* probs;              // [B, m, 2] (nullable)
+    int* error_flag;           // set to 1 if a sparse instance did not fit the shared-memory plan
+    int store_A;               // bipartite general kernel: 2 = normalised A + aggregation buffer in shared memory,
+                               // 1 = aggregation buffer only (adjacency from global A), 0 = dense instances only
+    const float* gram;         // complete: [B][3][gram_pitch] Wp, Wn, wc from the tensor-core Gram kernel (nullable)
+    int gram_pitch;
+    int* inst_flag;            // bipartite: [B] set to 1 by the dense kernel for instances with a zero coefficient
+    int* flag_count;           // number of flagged instances
+    int only_flagged;          // general bipartite kernel: process only instances whose inst_flag is 1
+};
+
 // ---------------------------------------------------------------------------------------------------------
 // mbarrier + 1-D bulk TMA (cp.async.bulk -> SASS UBLKCP) helpers
 // ---------------------------------------------------------------------------------------------------------

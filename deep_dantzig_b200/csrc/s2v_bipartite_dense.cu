@@ -1,0 +1,456 @@
+// Batched forward of the reference classifier, bipartite variant, DENSE instances (the reference's random-LP
+// distribution: every coefficient of A is non-zero): one instance per CTA iteration, fp32 arithmetic on fp64 inputs,
+// HBM-bound by design -- A (8 m n bytes per instance) is read from HBM exactly once, everything else is O(p (m + n)).
+//
+// Replaces Model._forward_bipartite + _s2v_bipartite (reference src/ml/models/s2v.py:253-323, 218-251) and the
+// per-instance batch loop of ml/utils.py:3-25 for a whole batch; quirk B9 (term2 laid out variables-first) is kept.
+// Instances that contain a zero coefficient (general adjacency) are only FLAGGED here; the general kernel of
+// s2v_forward.cu processes exactly those in a second launch (capi.cu).
+//
+// Structure per instance (256 threads):
+//   1. A pass.  A is streamed in 32-row chunks by 1-D bulk TMA (cp.async.bulk -> mbarrier, two stages; the first chunks
+//      of the NEXT instance are already in flight while this instance runs its rounds and head).  Thread (row r of the
+//      chunk, column phase s in 0..3, half g in 0..1) owns the columns  g * SL + s + 4u  of its row: with a row stride
+//      of 100 doubles a half-warp (4 rows x 4 phases) touches 16 different 8-byte banks.  The 8 threads of a row are
+//      lanes of ONE warp, so the row statistics (norm, cosine with c, sums of relu(+-a)) are three xor-shuffles away
+//      and every thread knows its row's 1 / norm at once; the column statistics sum_i relu(+-a_ij / norm_i) accumulate
+//      in registers over all the rows a thread sees and are reduced once per instance.  No __syncthreads per chunk
+//      other than the one that frees the stage.
+//   2. T rounds.  On a dense instance mu . normalize(adj) is a group mean, so a round only needs the two mean vectors
+//      of the previous one: thread (l, group) sums relu(base_l(q) + y_l) over its share of the nodes, base being five
+//      FMAs on the node statistics.  Only the last round stores the constraint embeddings (p x m, fp32, shared memory).
+//   3. Head.  relu(t7 mu_c) is the one dense product per instance (p x p x m): register-tiled, thread = 4 nodes x 8
+//      outputs, 3 LDS.128 per 32 FMAs; then t8, log-softmax, 16 bytes out per constraint.
+#include "common.cuh"
+
+namespace ddb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kChunkRows = 32;
+constexpr int kStages = 2;
+constexpr int kMaxU = 16;          // most columns per thread in the A pass (template parameter U <= kMaxU): n <= 128
+
+__host__ __device__ inline int dpad4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int dpad8(int v) { return (v + 7) & ~7; }
+
+struct DenseLayout {   // byte offsets
+    size_t ring, bars, mu, t7T, feat, part, yv, small, total;
+};
+__host__ __device__ inline DenseLayout dense_layout(int m, int n, int p) {
+    const int MP = dpad4(m), PP8 = dpad8(p);
+    const int G = kThreads / p;
+    DenseLayout L;
+    size_t off = 0;
+    L.ring = off;  off += (size_t)kStages * kChunkRows * n * 8;  off = (off + 15) & ~(size_t)15;
+    L.bars = off;  off += 64;
+    L.mu = off;    off += (size_t)p * MP * 4;                    // final-round constraint embeddings [l][i]
+    L.t7T = off;   off += (size_t)p * PP8 * 4;                   // t7T[l][k] = t7[k][l]
+    L.feat = off;  off += (size_t)(4 * MP + 3 * dpad4(n)) * 4;   // rb, cos, Sp, Sn [m]; cj, Cp, Cn [n]
+    L.part = off;                                                // scratch: column partials / round partials / head partials
+    {
+        size_t a = (size_t)8 * 2 * 8 * kMaxU * 4;                // A pass: [warp][Cp|Cn][column slot]
+        size_t b = (size_t)(G > 0 ? G : 1) * 2 * PP8 * 4;        // rounds: [group][c|v][l]
+        size_t c = (size_t)(PP8 / 8) * MP * 2 * 4;               // head: [kgroup][node][2]
+        size_t mx = a > b ? a : b;
+        mx = mx > c ? mx : c;
+        off += (mx + 15) & ~(size_t)15;
+    }
+    L.yv = off;    off += (size_t)8 * PP8 * 4;                   // meanc, meanv, yv, yc, u6, w3cp.. (small p-vectors)
+    L.small = off; off += 64;
+    L.total = off;
+    return L;
+}
+
+__device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
+
+template <int U>
+__global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArgs a) {
+    extern __shared__ __align__(128) unsigned char smraw[];
+    const int m = a.m, n = a.n, p = a.p, T = a.T;
+    const int MP = dpad4(m), NP4 = dpad4(n), PP8 = dpad8(p);
+    const DenseLayout L = dense_layout(m, n, p);
+    double* ring = reinterpret_cast<double*>(smraw + L.ring);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smraw + L.bars);
+    float* mu = reinterpret_cast<float*>(smraw + L.mu);
+    float* t7T = reinterpret_cast<float*>(smraw + L.t7T);
+    float* rb = reinterpret_cast<float*>(smraw + L.feat);
+    float* cosv = rb + MP;
+    float* Sp = cosv + MP;
+    float* Sn = Sp + MP;
+    float* cj = Sn + MP;
+    float* Cp = cj + NP4;
+    float* Cn = Cp + NP4;
+    float* part = reinterpret_cast<float*>(smraw + L.part);
+    float* meanc = reinterpret_cast<float*>(smraw + L.yv);
+    float* meanv = meanc + PP8;
+    float* yv = meanv + PP8;
+    float* yc = yv + PP8;
+    float* u6 = yc + PP8;
+    float* su6 = u6 + PP8;        // [2]: t8[:, :p] . relu(u6)
+    int* sflag = reinterpret_cast<int*>(smraw + L.small);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* P = a.params;
+    const float* t0 = P;                 P += p;
+    const float* t1c = P;                P += 4 * p;
+    const float* t1v = P;                P += p;
+    const float* t2c = P;                P += p * p;
+    const float* t2v = P;                P += p * p;
+    const float* t3c = P;                P += p * p;
+    const float* t3v = P;                P += p * p;
+    const float* t4c = P;                P += p;
+    const float* t4v = P;                P += p;
+    const float* t6c = P;                P += p * p;
+    const float* t6v = P;                P += p * p;
+    const float* t7 = P;                 P += p * p;
+    const float* t8 = P;
+    const int W8 = 2 * p + 4;
+
+    // ---- once per CTA -------------------------------------------------------------------------------------------------
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(full + s, 1);
+        fence_mbar_init();
+    }
+    for (int e = tid; e < p * PP8; e += kThreads) {
+        const int l = e / PP8, k = e - l * PP8;
+        t7T[e] = (k < p) ? __ldg(t7 + k * p + l) : 0.f;
+    }
+    // round-role constants: thread (l, grp) with l = tid % p, grp = tid / p (threads beyond p * G idle in the rounds)
+    const int G = kThreads / p;
+    const int rl = tid % p, rgrp = tid / p;
+    const bool ractive = rgrp < G;
+    float kc0, kc1, kc3, kcp, kcn, kv0, kv1, kvp, kvn;
+    {
+        // w3 = t3 . relu(+-t4): four p-vectors, entry rl
+        float a_cp = 0.f, a_cn = 0.f, a_vp = 0.f, a_vn = 0.f;
+        for (int q = 0; q < p; ++q) {
+            const float c4 = __ldg(t4c + q), v4 = __ldg(t4v + q);
+            const float w3c = __ldg(t3c + rl * p + q), w3v = __ldg(t3v + rl * p + q);
+            a_cp = fmaf(w3c, relu(c4), a_cp);
+            a_cn = fmaf(w3c, relu(-c4), a_cn);
+            a_vp = fmaf(w3v, relu(v4), a_vp);
+            a_vn = fmaf(w3v, relu(-v4), a_vn);
+        }
+        kc0 = __ldg(t0 + rl) + __ldg(t1c + 4 * rl);   // is_inequality = 1
+        kc1 = __ldg(t1c + 4 * rl + 1);                // rhs'
+        kc3 = __ldg(t1c + 4 * rl + 3);                // cosine     (is_bound = 0 drops t1c[:, 2])
+        kcp = a_cp; kcn = a_cn;
+        kv0 = __ldg(t0 + rl);
+        kv1 = __ldg(t1v + rl);
+        kvp = a_vp; kvn = a_vn;
+    }
+    __syncthreads();
+
+    // ---- A-pass roles -------------------------------------------------------------------------------------------------
+    const int SL = ((n + 1) / 2 + 3) & ~3;            // columns per half (multiple of 4)
+    const int as = lane & 3, ar = (lane >> 2) & 3, ag = lane >> 4;
+    const int arow = warp * 4 + ar;                   // my row inside a chunk
+    const int col0 = ag * SL + as;                    // my columns: col0 + 4u
+    const int nchunk = (m + kChunkRows - 1) / kChunkRows;
+    const size_t row_bytes = (size_t)n * 8;
+
+    // chunk c (global index over this CTA's instances) lives in stage c % kStages; thread 0 is the TMA producer
+    long long issued = 0, consumed = 0;
+    const long long my_first = blockIdx.x;
+    const long long my_count = (a.B > my_first) ? (a.B - my_first + gridDim.x - 1) / gridDim.x : 0;
+    const long long total_chunks = my_count * nchunk;
+    auto issue = [&](long long c) {   // thread 0 only
+        const long long k = c / nchunk;
+        const int ci = (int)(c - k * nchunk);
+        const long long lp = my_first + k * gridDim.x;
+        const int rows = (m - ci * kChunkRows < kChunkRows) ? (m - ci * kChunkRows) : kChunkRows;
+        const int s = (int)(c % kStages);
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.A) + ((size_t)lp * m + (size_t)ci * kChunkRows) * row_bytes;
+        unsigned char* dst = reinterpret_cast<unsigned char*>(ring) + (size_t)s * kChunkRows * row_bytes;
+        const uint32_t bytes = (uint32_t)(rows * row_bytes);
+        fence_proxy_async();
+        mbar_expect_tx(full + s, bytes);
+        tma_load_1d(dst, src, bytes, full + s);
+    };
+    if (tid == 0)
+        for (; issued < kStages && issued < total_chunks; ++issued) issue(issued);
+
+    for (long long k = 0; k < my_count; ++k) {
+        const long long lp = my_first + k * gridDim.x;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+        for (int j = tid; j < n; j += kThreads) cj[j] = (float)cg[j];
+        if (tid == 0) *sflag = 0;
+        __syncthreads();
+        float ccol[U];              // my columns of c
+        float accp[U], accn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = col0 + 4 * u;
+            ccol[u] = (4 * u + as < SL && j < n) ? cj[j] : 0.f;
+            accp[u] = 0.f;
+            accn[u] = 0.f;
+        }
+        int sparse = 0;
+
+        // ---- 1. A pass ------------------------------------------------------------------------------------------------
+        for (int ci = 0; ci < nchunk; ++ci, ++consumed) {
+            const int s = (int)(consumed % kStages);
+            mbar_wait(full + s, (uint32_t)((consumed / kStages) & 1));
+            const int i = ci * kChunkRows + arow;
+            const bool rowok = i < m;
+            const double* rp = ring + (size_t)s * kChunkRows * n + (size_t)arow * n;
+            float x[U];
+            float ss = 0.f, cs = 0.f, sp = 0.f, sn = 0.f;
+            int nz = 0, cnt = 0;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int j = col0 + 4 * u;
+                const bool ok = rowok && (4 * u + as < SL) && (j < n);
+                const float v = ok ? (float)rp[j] : 0.f;
+                x[u] = v;
+                ss = fmaf(v, v, ss);
+                cs = fmaf(v, ccol[u], cs);
+                sp += relu(v);
+                sn += relu(-v);
+                nz += (ok && v != 0.f) ? 1 : 0;
+                cnt += ok ? 1 : 0;
+            }
+            sparse |= (nz != cnt);
+            // the 8 threads of a row are lanes {as, ag} of one warp: xor 1, 2, 16
+#pragma unroll
+            for (int off = 1; off <= 16; off = (off == 2) ? 16 : off * 2) {
+                ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                cs += __shfl_xor_sync(0xffffffffu, cs, off);
+                sp += __shfl_xor_sync(0xffffffffu, sp, off);
+                sn += __shfl_xor_sync(0xffffffffu, sn, off);
+            }
+            const float bi = rowok ? (float)bg[i] : 0.f;
+            ss = fmaf(bi, bi, ss);                                // ||[a_i | -b_i]||^2   (s2v.py:292)
+            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float xs = x[u] * inv;
+                accp[u] += relu(xs);
+                accn[u] += relu(-xs);
+            }
+            if (rowok && as == 0 && ag == 0) {
+                rb[i] = bi * inv;          // c_feats[:, 1] <- -(-b_i / norm)   (s2v.py:293)
+                cosv[i] = cs * inv;        // <a_i / norm, c>                   (s2v.py:297)
+                Sp[i] = sp * inv;
+                Sn[i] = sn * inv;
+            }
+            __syncthreads();               // every thread has finished reading stage s
+            if (tid == 0 && issued < total_chunks) { issue(issued); ++issued; }
+        }
+        // column statistics: reduce over the 4 rows of a warp (lane bits 2, 3), then over the 8 warps through shared memory
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            accp[u] += __shfl_xor_sync(0xffffffffu, accp[u], 4);
+            accn[u] += __shfl_xor_sync(0xffffffffu, accn[u], 4);
+            accp[u] += __shfl_xor_sync(0xffffffffu, accp[u], 8);
+            accn[u] += __shfl_xor_sync(0xffffffffu, accn[u], 8);
+        }
+        if (ar == 0) {
+            // slot = (ag, as, u) -> [warp][2][8 * kMaxU]
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                part[(warp * 2 + 0) * 8 * kMaxU + (ag * 4 + as) * kMaxU + u] = accp[u];
+                part[(warp * 2 + 1) * 8 * kMaxU + (ag * 4 + as) * kMaxU + u] = accn[u];
+            }
+        }
+        if (__syncthreads_or(sparse)) {
+            // general adjacency: not this kernel's job -- flag the instance for the general kernel and go on
+            if (tid == 0) {
+                a.inst_flag[lp] = 1;
+                atomicAdd(a.flag_count, 1);
+            }
+            continue;
+        }
+        for (int j = tid; j < n; j += kThreads) {
+            const int g2 = j / SL, rem = j - g2 * SL, s2 = rem & 3, u2 = rem >> 2;
+            float sp2 = 0.f, sn2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) {
+                sp2 += part[(w * 2 + 0) * 8 * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
+                sn2 += part[(w * 2 + 1) * 8 * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
+            }
+            Cp[j] = sp2;
+            Cn[j] = sn2;
+        }
+        for (int l = tid; l < PP8; l += kThreads) { yv[l] = 0.f; yc[l] = 0.f; meanc[l] = 0.f; meanv[l] = 0.f; }
+        if (T == 0)
+            for (int e = tid; e < p * MP; e += kThreads) mu[e] = 0.f;
+        __syncthreads();
+
+        // ---- 2. T rounds: only the group means travel between rounds ---------------------------------------------------------
+        for (int t = 0; t < T; ++t) {
+            const bool last = (t == T - 1);
+            float sc = 0.f, sv = 0.f;
+            if (ractive) {
+                const float ya = yv[rl], yb = yc[rl];       // node positions < n get yv, positions >= n get yc (B9)
+                for (int i = rgrp; i < m; i += G) {
+                    float val = kc0;
+                    val = fmaf(kc1, rb[i], val);
+                    val = fmaf(kc3, cosv[i], val);
+                    val = fmaf(kcp, Sp[i], val);
+                    val = fmaf(kcn, Sn[i], val);
+                    val = relu(val + (i < n ? ya : yb));
+                    sc += val;
+                    if (last) mu[rl * MP + i] = val;
+                }
+                for (int j = rgrp; j < n; j += G) {
+                    float val = kv0;
+                    val = fmaf(kv1, cj[j], val);
+                    val = fmaf(kvp, Cp[j], val);
+                    val = fmaf(kvn, Cn[j], val);
+                    val = relu(val + ((m + j) < n ? ya : yb));
+                    sv += val;
+                }
+                part[(rgrp * 2 + 0) * PP8 + rl] = sc;
+                part[(rgrp * 2 + 1) * PP8 + rl] = sv;
+            }
+            __syncthreads();
+            if (tid < p) {
+                float tc = 0.f, tv = 0.f;
+                for (int g2 = 0; g2 < G; ++g2) {
+                    tc += part[(g2 * 2 + 0) * PP8 + tid];
+                    tv += part[(g2 * 2 + 1) * PP8 + tid];
+                }
+                meanc[tid] = tc / (float)m;
+                meanv[tid] = tv / (float)n;
+            }
+            __syncthreads();
+            if (!last) {
+                // yv = t2c . mean_c, yc = t2v . mean_v: warp w computes outputs w, w + 8, ...
+                for (int o = warp; o < 2 * p; o += 8) {
+                    const int kk = (o < p) ? o : o - p;
+                    const float* Wr = ((o < p) ? t2c : t2v) + kk * p;
+                    const float* xin = (o < p) ? meanc : meanv;
+                    float acc = 0.f;
+                    for (int q = lane; q < p; q += 32) acc = fmaf(__ldg(Wr + q), xin[q], acc);
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+                    if (lane == 0) ((o < p) ? yv : yc)[kk] = acc;
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---- 3. head ---------------------------------------------------------------------------------------------------------
+        // u6 = relu(t6c mean_c + t6v mean_v); su6[c] = t8[c, :p] . u6
+        for (int o = warp; o < p; o += 8) {
+            float acc = 0.f;
+            for (int q = lane; q < p; q += 32)
+                acc = fmaf(__ldg(t6c + o * p + q), meanc[q], fmaf(__ldg(t6v + o * p + q), meanv[q], acc));
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) u6[o] = relu(acc);
+        }
+        __syncthreads();
+        if (warp < 2) {
+            float acc = 0.f;
+            for (int q = lane; q < p; q += 32) acc = fmaf(__ldg(t8 + warp * W8 + q), u6[q], acc);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) su6[warp] = acc;
+        }
+        // z = relu(t7 mu_c): thread = (node group of 4, output group of 8); partial scores per output group
+        {
+            const int NG = MP / 4, KG = PP8 / 8;
+            for (int w = tid; w < NG * KG; w += kThreads) {
+                const int ng = w % NG, kg = w / NG;
+                float acc[4][8];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) acc[q][r] = 0.f;
+                for (int l = 0; l < p; ++l) {
+                    const float4 mv = *reinterpret_cast<const float4*>(mu + l * MP + 4 * ng);
+                    const float4 w0 = *reinterpret_cast<const float4*>(t7T + l * PP8 + 8 * kg);
+                    const float4 w1 = *reinterpret_cast<const float4*>(t7T + l * PP8 + 8 * kg + 4);
+                    const float mq[4] = {mv.x, mv.y, mv.z, mv.w};
+                    const float wr[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < 8; ++r) acc[q][r] = fmaf(wr[r], mq[q], acc[q][r]);
+                }
+                float w80[8], w81[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    const int kk = 8 * kg + r;
+                    w80[r] = (kk < p) ? __ldg(t8 + p + kk) : 0.f;
+                    w81[r] = (kk < p) ? __ldg(t8 + W8 + p + kk) : 0.f;
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        const float z = relu(acc[q][r]);
+                        s0 = fmaf(w80[r], z, s0);
+                        s1 = fmaf(w81[r], z, s1);
+                    }
+                    *reinterpret_cast<float2*>(part + ((size_t)kg * MP + 4 * ng + q) * 2) = make_float2(s0, s1);
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const int KG = PP8 / 8;
+            const float c00 = __ldg(t8 + 2 * p), c01 = __ldg(t8 + 2 * p + 1), c03 = __ldg(t8 + 2 * p + 3);
+            const float c10 = __ldg(t8 + W8 + 2 * p), c11 = __ldg(t8 + W8 + 2 * p + 1), c13 = __ldg(t8 + W8 + 2 * p + 3);
+            for (int i = tid; i < m; i += kThreads) {
+                float s0 = su6[0], s1 = su6[1];
+                for (int kg = 0; kg < KG; ++kg) {
+                    const float2 v = *reinterpret_cast<const float2*>(part + ((size_t)kg * MP + i) * 2);
+                    s0 += v.x;
+                    s1 += v.y;
+                }
+                const float f1 = rb[i], f3 = cosv[i];       // c_feats = [is_inequality = 1, rhs', is_bound = 0, cosine]
+                s0 += c00 + c01 * f1 + c03 * f3;
+                s1 += c10 + c11 * f1 + c13 * f3;
+                const float mx = fmaxf(s0, s1);
+                const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
+                *reinterpret_cast<float2*>(a.logp + ((size_t)lp * m + i) * 2) = make_float2(s0 - lse, s1 - lse);
+                if (a.probs)
+                    *reinterpret_cast<float2*>(a.probs + ((size_t)lp * m + i) * 2) = make_float2(expf(s0 - lse), expf(s1 - lse));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+// Shapes the dense kernel covers; everything else (and every instance with a zero coefficient) goes to the general kernel.
+static int dense_u(int n) { return ((((n + 1) / 2 + 3) & ~3) + 3) / 4; }   // columns per thread: ceil(SL / 4)
+
+bool s2v_bipartite_dense_supported(int m, int n, int p, const void* A, long long smem_optin) {
+    if (dense_u(n) > kMaxU || p > kThreads || p < 1) return false;
+    if (((size_t)m * n * 8) % 16 != 0 || ((size_t)n * 8 * kChunkRows) % 16 != 0) return false;   // bulk-copy alignment
+    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
+    return (long long)dense_layout(m, n, p).total <= smem_optin;
+}
+
+template <int U>
+static cudaError_t launch_dense_u(const S2vArgs& a, int sm_count, cudaStream_t st) {
+    const size_t smem = dense_layout(a.m, a.n, a.p).total;
+    cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_dense_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_bipartite_dense_kernel<U>, kThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    s2v_bipartite_dense_kernel<U><<<(int)grid, kThreads, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_s2v_bipartite_dense(const S2vArgs& a, int sm_count, cudaStream_t st) {
+    const int u = dense_u(a.n);
+    if (u <= 3) return launch_dense_u<3>(a, sm_count, st);
+    if (u <= 7) return launch_dense_u<7>(a, sm_count, st);
+    if (u <= 13) return launch_dense_u<13>(a, sm_count, st);
+    return launch_dense_u<kMaxU>(a, sm_count, st);
+}
+
+}  // namespace ddb

@@ -18,21 +18,6 @@
 
 namespace ddb {
 
-struct S2vArgs {
-    int graph;                 // 0 complete, 1 bipartite
-    long long B;
-    int m, n, p, T;
-    const double* A;
-    const double* b;
-    const double* c;
-    const float* params;       // flat, reference state_dict order (oracle/classifier.py: *_PARAMS)
-    float* logp;               // [B, m, 2]
-    float* probs;              // [B, m, 2] (nullable)
-    int* error_flag;           // set to 1 if a sparse instance did not fit the shared-memory plan
-    int store_A;               // bipartite: normalised A kept in shared memory (general adjacency supported)
-    const float* gram;         // complete: [B][3][gram_pitch] Wp, Wn, wc from the tensor-core Gram kernel (nullable)
-    int gram_pitch;
-};
 
 __host__ __device__ inline int pad4(int v) { return (v + 3) & ~3; }
 
@@ -91,7 +76,9 @@ __device__ __forceinline__ void stage_transposed(const float* __restrict__ W, in
 struct BipLayout {
     size_t t2c, t2v, t7, mu, agg, An, vecs, total;   // offsets in floats
 };
-__host__ __device__ inline BipLayout bip_layout(int m, int n, int p, bool store_A) {
+// mode 2: normalised A and the aggregation buffer in shared memory; 1: aggregation buffer only (adjacency re-read from
+// global memory); 0: neither (dense instances only -- a sparse instance then gets NaN outputs and sets the error flag)
+__host__ __device__ inline BipLayout bip_layout(int m, int n, int p, int mode) {
     const int PP = pad4(p);
     BipLayout L;
     size_t off = 0;
@@ -99,19 +86,19 @@ __host__ __device__ inline BipLayout bip_layout(int m, int n, int p, bool store_
     L.t2v = off; off += (size_t)p * PP;
     L.t7 = off;  off += (size_t)p * PP;
     L.mu = off;  off += (size_t)p * (m + n);
-    L.agg = off; off += store_A ? (size_t)p * (m + n) : 0;
-    L.An = off;  off += store_A ? (size_t)m * n : 0;
+    L.agg = off; off += mode >= 1 ? (size_t)p * (m + n) : 0;
+    L.An = off;  off += mode >= 2 ? (size_t)m * n : 0;
     L.vecs = off;
     off += (size_t)6 * m + 5 * n + 16 * PP + 64;     // row/col statistics + small p-vectors
     L.total = off;
     return L;
 }
-size_t s2v_bipartite_smem_bytes(int m, int n, int p, bool store_A) { return bip_layout(m, n, p, store_A).total * 4; }
+size_t s2v_bipartite_smem_bytes(int m, int n, int p, int mode) { return bip_layout(m, n, p, mode).total * 4; }
 
 __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int m = a.m, n = a.n, p = a.p, PP = pad4(p), NP = m + n;
-    const BipLayout L = bip_layout(m, n, p, a.store_A != 0);
+    const BipLayout L = bip_layout(m, n, p, a.store_A);
     float* t2cT = sm + L.t2c;
     float* t2vT = sm + L.t2v;
     float* t7T = sm + L.t7;
@@ -178,7 +165,9 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
     small_matvec(t3v, p, r4 + 3 * PP, w3vn, warp, lane, nw);
     __syncthreads();
 
+    if (a.only_flagged && *a.flag_count == 0) return;   // the dense kernel handled every instance
     for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
+        if (a.only_flagged && a.inst_flag[lp] == 0) continue;
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
@@ -211,7 +200,7 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
                 atomicAdd(&Cp[j], fmaxf(x, 0.f));
                 atomicAdd(&Cn[j], fmaxf(-x, 0.f));
                 atomicAdd(&ccnt[j], nz);
-                if (a.store_A) An[(size_t)i * n + j] = x;
+                if (a.store_A >= 2) An[(size_t)i * n + j] = x;
             }
             cs = warp_sumf(cs); sp = warp_sumf(sp); sn = warp_sumf(sn); cnt = warp_sumf(cnt);
             if (lane == 0) {
@@ -224,13 +213,26 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
         for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
         __syncthreads();
         const bool dense = (*iflag == 0);
-        if (!dense && !a.store_A) {
+        if (!dense && a.store_A == 0) {
+            // general adjacency does not fit in shared memory for this shape: fail loudly (NaN outputs + error flag)
             if (tid == 0) *a.error_flag = 1;
+            const float qnan = __int_as_float(0x7fc00000);
+            for (int e = tid; e < 2 * m; e += nt) {
+                a.logp[(size_t)lp * m * 2 + e] = qnan;
+                if (a.probs) a.probs[(size_t)lp * m * 2 + e] = qnan;
+            }
+            __syncthreads();
+            continue;
         }
+        // adjacency test of the general path: from the shared-memory copy, else from the caller's A (fp32 cast as the
+        // reference's item tensors, s2v.py:275-283)
+        auto adjacent = [&](int i, int j) -> bool {
+            return (a.store_A >= 2) ? (An[(size_t)i * n + j] != 0.f) : ((float)Ag[(size_t)i * n + j] != 0.f);
+        };
 
         // ---- T rounds of message passing ---------------------------------------------------------------------------------
         for (int t = 0; t < a.T; ++t) {
-            if (dense || !a.store_A) {
+            if (dense) {
                 for (int l = warp; l < p; l += nw) {
                     float sc = 0.f, svv = 0.f;
                     for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
@@ -248,14 +250,14 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
                     const int l = e / n, j = e - l * n;
                     float acc = 0.f;
                     for (int i = 0; i < m; ++i)
-                        if (An[(size_t)i * n + j] != 0.f) acc += mu[l * NP + i];
+                        if (adjacent(i, j)) acc += mu[l * NP + i];
                     agg[l * NP + j] = acc / fmaxf(ccnt[j], 1e-12f);
                 }
                 for (int e = tid; e < p * m; e += nt) {
                     const int l = e / m, i = e - l * m;
                     float acc = 0.f;
                     for (int j = 0; j < n; ++j)
-                        if (An[(size_t)i * n + j] != 0.f) acc += mu[l * NP + m + j];
+                        if (adjacent(i, j)) acc += mu[l * NP + m + j];
                     agg[l * NP + n + i] = acc / fmaxf(rcnt[i], 1e-12f);
                 }
                 __syncthreads();
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
                     const int j = q - m;
                     val += __ldg(t1v + l) * cj[j] + w3vp[l] * Cp[j] + w3vn[l] * Cn[j];
                 }
-                if (dense || !a.store_A) val += (q < n) ? yv[l] : yc[l];
+                if (dense) val += (q < n) ? yv[l] : yc[l];
                 else val += mu[e];
                 mu[e] = fmaxf(val, 0.f);
             }
@@ -590,8 +592,9 @@ cudaError_t launch_s2v_forward(const S2vArgs& a0, int sm_count, long long smem_o
     S2vArgs a = a0;
     *why = "";
     if (a.graph == 1) {
-        a.store_A = (long long)s2v_bipartite_smem_bytes(a.m, a.n, a.p, true) <= smem_optin ? 1 : 0;
-        const size_t smem = s2v_bipartite_smem_bytes(a.m, a.n, a.p, a.store_A != 0);
+        a.store_A = (long long)s2v_bipartite_smem_bytes(a.m, a.n, a.p, 2) <= smem_optin ? 2
+                    : ((long long)s2v_bipartite_smem_bytes(a.m, a.n, a.p, 1) <= smem_optin ? 1 : 0);
+        const size_t smem = s2v_bipartite_smem_bytes(a.m, a.n, a.p, a.store_A);
         if ((long long)smem > smem_optin) { *why = "bipartite forward: embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
         cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

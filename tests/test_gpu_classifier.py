@@ -237,3 +237,34 @@ def test_streaming_training_and_reduced_solve(cuda_device):
     # a threshold that drops active rows is caught by the certificate and repaired by the full re-solve
     t2 = reduced.timing_forward_pass(model, A, b, c, min(0.999, thr + 0.25))
     assert t2['status_match'] == 2000 and t2['label_match'] == 2000 and t2['certified_frac_of_optimal'] < 1.0
+
+
+@pytest.mark.parametrize('m,n,p,T', [(200, 100, 40, 3), (50, 20, 12, 4), (64, 32, 13, 1), (120, 128, 64, 2), (40, 20, 7, 0)])
+def test_dense_streaming_kernel_and_flagged_instances(cuda_device, m, n, p, T):
+    """The HBM-streaming dense kernel (csrc/s2v_bipartite_dense.cu) against the oracle; instances with a zero coefficient
+    inside an otherwise dense batch are flagged on the device and take the general-adjacency kernel."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import solver
+    torch.manual_seed(21)
+    model = Model('bipartite', p, T, on_cuda=True, verbose_init=False)
+    B = 700
+    A, b, c = solver.generate(13, 0, B, m, n)
+    sparse_ids = [3, 150, 151, B - 1]
+    for k in sparse_ids:
+        A[k, (k * 7) % m, (k * 3) % n] = 0.0
+        A[k, 0, :n // 2] = 0.0
+    with torch.no_grad():
+        lp = model.forward_batch(A, b, c).cpu().numpy()
+        pr = model.probs.cpu().numpy()
+    P = {k: v.detach().cpu() for k, v in model.named_parameters()}
+    An, bn, cn = A.cpu().numpy(), b.cpu().numpy(), c.cpu().numpy()
+    for k in sparse_ids + [0, 1, 2, 149, 152, 295, 296, 400, B - 2]:
+        ref, refp = oc.forward('bipartite', P, An[k], bn[k], cn[k], T)
+        assert _close(lp[k], ref.numpy()), k
+        assert _close(pr[k], refp.numpy()), k
+    assert np.isfinite(lp).all() and np.allclose(np.exp(lp).sum(2), 1.0, atol=1e-5)
+    # the general kernel alone computes the same thing on the whole batch
+    os.environ['DDB_S2V_NO_DENSE_CHECK'] = '1'
+    with torch.no_grad():
+        lpt = model.forward_batch_torch(A, b, c).cpu().numpy()
+    assert _close(lp, lpt)
