@@ -46,7 +46,7 @@ __host__ __device__ inline DenseLayout dense_layout(int m, int n, int p) {
     L.bars = off;  off += 64;
     L.mu = off;    off += (size_t)p * MP * 4;                    // final-round constraint embeddings [l][i]
     L.t7T = off;   off += (size_t)p * PP8 * 4;                   // t7T[l][k] = t7[k][l]
-    L.feat = off;  off += (size_t)(4 * MP + 3 * dpad4(n)) * 4;   // rb, cos, Sp, Sn [m]; cj, Cp, Cn [n]
+    L.feat = off;  off += (size_t)(5 * MP + 3 * dpad4(n)) * 4;   // rb, cos, Sp, Sn, b [m]; cj, Cp, Cn [n]
     L.part = off;                                                // scratch: column partials / round partials / head partials
     {
         size_t a = (size_t)8 * 2 * 8 * kMaxU * 4;                // A pass: [warp][Cp|Cn][column slot]
@@ -64,10 +64,12 @@ __host__ __device__ inline DenseLayout dense_layout(int m, int n, int p) {
 
 __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 
-template <int U>
+// CM, CN, CP: compile-time (m, n, p) of a specialised instantiation (0 = take them from the arguments); the headline
+// shapes get one, which turns every shared-memory offset into an immediate and every node loop into straight-line code.
+template <int U, int CM, int CN, int CP>
 __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
-    const int m = a.m, n = a.n, p = a.p, T = a.T;
+    const int m = CM ? CM : a.m, n = CN ? CN : a.n, p = CP ? CP : a.p, T = a.T;
     const int MP = dpad4(m), NP4 = dpad4(n), PP8 = dpad8(p);
     const DenseLayout L = dense_layout(m, n, p);
     double* ring = reinterpret_cast<double*>(smraw + L.ring);
@@ -78,7 +80,8 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
     float* cosv = rb + MP;
     float* Sp = cosv + MP;
     float* Sn = Sp + MP;
-    float* cj = Sn + MP;
+    float* bsm = Sn + MP;
+    float* cj = bsm + MP;
     float* Cp = cj + NP4;
     float* Cn = Cp + NP4;
     float* part = reinterpret_cast<float*>(smraw + L.part);
@@ -171,21 +174,31 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
     if (tid == 0)
         for (; issued < kStages && issued < total_chunks; ++issued) issue(issued);
 
+    // static column validity of my U columns (1 / 0) and how many are padding
+    float cm[U];
+    int npad = 0;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const bool ok = (4 * u + as < SL) && (col0 + 4 * u < n);
+        cm[u] = ok ? 1.f : 0.f;
+        npad += ok ? 0 : 1;
+    }
+
     for (long long k = 0; k < my_count; ++k) {
         const long long lp = my_first + k * gridDim.x;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
         for (int j = tid; j < n; j += kThreads) cj[j] = (float)cg[j];
+        for (int i = tid; i < m; i += kThreads) bsm[i] = (float)bg[i];
         if (tid == 0) *sflag = 0;
         __syncthreads();
         float ccol[U];              // my columns of c
-        float accp[U], accn[U];
+        float accp[U], accs[U];     // column sums of relu(a') and of a' (relu(-a') = relu(a') - a')
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-            const int j = col0 + 4 * u;
-            ccol[u] = (4 * u + as < SL && j < n) ? cj[j] : 0.f;
+            ccol[u] = (cm[u] != 0.f) ? cj[col0 + 4 * u] : 0.f;
             accp[u] = 0.f;
-            accn[u] = 0.f;
+            accs[u] = 0.f;
         }
         int sparse = 0;
 
@@ -194,51 +207,54 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
             const int s = (int)(consumed % kStages);
             mbar_wait(full + s, (uint32_t)((consumed / kStages) & 1));
             const int i = ci * kChunkRows + arow;
-            const bool rowok = i < m;
-            const double* rp = ring + (size_t)s * kChunkRows * n + (size_t)arow * n;
+            const bool rowok = i < m;                             // false only in the last, partial chunk
+            const double* rp = ring + (size_t)s * kChunkRows * n + (size_t)(rowok ? arow : 0) * n;
+            const float rmask = rowok ? 1.f : 0.f;
             float x[U];
-            float ss = 0.f, cs = 0.f, sp = 0.f, sn = 0.f;
-            int nz = 0, cnt = 0;
+            float ss = 0.f, cs = 0.f, sp = 0.f, sx = 0.f;
+            int nzero = 0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int j = col0 + 4 * u;
-                const bool ok = rowok && (4 * u + as < SL) && (j < n);
-                const float v = ok ? (float)rp[j] : 0.f;
+                // padding columns read a valid entry (the row's first) and are multiplied by 0
+                const float v = (float)rp[(cm[u] != 0.f) ? col0 + 4 * u : 0] * cm[u];
                 x[u] = v;
                 ss = fmaf(v, v, ss);
                 cs = fmaf(v, ccol[u], cs);
                 sp += relu(v);
-                sn += relu(-v);
-                nz += (ok && v != 0.f) ? 1 : 0;
-                cnt += ok ? 1 : 0;
+                sx += v;
+                nzero += (v == 0.f) ? 1 : 0;
             }
-            sparse |= (nz != cnt);
+            sparse |= (rowok && nzero != npad);
             // the 8 threads of a row are lanes {as, ag} of one warp: xor 1, 2, 16
 #pragma unroll
             for (int off = 1; off <= 16; off = (off == 2) ? 16 : off * 2) {
                 ss += __shfl_xor_sync(0xffffffffu, ss, off);
                 cs += __shfl_xor_sync(0xffffffffu, cs, off);
                 sp += __shfl_xor_sync(0xffffffffu, sp, off);
-                sn += __shfl_xor_sync(0xffffffffu, sn, off);
+                sx += __shfl_xor_sync(0xffffffffu, sx, off);
             }
-            const float bi = rowok ? (float)bg[i] : 0.f;
+            const float bi = bsm[rowok ? i : 0];
             ss = fmaf(bi, bi, ss);                                // ||[a_i | -b_i]||^2   (s2v.py:292)
             const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
+            const float invm = inv * rmask;                        // rows beyond m contribute nothing
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const float xs = x[u] * inv;
+                const float xs = x[u] * invm;
                 accp[u] += relu(xs);
-                accn[u] += relu(-xs);
+                accs[u] += xs;
             }
             if (rowok && as == 0 && ag == 0) {
                 rb[i] = bi * inv;          // c_feats[:, 1] <- -(-b_i / norm)   (s2v.py:293)
                 cosv[i] = cs * inv;        // <a_i / norm, c>                   (s2v.py:297)
                 Sp[i] = sp * inv;
-                Sn[i] = sn * inv;
+                Sn[i] = (sp - sx) * inv;   // sum_j relu(-a'_ij)
             }
             __syncthreads();               // every thread has finished reading stage s
             if (tid == 0 && issued < total_chunks) { issue(issued); ++issued; }
         }
+        float accn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) accn[u] = accp[u] - accs[u];
         // column statistics: reduce over the 4 rows of a warp (lane bits 2, 3), then over the 8 warps through shared memory
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -280,29 +296,13 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
         __syncthreads();
 
         // ---- 2. T rounds: only the group means travel between rounds ---------------------------------------------------------
-        for (int t = 0; t < T; ++t) {
-            const bool last = (t == T - 1);
-            float sc = 0.f, sv = 0.f;
+        // base_l(q) (five FMAs on the node statistics) does not change between rounds: when a thread's share of the nodes
+        // fits, it is kept in registers and a round costs three instructions per node and no shared-memory traffic.
+        constexpr int GS = CP ? kThreads / CP : 0;                          // groups when the shape is compile-time
+        constexpr int RC = CM ? (CM + GS - 1) / GS : 36, RV = CN ? (CN + GS - 1) / GS : 20;
+        const bool regfit = (m <= RC * G) && (n <= RV * G);                  // uniform
+        auto round_tail = [&](float sc, float sv, bool last) {
             if (ractive) {
-                const float ya = yv[rl], yb = yc[rl];       // node positions < n get yv, positions >= n get yc (B9)
-                for (int i = rgrp; i < m; i += G) {
-                    float val = kc0;
-                    val = fmaf(kc1, rb[i], val);
-                    val = fmaf(kc3, cosv[i], val);
-                    val = fmaf(kcp, Sp[i], val);
-                    val = fmaf(kcn, Sn[i], val);
-                    val = relu(val + (i < n ? ya : yb));
-                    sc += val;
-                    if (last) mu[rl * MP + i] = val;
-                }
-                for (int j = rgrp; j < n; j += G) {
-                    float val = kv0;
-                    val = fmaf(kv1, cj[j], val);
-                    val = fmaf(kvp, Cp[j], val);
-                    val = fmaf(kvn, Cn[j], val);
-                    val = relu(val + ((m + j) < n ? ya : yb));
-                    sv += val;
-                }
                 part[(rgrp * 2 + 0) * PP8 + rl] = sc;
                 part[(rgrp * 2 + 1) * PP8 + rl] = sv;
             }
@@ -318,30 +318,113 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
             }
             __syncthreads();
             if (!last) {
-                // yv = t2c . mean_c, yc = t2v . mean_v: warp w computes outputs w, w + 8, ...
-                for (int o = warp; o < 2 * p; o += 8) {
-                    const int kk = (o < p) ? o : o - p;
-                    const float* Wr = ((o < p) ? t2c : t2v) + kk * p;
-                    const float* xin = (o < p) ? meanc : meanv;
-                    float acc = 0.f;
-                    for (int q = lane; q < p; q += 32) acc = fmaf(__ldg(Wr + q), xin[q], acc);
-#pragma unroll
-                    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-                    if (lane == 0) ((o < p) ? yv : yc)[kk] = acc;
+                // yv = t2c . mean_c, yc = t2v . mean_v: one thread per output, four partial sums
+                if (tid < 2 * p) {
+                    const int kk = (tid < p) ? tid : tid - p;
+                    const float* Wr = ((tid < p) ? t2c : t2v) + kk * p;
+                    const float* xin = (tid < p) ? meanc : meanv;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    int q = 0;
+                    for (; q + 3 < p; q += 4) {
+                        a0 = fmaf(__ldg(Wr + q), xin[q], a0);
+                        a1 = fmaf(__ldg(Wr + q + 1), xin[q + 1], a1);
+                        a2 = fmaf(__ldg(Wr + q + 2), xin[q + 2], a2);
+                        a3 = fmaf(__ldg(Wr + q + 3), xin[q + 3], a3);
+                    }
+                    for (; q < p; ++q) a0 = fmaf(__ldg(Wr + q), xin[q], a0);
+                    ((tid < p) ? yv : yc)[kk] = (a0 + a1) + (a2 + a3);
                 }
                 __syncthreads();
+            }
+        };
+        if (regfit) {
+            float bc[RC], bv[RV];
+            const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                const int i = rgrp + q * G;
+                float val = ninf;
+                if (ractive && i < m) {
+                    val = kc0;
+                    val = fmaf(kc1, rb[i], val);
+                    val = fmaf(kc3, cosv[i], val);
+                    val = fmaf(kcp, Sp[i], val);
+                    val = fmaf(kcn, Sn[i], val);
+                }
+                bc[q] = val;
+            }
+#pragma unroll
+            for (int q = 0; q < RV; ++q) {
+                const int j = rgrp + q * G;
+                float val = ninf;
+                if (ractive && j < n) {
+                    val = kv0;
+                    val = fmaf(kv1, cj[j], val);
+                    val = fmaf(kvp, Cp[j], val);
+                    val = fmaf(kvn, Cn[j], val);
+                }
+                bv[q] = val;
+            }
+            // node positions < n get yv, positions >= n get yc (quirk B9): my first qc constraint / qv variable nodes
+            const int qc = (n > rgrp) ? (n - rgrp + G - 1) / G : 0;
+            const int qv = (n - m > rgrp) ? (n - m - rgrp + G - 1) / G : 0;
+            for (int t = 0; t < T; ++t) {
+                const bool last = (t == T - 1);
+                const float ya = yv[rl], yb = yc[rl];
+                float sc = 0.f, sv = 0.f;
+#pragma unroll
+                for (int q = 0; q < RC; ++q) {
+                    const float val = relu(bc[q] + (q < qc ? ya : yb));
+                    sc += val;
+                    if (last) {
+                        const int i = rgrp + q * G;
+                        if (ractive && i < m) mu[rl * MP + i] = val;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < RV; ++q) sv += relu(bv[q] + (q < qv ? ya : yb));
+                round_tail(sc, sv, last);
+            }
+        } else {
+            for (int t = 0; t < T; ++t) {
+                const bool last = (t == T - 1);
+                float sc = 0.f, sv = 0.f;
+                if (ractive) {
+                    const float ya = yv[rl], yb = yc[rl];
+                    for (int i = rgrp; i < m; i += G) {
+                        float val = kc0;
+                        val = fmaf(kc1, rb[i], val);
+                        val = fmaf(kc3, cosv[i], val);
+                        val = fmaf(kcp, Sp[i], val);
+                        val = fmaf(kcn, Sn[i], val);
+                        val = relu(val + (i < n ? ya : yb));
+                        sc += val;
+                        if (last) mu[rl * MP + i] = val;
+                    }
+                    for (int j = rgrp; j < n; j += G) {
+                        float val = kv0;
+                        val = fmaf(kv1, cj[j], val);
+                        val = fmaf(kvp, Cp[j], val);
+                        val = fmaf(kvn, Cn[j], val);
+                        val = relu(val + ((m + j) < n ? ya : yb));
+                        sv += val;
+                    }
+                }
+                round_tail(sc, sv, last);
             }
         }
 
         // ---- 3. head ---------------------------------------------------------------------------------------------------------
         // u6 = relu(t6c mean_c + t6v mean_v); su6[c] = t8[c, :p] . u6
-        for (int o = warp; o < p; o += 8) {
-            float acc = 0.f;
-            for (int q = lane; q < p; q += 32)
-                acc = fmaf(__ldg(t6c + o * p + q), meanc[q], fmaf(__ldg(t6v + o * p + q), meanv[q], acc));
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
-            if (lane == 0) u6[o] = relu(acc);
+        if (tid < p) {
+            const float* Wc = t6c + tid * p;
+            const float* Wv = t6v + tid * p;
+            float a0 = 0.f, a1 = 0.f;
+            for (int q = 0; q < p; ++q) {
+                a0 = fmaf(__ldg(Wc + q), meanc[q], a0);
+                a1 = fmaf(__ldg(Wv + q), meanv[q], a1);
+            }
+            u6[tid] = relu(a0 + a1);
         }
         __syncthreads();
         if (warp < 2) {
@@ -430,27 +513,32 @@ bool s2v_bipartite_dense_supported(int m, int n, int p, const void* A, long long
     return (long long)dense_layout(m, n, p).total <= smem_optin;
 }
 
-template <int U>
+template <int U, int CM, int CN, int CP>
 static cudaError_t launch_dense_u(const S2vArgs& a, int sm_count, cudaStream_t st) {
+    auto kern = s2v_bipartite_dense_kernel<U, CM, CN, CP>;
     const size_t smem = dense_layout(a.m, a.n, a.p).total;
-    cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_dense_kernel<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_bipartite_dense_kernel<U>, kThreads, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     long long grid = (long long)sm_count * per_sm;
     if (grid > a.B) grid = a.B;
-    s2v_bipartite_dense_kernel<U><<<(int)grid, kThreads, smem, st>>>(a);
+    kern<<<(int)grid, kThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 cudaError_t launch_s2v_bipartite_dense(const S2vArgs& a, int sm_count, cudaStream_t st) {
+    // specialised instantiations: BASELINE.json configs[1] shape with the reference's benchmark model (p = 40,
+    // benchmark.py:166-167) and configs[0] shape with the run.py / phase_transitions model sizes (p = 12, 13)
+    if (a.m == 200 && a.n == 100 && a.p == 40) return launch_dense_u<13, 200, 100, 40>(a, sm_count, st);
+    if (a.m == 50 && a.n == 20 && a.p == 12) return launch_dense_u<3, 50, 20, 12>(a, sm_count, st);
     const int u = dense_u(a.n);
-    if (u <= 3) return launch_dense_u<3>(a, sm_count, st);
-    if (u <= 7) return launch_dense_u<7>(a, sm_count, st);
-    if (u <= 13) return launch_dense_u<13>(a, sm_count, st);
-    return launch_dense_u<kMaxU>(a, sm_count, st);
+    if (u <= 3) return launch_dense_u<3, 0, 0, 0>(a, sm_count, st);
+    if (u <= 7) return launch_dense_u<7, 0, 0, 0>(a, sm_count, st);
+    if (u <= 13) return launch_dense_u<13, 0, 0, 0>(a, sm_count, st);
+    return launch_dense_u<kMaxU, 0, 0, 0>(a, sm_count, st);
 }
 
 }  // namespace ddb
