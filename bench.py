@@ -289,6 +289,53 @@ def run_ours(args):
     h2d = Be * (M * N_VARS + M + N_VARS) * 8
     d2h = Be * (4 + N_VARS * 8 + 8 + M + 4 + 16 + 4 + 4)
 
+    # ---- second half of the hot path: batched classifier forward (and the training step's loss + gradient) over the
+    # same resident instances, reference benchmark model (bipartite, p = 40, T = 3: src/benchmark.py:166-167) ---------
+    classifier = None
+    if rank == 0:
+        from deep_dantzig_b200.ml.models.s2v import Model
+        torch.manual_seed(0)
+        model = Model('bipartite', 40, 3, on_cuda=True, verbose_init=False)
+        cev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        with torch.no_grad():
+            for _ in range(3):
+                model.forward_batch(A, b, c)
+            cev[0].record()
+            for _ in range(5):
+                model.forward_batch(A, b, c)
+            cev[1].record()
+        Bg = min(B, 8192)
+        gA, gb, gc, gy = A[:Bg], b[:Bg], c[:Bg], out['labels'][:Bg]
+        for _ in range(2):
+            model.zero_grad(); model.loss_and_grad_batch(gA, gb, gc, gy, [0.25, 0.75])
+        cev[2].record()
+        for _ in range(3):
+            model.zero_grad(); model.loss_and_grad_batch(gA, gb, gc, gy, [0.25, 0.75])
+        cev[3].record()
+        torch.cuda.synchronize()
+        f_s = cev[0].elapsed_time(cev[1]) / 5 * 1e-3
+        g_s = cev[2].elapsed_time(cev[3]) / 3 * 1e-3
+        cls_bytes = 8 * (M * N_VARS + M + N_VARS) + 16 * M          # fp64 instance in, log-probs + probs out
+        hbm_peak_c, _ = _peaks()
+        classifier = {'model': 'bipartite s2v, p=40, T=3 (reference benchmark.py:166-167)', 'instances_per_launch': B,
+                      'forward_instances_per_s': B / f_s, 'forward_ms': f_s * 1e3,
+                      'roofline': {'bound': 'hbm', 'achieved': cls_bytes * B / f_s / 1e9, 'peak': hbm_peak_c, 'unit': 'GB/s',
+                                   'frac': cls_bytes * B / f_s / 1e9 / hbm_peak_c, 'algorithmic_bytes_per_instance': cls_bytes},
+                      'loss_grad_instances_per_s': Bg / g_s, 'loss_grad_ms': g_s * 1e3, 'loss_grad_instances_per_launch': Bg}
+        if not args.no_cpu and world == 1:
+            # the reference runs its model one instance at a time on the host (ml/utils.py:3-25): the oracle port, 1 core
+            from oracle import classifier as oc
+            Pcpu = {k_: v_.detach().cpu() for k_, v_ in model.named_parameters()}
+            nsmp = 24
+            sA, sb, sc2 = A[:nsmp].cpu().numpy(), b[:nsmp].cpu().numpy(), c[:nsmp].cpu().numpy()
+            oc.forward('bipartite', Pcpu, sA[0], sb[0], sc2[0], 3)
+            tc0 = time.perf_counter()
+            for q in range(nsmp):
+                oc.forward('bipartite', Pcpu, sA[q], sb[q], sc2[q], 3)
+            dtc = time.perf_counter() - tc0
+            classifier['cpu_baseline'] = {'value': nsmp / dtc, 'unit': 'instances/s', 'cores': 1, 'kind': 'port',
+                                          'sample': '%d instances of the same batch, oracle restatement of Model.forward in torch fp32, one at a time' % nsmp}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -362,6 +409,7 @@ def run_ours(args):
                    'fraction_optimal': float((st == 2).mean()), 'fraction_unbounded': float((st == 5).mean()),
                    'value_per_optimal_lp': value * float((st == 2).mean())},
         'roofline': roofline, 'roofline_onchip': onchip, 'cpu_baseline': cpu, 'label_match': match,
+        'classifier': classifier,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'lps_per_step': Be, 'steps': e2e_steps, 'api': 'ddb_solve_label_host (pinned host buffers)'},
         'gpu_launches': int(launches), 'kernel_ms_per_step': statistics.mean(kern_ms), 'clocks': clocks,
