@@ -261,10 +261,10 @@ def run_ours(args):
     value = world * B * args.steps / (ms_total * 1e-3)
 
     # ---- end-to-end through the host-buffer C-ABI entry point (pinned host inputs, H2D + D2H timed) -----------
-    Be = args.e2e_batch
-    hA = torch.empty(Be, M, N_VARS, dtype=torch.float64).pin_memory()
-    hb = torch.empty(Be, M, dtype=torch.float64).pin_memory()
-    hc = torch.empty(Be, N_VARS, dtype=torch.float64).pin_memory()
+    Be = min(args.e2e_batch, B)
+    hA = torch.empty(Be, M, N_VARS, dtype=torch.float64, pin_memory=True)
+    hb = torch.empty(Be, M, dtype=torch.float64, pin_memory=True)
+    hc = torch.empty(Be, N_VARS, dtype=torch.float64, pin_memory=True)
     hA.copy_(A[:Be]); hb.copy_(b[:Be]); hc.copy_(c[:Be])
     torch.cuda.synchronize()
     hout = solver.SolveResult(
@@ -276,7 +276,7 @@ def run_ours(args):
     solver.solve_label_host(nA, nb_, nc, device=local, out=hout)          # warm-up (allocates the staging slots)
     if world > 1:
         dist.barrier()
-    e2e_steps = max(2, min(args.steps, 4))
+    e2e_steps = max(2, min(args.steps, 3))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         solver.solve_label_host(nA, nb_, nc, device=local, out=hout)
@@ -446,7 +446,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch', type=int, default=32768, help='LPs per GPU per step')
-    ap.add_argument('--e2e-batch', type=int, default=8192)
+    ap.add_argument('--e2e-batch', type=int, default=32768, help='LPs per end-to-end call (host buffers)')
     ap.add_argument('--cpu-sample', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     args = ap.parse_args()

@@ -345,7 +345,10 @@ extern "C" int ddb_solve_label_host(ddb_ctx* ctx, int64_t B, int m, int n, const
     if (B == 0) return DDB_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
-    int64_t chunk = (int64_t)((size_t)(256u << 20) / per_lp);
+    // chunks of ~192 MB: the copy engine is the bottleneck (PCIe ~52 GB/s vs 8(mn+m+n) bytes per LP), so the pipeline
+    // fill (first H2D) and drain (last solve) are what chunking can shrink; at least 8 LPs per SM keep the solver's
+    // persistent CTAs balanced
+    int64_t chunk = (int64_t)((size_t)(192u << 20) / per_lp);
     const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > B) chunk = B;
