@@ -82,6 +82,8 @@ __host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, in
     return L;
 }
 
+constexpr int AU = 16;   // columns per thread of the streaming A pass (n <= 128)
+
 __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, int npar) {
     extern __shared__ __align__(16) float sm[];
     const int m = a.m, n = a.n, p = a.p, T = a.T, PP = bpad4(p), NP = m + n;
@@ -157,30 +159,112 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
         }
         if (tid == 0) *iflag = 0;
         __syncthreads();
-        // ---- pass over A (as the forward kernel): row normalisation, cosines, relu row / column sums -------------------
-        for (int i = warp; i < m; i += nw) {
-            const float bi = (float)bg[i];
-            float ss = 0.f;
-            for (int j = lane; j < n; j += 32) {
-                const float x = (float)Ag[(size_t)i * n + j];
-                ss = fmaf(x, x, ss);
+        // ---- pass over A: row normalisation, cosines, relu row / column sums ---------------------------------------------------
+        if (n <= 8 * AU) {
+            // streaming layout of s2v_bipartite_dense.cu: 32-row chunks, thread = (row of the chunk, column phase s, half g)
+            // owning columns g * SL + s + 4u; the 8 threads of a row are lanes of one warp (xor 1, 2, 16), the column sums
+            // accumulate in registers over all rows; the next chunk's loads are in flight while this one is reduced
+            const int SL = ((n + 1) / 2 + 3) & ~3;
+            const int as = lane & 3, ar = (lane >> 2) & 3, ag = lane >> 4;
+            const int arow = warp * 4 + ar, col0 = ag * SL + as;
+            float cmk[AU], ccol[AU], accp[AU], accs[AU];
+            int npad = 0;
+#pragma unroll
+            for (int u = 0; u < AU; ++u) {
+                const bool ok = (4 * u + as < SL) && (col0 + 4 * u < n);
+                cmk[u] = ok ? 1.f : 0.f;
+                npad += ok ? 0 : 1;
+                ccol[u] = ok ? cj[col0 + 4 * u] : 0.f;
+                accp[u] = 0.f;
+                accs[u] = 0.f;
             }
-            ss = wsum(ss) + bi * bi;
-            const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
-            float cs = 0.f, sp = 0.f, sn = 0.f, cnt = 0.f;
-            for (int j = lane; j < n; j += 32) {
-                const float x = (float)Ag[(size_t)i * n + j] * inv;
-                cs = fmaf(x, cj[j], cs);
-                sp += fmaxf(x, 0.f);
-                sn += fmaxf(-x, 0.f);
-                cnt += (x != 0.f) ? 1.f : 0.f;
-                atomicAdd(&Cp[j], fmaxf(x, 0.f));
-                atomicAdd(&Cn[j], fmaxf(-x, 0.f));
+            const int nchunk = (m + 31) / 32;
+            double xn[AU];
+            auto load_chunk = [&](int ci) {
+                const int i = ci * 32 + arow;
+                const double* rp = Ag + (size_t)(i < m ? i : 0) * n;
+#pragma unroll
+                for (int u = 0; u < AU; ++u) xn[u] = __ldg(rp + ((cmk[u] != 0.f) ? col0 + 4 * u : 0));
+            };
+            load_chunk(0);
+            int sparse = 0;
+            for (int ci = 0; ci < nchunk; ++ci) {
+                float x[AU];
+#pragma unroll
+                for (int u = 0; u < AU; ++u) x[u] = (float)xn[u] * cmk[u];
+                if (ci + 1 < nchunk) load_chunk(ci + 1);
+                const int i = ci * 32 + arow;
+                const bool rowok = i < m;
+                float ss = 0.f, cs = 0.f, sp = 0.f, sx = 0.f;
+                int nzero = 0;
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    const float v = x[u];
+                    ss = fmaf(v, v, ss);
+                    cs = fmaf(v, ccol[u], cs);
+                    sp += fmaxf(v, 0.f);
+                    sx += v;
+                    nzero += (v == 0.f) ? 1 : 0;
+                }
+                sparse |= (rowok && nzero != npad);
+#pragma unroll
+                for (int off = 1; off <= 16; off = (off == 2) ? 16 : off * 2) {
+                    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                    cs += __shfl_xor_sync(0xffffffffu, cs, off);
+                    sp += __shfl_xor_sync(0xffffffffu, sp, off);
+                    sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                }
+                const float bi = (float)bg[rowok ? i : 0];
+                ss = fmaf(bi, bi, ss);
+                const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+                const float invm = rowok ? inv : 0.f;
+#pragma unroll
+                for (int u = 0; u < AU; ++u) {
+                    const float xs = x[u] * invm;
+                    accp[u] += fmaxf(xs, 0.f);
+                    accs[u] += xs;
+                }
+                if (rowok && as == 0 && ag == 0) {
+                    rb[i] = bi * inv; cosv[i] = cs * inv; Sp[i] = sp * inv; Sn[i] = (sp - sx) * inv;
+                }
             }
-            cs = wsum(cs); sp = wsum(sp); sn = wsum(sn); cnt = wsum(cnt);
-            if (lane == 0) {
-                rb[i] = bi * inv; cosv[i] = cs; Sp[i] = sp; Sn[i] = sn;
-                if (cnt != (float)n) *iflag = 1;
+            if (sparse) *iflag = 1;
+            // column sums: over the 4 rows of a warp by shuffles, over the 8 warps by shared-memory atomics
+#pragma unroll
+            for (int u = 0; u < AU; ++u) {
+                float cp = accp[u], cn = accp[u] - accs[u];
+                cp += __shfl_xor_sync(0xffffffffu, cp, 4); cn += __shfl_xor_sync(0xffffffffu, cn, 4);
+                cp += __shfl_xor_sync(0xffffffffu, cp, 8); cn += __shfl_xor_sync(0xffffffffu, cn, 8);
+                if (ar == 0 && cmk[u] != 0.f) {
+                    atomicAdd(&Cp[col0 + 4 * u], cp);
+                    atomicAdd(&Cn[col0 + 4 * u], cn);
+                }
+            }
+        } else {
+            for (int i = warp; i < m; i += nw) {
+                const float bi = (float)bg[i];
+                float ss = 0.f;
+                for (int j = lane; j < n; j += 32) {
+                    const float x = (float)Ag[(size_t)i * n + j];
+                    ss = fmaf(x, x, ss);
+                }
+                ss = wsum(ss) + bi * bi;
+                const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+                float cs = 0.f, sp = 0.f, sn = 0.f, cnt = 0.f;
+                for (int j = lane; j < n; j += 32) {
+                    const float x = (float)Ag[(size_t)i * n + j] * inv;
+                    cs = fmaf(x, cj[j], cs);
+                    sp += fmaxf(x, 0.f);
+                    sn += fmaxf(-x, 0.f);
+                    cnt += (x != 0.f) ? 1.f : 0.f;
+                    atomicAdd(&Cp[j], fmaxf(x, 0.f));
+                    atomicAdd(&Cn[j], fmaxf(-x, 0.f));
+                }
+                cs = wsum(cs); sp = wsum(sp); sn = wsum(sn); cnt = wsum(cnt);
+                if (lane == 0) {
+                    rb[i] = bi * inv; cosv[i] = cs; Sp[i] = sp; Sn[i] = sn;
+                    if (cnt != (float)n) *iflag = 1;
+                }
             }
         }
         for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
