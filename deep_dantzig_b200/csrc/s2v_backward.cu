@@ -62,7 +62,7 @@ __device__ __forceinline__ void matvec_gT(const float* __restrict__ W, int p, co
 }
 
 struct GradLayout {          // offsets in floats
-    size_t t7T, t7N, mu, zr, dmu, gacc, mask, vecs, total;
+    size_t t7T, t7N, mu, zr, dmu, gacc, mask, part, vecs, total;
 };
 __host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, int npar) {
     const int PP = bpad4(p), NP = m + n;
@@ -76,8 +76,9 @@ __host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, in
     L.gacc = off; off += (size_t)((npar + 3) & ~3);
     off = (off + 1) & ~(size_t)1;
     L.mask = off; off += (size_t)2 * T * NP;                       // one 64-bit mask per (round, node)
+    L.part = off; off += (size_t)12 * (256 / (p < 1 ? 1 : p) + 1) * PP;   // [group][12 sums][l]: register-path round reductions
     L.vecs = off;
-    off += (size_t)8 * m + 5 * n + (size_t)(24 + 2 * T) * PP + 64;
+    off += (size_t)8 * m + 5 * n + (size_t)(24 + 4 * T) * PP + 64;
     L.total = off;
     return L;
 }
@@ -107,6 +108,9 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
     float* gw3 = v;    v += 4 * PP;            // per-CTA accumulators of d w3cp, d w3cn, d w3vp, d w3vn
     float* mcs = v;    v += (size_t)T * PP;    // input mean_c of every round
     float* mvs = v;    v += (size_t)T * PP;    // input mean_v of every round
+    float* yvs = v;    v += (size_t)T * PP;    // t2c . mean_c added in every round (node positions < n)
+    float* ycs = v;    v += (size_t)T * PP;    // t2v . mean_v added in every round (node positions >= n)
+    float* part = sm + L.part;
     int* iflag = reinterpret_cast<int*>(v);
     (void)spare;
 
@@ -147,6 +151,15 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
     matvec_g(t3v, p, r4 + 3 * PP, w3vn, warp, lane, nw);
     __syncthreads();
     double loss_cta = 0.0;
+    // register path of the rounds: thread (l, group); RC / RV node slots per thread
+    constexpr int RC = 36, RV = 20;
+    const int G = nt / p;
+    const int rl = tid % p, rgrp = tid / p;
+    const bool ractive = rgrp < G;
+    const bool regfit = (m <= RC * G) && (n <= RV * G) && T >= 1;      // uniform
+    const float kc0 = __ldg(t0 + rl) + __ldg(t1c + 4 * rl), kc1 = __ldg(t1c + 4 * rl + 1), kc3 = __ldg(t1c + 4 * rl + 3);
+    const float kcp = w3cp[rl], kcn = w3cn[rl];
+    const float kv0 = __ldg(t0 + rl), kv1 = __ldg(t1v + rl), kvp = w3vp[rl], kvn = w3vn[rl];
 
     for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
         const double* Ag = a.A + (size_t)lp * m * n;
@@ -267,7 +280,8 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
                 }
             }
         }
-        for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
+        if (!regfit)
+            for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
         __syncthreads();
         if (*iflag) {                     // sparse instance: not handled by this kernel (uniform decision)
             if (tid == 0) *a.error_flag = 1;
@@ -275,51 +289,130 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
             continue;
         }
 
-        // ---- forward rounds, keeping the activity masks and the input means of every round -----------------------------
-        for (int t = 0; t < T; ++t) {
+        // ---- forward rounds ------------------------------------------------------------------------------------------------------
+        // Register path (shapes whose per-thread share of the nodes fits): thread (l, group) keeps base_l(q) of its nodes in
+        // registers -- five FMAs on the node statistics, the same for every round -- so a round is add / relu / sum per node,
+        // and the backward recomputes the activity of a (node, l) pair from base + y_t instead of storing masks.
+        float bc[RC], bv[RV];
+        int qc = 0, qv = 0;
+        if (regfit) {
+            const float ninf = __int_as_float(0xff800000);
+#pragma unroll
+            for (int q = 0; q < RC; ++q) {
+                const int i = rgrp + q * G;
+                float val = ninf;
+                if (ractive && i < m) {
+                    val = kc0;
+                    val = fmaf(kc1, rb[i], val); val = fmaf(kc3, cosv[i], val);
+                    val = fmaf(kcp, Sp[i], val); val = fmaf(kcn, Sn[i], val);
+                }
+                bc[q] = val;
+            }
+#pragma unroll
+            for (int q = 0; q < RV; ++q) {
+                const int j = rgrp + q * G;
+                float val = ninf;
+                if (ractive && j < n) {
+                    val = kv0;
+                    val = fmaf(kv1, cj[j], val); val = fmaf(kvp, Cp[j], val); val = fmaf(kvn, Cn[j], val);
+                }
+                bv[q] = val;
+            }
+            // node positions < n get yv, positions >= n get yc (quirk B9): my first qc constraint / qv variable nodes
+            qc = (n > rgrp) ? (n - rgrp + G - 1) / G : 0;
+            qv = (n - m > rgrp) ? (n - m - rgrp + G - 1) / G : 0;
+            for (int l = tid; l < p; l += nt) { meanc[l] = 0.f; meanv[l] = 0.f; }
+            __syncthreads();
+            for (int t = 0; t < T; ++t) {
+                const bool last = (t == T - 1);
+                // input means of this round and what they add: y = t2 . mean (one thread per output)
+                if (tid < 2 * p) {
+                    const int kk = (tid < p) ? tid : tid - p;
+                    const float* Wr = ((tid < p) ? t2c : t2v) + kk * p;
+                    const float* xin = (tid < p) ? meanc : meanv;
+                    float a0 = 0.f, a1 = 0.f;
+                    int q = 0;
+                    for (; q + 1 < p; q += 2) { a0 = fmaf(__ldg(Wr + q), xin[q], a0); a1 = fmaf(__ldg(Wr + q + 1), xin[q + 1], a1); }
+                    if (q < p) a0 = fmaf(__ldg(Wr + q), xin[q], a0);
+                    ((tid < p) ? yvs : ycs)[t * PP + kk] = a0 + a1;
+                    ((tid < p) ? mcs : mvs)[t * PP + kk] = xin[kk];
+                }
+                __syncthreads();
+                float sc = 0.f, sv = 0.f;
+                if (ractive) {
+                    const float ya = yvs[t * PP + rl], yb = ycs[t * PP + rl];
+#pragma unroll
+                    for (int q = 0; q < RC; ++q) {
+                        const float val = fmaxf(bc[q] + (q < qc ? ya : yb), 0.f);
+                        sc += val;
+                        if (last) {
+                            const int i = rgrp + q * G;
+                            if (i < m) mu[rl * NP + i] = val;
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < RV; ++q) sv += fmaxf(bv[q] + (q < qv ? ya : yb), 0.f);
+                    part[(rgrp * 12 + 0) * PP + rl] = sc;
+                    part[(rgrp * 12 + 1) * PP + rl] = sv;
+                }
+                __syncthreads();
+                if (tid < p) {
+                    float tc = 0.f, tv = 0.f;
+                    for (int g2 = 0; g2 < G; ++g2) { tc += part[(g2 * 12 + 0) * PP + tid]; tv += part[(g2 * 12 + 1) * PP + tid]; }
+                    meanc[tid] = tc / (float)m;          // means of this round's output: input of the next round / of the head
+                    meanv[tid] = tv / (float)n;
+                }
+                __syncthreads();
+            }
+        } else {
+            for (int t = 0; t < T; ++t) {
+                for (int l = warp; l < p; l += nw) {
+                    float sc = 0.f, svv = 0.f;
+                    for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
+                    for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
+                    sc = wsum(sc); svv = wsum(svv);
+                    if (lane == 0) {
+                        meanc[l] = sc / (float)m; meanv[l] = svv / (float)n;
+                        mcs[t * PP + l] = meanc[l]; mvs[t * PP + l] = meanv[l];
+                    }
+                }
+                __syncthreads();
+                matvec_g(t2c, p, meanc, yv, warp, lane, nw);
+                matvec_g(t2v, p, meanv, yc, warp, lane, nw);
+                __syncthreads();
+                for (int q = tid; q < NP; q += nt) {
+                    unsigned long long bits = 0ull;
+                    for (int l = 0; l < p; ++l) {
+                        float val = __ldg(t0 + l);
+                        if (q < m) {
+                            val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
+                            val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
+                        } else {
+                            const int j = q - m;
+                            val += __ldg(t1v + l) * cj[j] + w3vp[l] * Cp[j] + w3vn[l] * Cn[j];
+                        }
+                        val += (q < n) ? yv[l] : yc[l];
+                        if (val > 0.f) bits |= 1ull << l;
+                        mu[l * NP + q] = fmaxf(val, 0.f);
+                    }
+                    mask[(size_t)t * NP + q] = bits;
+                }
+                __syncthreads();
+            }
+
+        }
+
+        // ---- head forward: scores, loss, d scores ---------------------------------------------------------------------------
+        if (!regfit) {
             for (int l = warp; l < p; l += nw) {
                 float sc = 0.f, svv = 0.f;
                 for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
                 for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
                 sc = wsum(sc); svv = wsum(svv);
-                if (lane == 0) {
-                    meanc[l] = sc / (float)m; meanv[l] = svv / (float)n;
-                    mcs[t * PP + l] = meanc[l]; mvs[t * PP + l] = meanv[l];
-                }
-            }
-            __syncthreads();
-            matvec_g(t2c, p, meanc, yv, warp, lane, nw);
-            matvec_g(t2v, p, meanv, yc, warp, lane, nw);
-            __syncthreads();
-            for (int q = tid; q < NP; q += nt) {
-                unsigned long long bits = 0ull;
-                for (int l = 0; l < p; ++l) {
-                    float val = __ldg(t0 + l);
-                    if (q < m) {
-                        val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
-                        val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
-                    } else {
-                        const int j = q - m;
-                        val += __ldg(t1v + l) * cj[j] + w3vp[l] * Cp[j] + w3vn[l] * Cn[j];
-                    }
-                    val += (q < n) ? yv[l] : yc[l];
-                    if (val > 0.f) bits |= 1ull << l;
-                    mu[l * NP + q] = fmaxf(val, 0.f);
-                }
-                mask[(size_t)t * NP + q] = bits;
+                if (lane == 0) { meanc[l] = sc / (float)m; meanv[l] = svv / (float)n; }
             }
             __syncthreads();
         }
-
-        // ---- head forward: scores, loss, d scores ---------------------------------------------------------------------------
-        for (int l = warp; l < p; l += nw) {
-            float sc = 0.f, svv = 0.f;
-            for (int i = lane; i < m; i += 32) sc += mu[l * NP + i];
-            for (int j = lane; j < n; j += 32) svv += mu[l * NP + m + j];
-            sc = wsum(sc); svv = wsum(svv);
-            if (lane == 0) { meanc[l] = sc / (float)m; meanv[l] = svv / (float)n; }
-        }
-        __syncthreads();
         matvec_g(t6c, p, meanc, tmp1, warp, lane, nw);
         matvec_g(t6v, p, meanv, tmp2, warp, lane, nw);
         __syncthreads();
@@ -328,26 +421,63 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
             u6r[l] = fmaxf(u6pre[l], 0.f);
         }
         __syncthreads();
+        const bool tiled = ((m & 3) == 0) && ((NP & 3) == 0);     // float4 rows of mu / zr / dmu (uniform)
+        if (tiled) {
+            // z = relu(t7 mu_c): register tile, thread = 4 nodes x 4 outputs, two LDS.128 per 16 FMAs
+            const int NG = m / 4, KG = PP / 4;
+            for (int w = tid; w < NG * KG; w += nt) {
+                const int ng = w % NG, kg = w / NG;
+                float acc[4][4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+                for (int l = 0; l < p; ++l) {
+                    const float4 mv = *reinterpret_cast<const float4*>(mu + l * NP + 4 * ng);
+                    const float4 wv = *reinterpret_cast<const float4*>(t7T + l * PP + 4 * kg);
+                    const float mq[4] = {mv.x, mv.y, mv.z, mv.w};
+                    const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(wr[r], mq[q], acc[q][r]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (4 * kg + r < p)
+                        *reinterpret_cast<float4*>(zr + (4 * kg + r) * m + 4 * ng) =
+                            make_float4(fmaxf(acc[0][r], 0.f), fmaxf(acc[1][r], 0.f), fmaxf(acc[2][r], 0.f), fmaxf(acc[3][r], 0.f));
+            }
+            __syncthreads();
+        }
         for (int i = tid; i < m; i += nt) {
             float s0 = 0.f, s1 = 0.f;
             for (int l = 0; l < p; ++l) {
                 s0 = fmaf(__ldg(t8 + l), u6r[l], s0);
                 s1 = fmaf(__ldg(t8 + W8 + l), u6r[l], s1);
             }
-            for (int kb = 0; kb < PP; kb += 4) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int l = 0; l < p; ++l) {
-                    const float x = mu[l * NP + i];
-                    const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
-                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+            if (tiled) {
+                for (int k = 0; k < p; ++k) {
+                    const float z = zr[k * m + i];
+                    s0 = fmaf(__ldg(t8 + p + k), z, s0);
+                    s1 = fmaf(__ldg(t8 + W8 + p + k), z, s1);
                 }
-                const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
+            } else {
+                for (int kb = 0; kb < PP; kb += 4) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int l = 0; l < p; ++l) {
+                        const float x = mu[l * NP + i];
+                        const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
+                        a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                    }
+                    const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (kb + u < p) {
-                        zr[(kb + u) * m + i] = r[u];
-                        s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
-                        s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
+                    for (int u = 0; u < 4; ++u) {
+                        if (kb + u < p) {
+                            zr[(kb + u) * m + i] = r[u];
+                            s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
+                            s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
+                        }
                     }
                 }
             }
@@ -420,81 +550,210 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
         matvec_gT(t6c, p, du6, tmp1, warp, lane, nw);     // tmp1 = t6c^T du6
         matvec_gT(t6v, p, du6, tmp2, warp, lane, nw);     // tmp2 = t6v^T du6
         // d t7[k][l] = sum_i dz[k][i] mu[l][i]
-        for (int e = tid; e < p * p; e += nt) {
-            const int k = e / p, l = e - k * p;
-            float acc = 0.f;
-            for (int i = 0; i < m; ++i) acc = fmaf(zr[k * m + i], mu[l * NP + i], acc);
-            gacc[o_t7 + e] += acc;
+        if (tiled) {
+            // thread = (4 outputs k, one l): lanes run over l (mu rows, conflict-free LDS.128), the dz rows are broadcast
+            for (int w = tid; w < (PP / 4) * p; w += nt) {
+                const int l = w % p, k0 = (w / p) * 4;
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int i = 0; i < m; i += 4) {
+                    const float4 x = *reinterpret_cast<const float4*>(mu + l * NP + i);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (k0 + r < p) {
+                            const float4 z = *reinterpret_cast<const float4*>(zr + (k0 + r) * m + i);
+                            acc[r] = fmaf(z.x, x.x, fmaf(z.y, x.y, fmaf(z.z, x.z, fmaf(z.w, x.w, acc[r]))));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+                    if (k0 + r < p) gacc[o_t7 + (k0 + r) * p + l] += acc[r];
+            }
+        } else {
+            for (int e = tid; e < p * p; e += nt) {
+                const int k = e / p, l = e - k * p;
+                float acc = 0.f;
+                for (int i = 0; i < m; ++i) acc = fmaf(zr[k * m + i], mu[l * NP + i], acc);
+                gacc[o_t7 + e] += acc;
+            }
         }
         __syncthreads();
         // d mu_c (last round) = t7^T dz + t6c^T du6 / m
-        for (int i = tid; i < m; i += nt) {
-            for (int lb = 0; lb < PP; lb += 4) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int k = 0; k < p; ++k) {
-                    const float x = zr[k * m + i];
-                    const float4 w = *reinterpret_cast<const float4*>(t7N + k * PP + lb);
-                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
-                }
-                const float r[4] = {a0, a1, a2, a3};
+        if (tiled) {
+            // register tile: thread = 4 nodes x 4 coordinates l, two LDS.128 per 16 FMAs
+            const int NG = m / 4, LG = PP / 4;
+            for (int w = tid; w < NG * LG; w += nt) {
+                const int ng = w % NG, lg = w / NG;
+                float acc[4][4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (lb + u < p) dmu[(lb + u) * m + i] = r[u] + tmp1[lb + u] / (float)m;
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+                for (int k = 0; k < p; ++k) {
+                    const float4 zv = *reinterpret_cast<const float4*>(zr + k * m + 4 * ng);
+                    const float4 wv = *reinterpret_cast<const float4*>(t7N + k * PP + 4 * lg);
+                    const float zq[4] = {zv.x, zv.y, zv.z, zv.w};
+                    const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(wr[r], zq[q], acc[q][r]);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    if (4 * lg + r < p) {
+                        const float add = tmp1[4 * lg + r] / (float)m;
+                        *reinterpret_cast<float4*>(dmu + (4 * lg + r) * m + 4 * ng) =
+                            make_float4(acc[0][r] + add, acc[1][r] + add, acc[2][r] + add, acc[3][r] + add);
+                    }
+                }
+            }
+        } else {
+            for (int i = tid; i < m; i += nt) {
+                for (int lb = 0; lb < PP; lb += 4) {
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int k = 0; k < p; ++k) {
+                        const float x = zr[k * m + i];
+                        const float4 w = *reinterpret_cast<const float4*>(t7N + k * PP + lb);
+                        a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
+                    }
+                    const float r[4] = {a0, a1, a2, a3};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (lb + u < p) dmu[(lb + u) * m + i] = r[u] + tmp1[lb + u] / (float)m;
+                }
             }
         }
         for (int l = tid; l < p; l += nt) dmv[l] = tmp2[l] / (float)n;      // same for every variable node
         __syncthreads();
 
         // ---- rounds backward ---------------------------------------------------------------------------------------------------
-        for (int t = T - 1; t >= 0; --t) {
-            const bool last = (t == T - 1);
-            // one warp per embedding coordinate l: the linear reductions of d pre[l][:] over the nodes
-            for (int l = warp; l < p; l += nw) {
-                float s_all = 0.f, s_t1c1 = 0.f, s_t1c3 = 0.f, s_c = 0.f, s_sp = 0.f, s_sn = 0.f;
-                float s_t1v = 0.f, s_cp = 0.f, s_cn = 0.f, s_a = 0.f, s_b = 0.f;
-                const float gc = last ? 0.f : dmc[l], gv = dmv[l];
-                for (int q = lane; q < NP; q += 32) {
-                    const bool on = (mask[(size_t)t * NP + q] >> l) & 1ull;
-                    float d = 0.f;
-                    if (on) d = (q < m) ? (last ? dmu[l * m + q] : gc) : gv;
-                    s_all += d;
-                    if (q < m) {
-                        s_c += d; s_t1c1 = fmaf(d, rb[q], s_t1c1); s_t1c3 = fmaf(d, cosv[q], s_t1c3);
-                        s_sp = fmaf(d, Sp[q], s_sp); s_sn = fmaf(d, Sn[q], s_sn);
-                    } else {
-                        const int j = q - m;
-                        s_t1v = fmaf(d, cj[j], s_t1v); s_cp = fmaf(d, Cp[j], s_cp); s_cn = fmaf(d, Cn[j], s_cn);
+        if (regfit) {
+            for (int t = T - 1; t >= 0; --t) {
+                const bool last = (t == T - 1);
+                if (ractive) {
+                    const float ya = yvs[t * PP + rl], yb = ycs[t * PP + rl];
+                    const float gc = last ? 0.f : dmc[rl], gv = dmv[rl];
+                    float s_c = 0.f, s_rb = 0.f, s_cos = 0.f, s_sp = 0.f, s_sn = 0.f, s_a = 0.f, s_b = 0.f;
+                    float s_v = 0.f, s_cj = 0.f, s_cp = 0.f, s_cn = 0.f;
+#pragma unroll
+                    for (int q = 0; q < RC; ++q) {
+                        const int i = rgrp + q * G;
+                        const bool on = (bc[q] + (q < qc ? ya : yb)) > 0.f;       // -inf base of padding slots: never active
+                        float d = 0.f;
+                        if (on) d = last ? dmu[rl * m + i] : gc;
+                        const int ii = (i < m) ? i : 0;
+                        s_c += d;
+                        s_rb = fmaf(d, rb[ii], s_rb); s_cos = fmaf(d, cosv[ii], s_cos);
+                        s_sp = fmaf(d, Sp[ii], s_sp); s_sn = fmaf(d, Sn[ii], s_sn);
+                        if (q < qc) s_a += d; else s_b += d;
                     }
-                    if (q < n) s_a += d; else s_b += d;
+#pragma unroll
+                    for (int q = 0; q < RV; ++q) {
+                        const int j = rgrp + q * G;
+                        const bool on = (bv[q] + (q < qv ? ya : yb)) > 0.f;
+                        const float d = on ? gv : 0.f;
+                        const int jj = (j < n) ? j : 0;
+                        s_v += d;
+                        s_cj = fmaf(d, cj[jj], s_cj); s_cp = fmaf(d, Cp[jj], s_cp); s_cn = fmaf(d, Cn[jj], s_cn);
+                        if (q < qv) s_a += d; else s_b += d;
+                    }
+                    float* pp = part + (size_t)rgrp * 12 * PP + rl;
+                    pp[0 * PP] = s_c; pp[1 * PP] = s_rb; pp[2 * PP] = s_cos; pp[3 * PP] = s_sp; pp[4 * PP] = s_sn;
+                    pp[5 * PP] = s_a; pp[6 * PP] = s_b; pp[7 * PP] = s_v; pp[8 * PP] = s_cj; pp[9 * PP] = s_cp; pp[10 * PP] = s_cn;
                 }
-                s_all = wsum(s_all); s_c = wsum(s_c); s_t1c1 = wsum(s_t1c1); s_t1c3 = wsum(s_t1c3);
-                s_sp = wsum(s_sp); s_sn = wsum(s_sn); s_t1v = wsum(s_t1v); s_cp = wsum(s_cp); s_cn = wsum(s_cn);
-                s_a = wsum(s_a); s_b = wsum(s_b);
-                if (lane == 0) {
-                    gacc[o_t0 + l] += s_all;
-                    gacc[o_t1c + 4 * l] += s_c;
-                    gacc[o_t1c + 4 * l + 1] += s_t1c1;
-                    gacc[o_t1c + 4 * l + 3] += s_t1c3;
-                    gacc[o_t1v + l] += s_t1v;
-                    gw3[l] += s_sp; gw3[PP + l] += s_sn; gw3[2 * PP + l] += s_cp; gw3[3 * PP + l] += s_cn;
-                    da[l] = s_a; db2[l] = s_b;
+                __syncthreads();
+                if (tid < p) {
+                    float r[11];
+#pragma unroll
+                    for (int q = 0; q < 11; ++q) r[q] = 0.f;
+                    for (int g2 = 0; g2 < G; ++g2)
+#pragma unroll
+                        for (int q = 0; q < 11; ++q) r[q] += part[((size_t)g2 * 12 + q) * PP + tid];
+                    const int l = tid;
+                    gacc[o_t0 + l] += r[0] + r[7];
+                    gacc[o_t1c + 4 * l] += r[0];
+                    gacc[o_t1c + 4 * l + 1] += r[1];
+                    gacc[o_t1c + 4 * l + 3] += r[2];
+                    gacc[o_t1v + l] += r[8];
+                    gw3[l] += r[3]; gw3[PP + l] += r[4]; gw3[2 * PP + l] += r[9]; gw3[3 * PP + l] += r[10];
+                    da[l] = r[5]; db2[l] = r[6];
                 }
+                __syncthreads();
+                // d t2c += da (x) mean_c(t), d t2v += db2 (x) mean_v(t); gradient of the input means (one thread per output)
+                for (int e = tid; e < p * p; e += nt) {
+                    const int k = e / p, l = e - k * p;
+                    gacc[o_t2c + e] += da[k] * mcs[t * PP + l];
+                    gacc[o_t2v + e] += db2[k] * mvs[t * PP + l];
+                }
+                if (tid < 2 * p) {
+                    const int l = (tid < p) ? tid : tid - p;
+                    const float* W = (tid < p) ? t2c : t2v;
+                    const float* xin = (tid < p) ? da : db2;
+                    float a0 = 0.f, a1 = 0.f;
+                    int k = 0;
+                    for (; k + 1 < p; k += 2) { a0 = fmaf(__ldg(W + k * p + l), xin[k], a0); a1 = fmaf(__ldg(W + (k + 1) * p + l), xin[k + 1], a1); }
+                    if (k < p) a0 = fmaf(__ldg(W + k * p + l), xin[k], a0);
+                    ((tid < p) ? tmp1 : tmp2)[l] = a0 + a1;
+                }
+                __syncthreads();
+                for (int l = tid; l < p; l += nt) {
+                    dmc[l] = tmp1[l] / (float)m;
+                    dmv[l] = tmp2[l] / (float)n;
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            // d t2c += da (x) mean_c(t), d t2v += db2 (x) mean_v(t); gradient of the input means
-            for (int e = tid; e < p * p; e += nt) {
-                const int k = e / p, l = e - k * p;
-                gacc[o_t2c + e] += da[k] * mcs[t * PP + l];
-                gacc[o_t2v + e] += db2[k] * mvs[t * PP + l];
+        } else {
+            for (int t = T - 1; t >= 0; --t) {
+                const bool last = (t == T - 1);
+                // one warp per embedding coordinate l: the linear reductions of d pre[l][:] over the nodes
+                for (int l = warp; l < p; l += nw) {
+                    float s_all = 0.f, s_t1c1 = 0.f, s_t1c3 = 0.f, s_c = 0.f, s_sp = 0.f, s_sn = 0.f;
+                    float s_t1v = 0.f, s_cp = 0.f, s_cn = 0.f, s_a = 0.f, s_b = 0.f;
+                    const float gc = last ? 0.f : dmc[l], gv = dmv[l];
+                    for (int q = lane; q < NP; q += 32) {
+                        const bool on = (mask[(size_t)t * NP + q] >> l) & 1ull;
+                        float d = 0.f;
+                        if (on) d = (q < m) ? (last ? dmu[l * m + q] : gc) : gv;
+                        s_all += d;
+                        if (q < m) {
+                            s_c += d; s_t1c1 = fmaf(d, rb[q], s_t1c1); s_t1c3 = fmaf(d, cosv[q], s_t1c3);
+                            s_sp = fmaf(d, Sp[q], s_sp); s_sn = fmaf(d, Sn[q], s_sn);
+                        } else {
+                            const int j = q - m;
+                            s_t1v = fmaf(d, cj[j], s_t1v); s_cp = fmaf(d, Cp[j], s_cp); s_cn = fmaf(d, Cn[j], s_cn);
+                        }
+                        if (q < n) s_a += d; else s_b += d;
+                    }
+                    s_all = wsum(s_all); s_c = wsum(s_c); s_t1c1 = wsum(s_t1c1); s_t1c3 = wsum(s_t1c3);
+                    s_sp = wsum(s_sp); s_sn = wsum(s_sn); s_t1v = wsum(s_t1v); s_cp = wsum(s_cp); s_cn = wsum(s_cn);
+                    s_a = wsum(s_a); s_b = wsum(s_b);
+                    if (lane == 0) {
+                        gacc[o_t0 + l] += s_all;
+                        gacc[o_t1c + 4 * l] += s_c;
+                        gacc[o_t1c + 4 * l + 1] += s_t1c1;
+                        gacc[o_t1c + 4 * l + 3] += s_t1c3;
+                        gacc[o_t1v + l] += s_t1v;
+                        gw3[l] += s_sp; gw3[PP + l] += s_sn; gw3[2 * PP + l] += s_cp; gw3[3 * PP + l] += s_cn;
+                        da[l] = s_a; db2[l] = s_b;
+                    }
+                }
+                __syncthreads();
+                // d t2c += da (x) mean_c(t), d t2v += db2 (x) mean_v(t); gradient of the input means
+                for (int e = tid; e < p * p; e += nt) {
+                    const int k = e / p, l = e - k * p;
+                    gacc[o_t2c + e] += da[k] * mcs[t * PP + l];
+                    gacc[o_t2v + e] += db2[k] * mvs[t * PP + l];
+                }
+                matvec_gT(t2c, p, da, tmp1, warp, lane, nw);
+                matvec_gT(t2v, p, db2, tmp2, warp, lane, nw);
+                __syncthreads();
+                for (int l = tid; l < p; l += nt) {
+                    dmc[l] = tmp1[l] / (float)m;
+                    dmv[l] = tmp2[l] / (float)n;
+                }
+                __syncthreads();
             }
-            matvec_gT(t2c, p, da, tmp1, warp, lane, nw);
-            matvec_gT(t2v, p, db2, tmp2, warp, lane, nw);
-            __syncthreads();
-            for (int l = tid; l < p; l += nt) {
-                dmc[l] = tmp1[l] / (float)m;
-                dmv[l] = tmp2[l] / (float)n;
-            }
-            __syncthreads();
         }
     }
 
