@@ -247,6 +247,16 @@ static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_
     if (per_sm > by_threads) per_sm = by_threads;
     if (per_sm > 16) per_sm = 16;
     long long grid = (long long)ctx->sm_count * per_sm;
+    if (!smem_tab) {
+        // global-memory tableau: every pivot streams the live part of a CTA's slab, so the slabs of all co-resident CTAs
+        // should stay in the 126 MB L2 -- cap the grid by an L2 budget (DDB_PLAN2_L2_MB overrides, 0 = no cap)
+        static const long long l2_mb = [] { const char* e = getenv("DDB_PLAN2_L2_MB"); return e ? atoll(e) : 96ll; }();
+        if (l2_mb > 0) {
+            long long cap = (l2_mb << 20) / ((long long)m * n * (long long)sizeof(double));
+            if (cap < 8) cap = 8;
+            if (grid > cap) grid = cap;
+        }
+    }
     if (grid > a.B) grid = a.B;
     if (!smem_tab) {
         const size_t need = (size_t)grid * m * n * sizeof(double);
