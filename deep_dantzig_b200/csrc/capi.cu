@@ -19,6 +19,7 @@ size_t regtile_scratch_bytes(int m, int n, int sm_count);
 bool tile2d_supported(int m, int n);
 cudaError_t launch_simplex_tile2d(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowreg_supported(int m, int n);
+size_t rowreg_scratch_bytes(int m, int n, int sm_count);
 cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowpipe_supported(int m, int n);
 cudaError_t launch_simplex_rowpipe(const SolveArgs& a, int sm_count, cudaStream_t st);
@@ -310,7 +311,8 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
         if (plan == 5) which = 3;
-        const size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count) : 0;
+        const size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count)
+                            : (which == 1 ? ddb::rowreg_scratch_bytes(m, n, ctx->sm_count) : 0);
         if (need) {
             if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
             if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());

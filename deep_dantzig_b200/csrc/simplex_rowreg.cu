@@ -141,6 +141,15 @@ __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int W
     return L;
 }
 
+// Rare path (ill-conditioned vertex, ~0.06 % of the instances): dot product of a tableau row parked in global memory with
+// a shared-memory vector.  Not inlined, so that it does not take part in the register allocation of the pivot loops.
+template <int NC>
+__device__ __noinline__ double saved_row_dot(const double* row, const double* vec, int n) {
+    double d = 0.0;
+    for (int c = 0; c < n && c < NC - 1; ++c) d = fma(row[c], vec[c], d);
+    return d;
+}
+
 template <int NC, int W, int MINB>
 __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs a) {
     constexpr int CS = (NC + 31) / 32;      // slots of the lane-distributed column vectors
@@ -599,7 +608,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         // ---- stage 4: x, objective, slacks, labels -----------------------------------------------------------------
         __syncthreads();
         uint8_t* lab = a.labels + (size_t)lp * m;
-        int nact = 0, nties = 0, nviol = 0, nref = 0;
+        int nact = 0, nties = 0, nviol = 0;
         if (need_generic) {
             status = -1;   // re-solved by the generic kernel (capi.cu)
         } else if (status == ST_OPTIMAL) {
@@ -639,38 +648,97 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
                 const int j = lane + 32 * cs;
                 xl[cs] = (j < n) ? xbuf[j] : 0.0;
             }
-            if (warp == 0) {
-                double acc = 0.0;
+            // my row goes to the per-CTA scratch (fire-and-forget stores) before T becomes a streaming buffer: the rare
+            // ill-conditioned instance reloads it for one step of iterative refinement
+            double* tsave = a.gtab + ((size_t)blockIdx.x * NT + tid) * PD;
+            if (tid < nN) publish(tsave);
+            auto write_x_obj = [&]() {
+                if (warp == 0) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0 && a.obj) a.obj[lp] = acc;
+                }
+                if (a.x)
+                    for (int j = tid; j < n; j += NT) a.x[(size_t)lp * n + j] = xbuf[j];
+            };
+            // labels exactly as gurobi_lp.py:435-443 from the caller's A; returns whether an active (nonbasic) row has a
+            // visible residual at this x
+            auto label_pass = [&]() -> int {
+                row_dots(Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x   (T is a streaming buffer from here on)
+                __syncthreads();
+                nact = 0; nties = 0; nviol = 0;
+                int nref = 0;
+                for (int i = tid; i < m; i += NT) {
+                    const double slack = __ldg(bg + i) - gbuf[i];
+                    const double as = fabs(slack);
+                    const int active = as <= a.thr;
+                    lab[i] = (uint8_t)active;
+                    nact += active;
+                    int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
+                    const bool excl = mask && mask[i] == 0;
+                    if (!excl) tie |= (active != (basic_tile[i] < 0));
+                    nties += tie;
+                    nviol += (slack < -a.thr * 10.0);
+                    nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);
+                }
+                return nref;
+            };
+            write_x_obj();
+            const int nref = label_pass();
+            if (__syncthreads_or(nref > 0)) {
+                // ---- one step of iterative refinement on the final active set (same arithmetic as simplex_generic.cu) ------
+                // rho_j = slack of the active (nonbasic) constraint of column j at the computed x; it should be 0.  At an
+                // ill-conditioned vertex it is not: move the nonbasic slacks from rho to 0 through the tableau and correct x
+                // through the crash inverse (second-order accurate).
+                double* rho = gnn;            // the crash scores are dead by now
+                int* colpos = order;          // so is the crash order: constraint -> column where its slack is nonbasic
+                for (int j = tid; j < n; j += NT) {
+                    const int q = cvsm[j];
+                    rho[j] = __ldg(bg + q) - gbuf[q];
+                    colpos[q] = j;
+                }
+                __syncthreads();
+                if (tid < nN) sval[tid] = lam * saved_row_dot<NC>(tsave, rho, n);      // true row . rho
+                __syncthreads();
+                for (int j0 = tid; j0 < n; j0 += NT) {
+                    const int q0 = colvar0[j0];
+                    const int bt = basic_tile[q0];
+                    sig[j0] = (bt >= 0) ? sval[bt] : -rho[colpos[q0]];
+                }
+                __syncthreads();
+                {
+                    double sl[CS];
+#pragma unroll
+                    for (int cs = 0; cs < CS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        sl[cs] = (j < n) ? sig[j] : 0.0;
+                    }
+                    for (int k = warp; k < n; k += W) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int cs = 0; cs < CS; ++cs) {
+                            const int j = lane + 32 * cs;
+                            if (j < n) acc = fma(Dsm[(size_t)k * PD + j], sl[cs], acc);
+                        }
+                        acc = warp_sum(acc);
+                        if (lane == 0) xbuf[k] -= acc;
+                    }
+                }
+                __syncthreads();
 #pragma unroll
                 for (int cs = 0; cs < CS; ++cs) {
                     const int j = lane + 32 * cs;
-                    if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                    xl[cs] = (j < n) ? xbuf[j] : 0.0;
                 }
-                acc = warp_sum(acc);
-                if (lane == 0 && a.obj) a.obj[lp] = acc;
-            }
-            if (a.x)
-                for (int j = tid; j < n; j += NT) a.x[(size_t)lp * n + j] = xbuf[j];
-            row_dots(Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x
-            __syncthreads();
-            for (int i = tid; i < m; i += NT) {
-                const double slack = __ldg(bg + i) - gbuf[i];
-                const double as = fabs(slack);
-                const int active = as <= a.thr;
-                lab[i] = (uint8_t)active;
-                nact += active;
-                int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
-                const bool excl = mask && mask[i] == 0;
-                if (!excl) tie |= (active != (basic_tile[i] < 0));
-                nties += tie;
-                nviol += (slack < -a.thr * 10.0);
-                nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);   // active row with a visible residual
+                write_x_obj();
+                label_pass();
             }
         }
-        // An optimal instance whose active rows do not have (numerically) zero slack at the computed x -- an
-        // ill-conditioned vertex -- is handed to the generic kernel, which holds the tableau in memory and can run a
-        // step of iterative refinement on the final active set (simplex_generic.cu).
-        if (__syncthreads_or(nref > 0) && status == ST_OPTIMAL) status = -1;
         if (!need_generic && status != ST_OPTIMAL) {
             for (int i = tid; i < m; i += NT) lab[i] = 0;
             if (a.x)
@@ -690,7 +758,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         DDB_TSTAMP(5);
 #ifdef DDB_TIMING
         if (tid == 0)
-            for (int q = 0; q < 8; ++q) a.gtab[(size_t)lp * 8 + q] = tacc[q];
+            for (int q = 0; q < 8; ++q) a.gtab[(size_t)gridDim.x * NT * PD + (size_t)lp * 8 + q] = tacc[q];   // behind the saved rows
 #endif
         if (tid == 0) {
             int t0 = 0, t1 = 0, t2 = 0;
@@ -725,7 +793,18 @@ namespace {
 struct RowVariant {
     int NC, W, MINB;
     cudaError_t (*launch)(const SolveArgs&, int, cudaStream_t);
+    int (*ctas_per_sm)(int m, int n);
 };
+
+template <int NC, int W, int MINB>
+int row_variant_ctas_per_sm(int m, int n) {
+    auto kern = simplex_rowreg_kernel<NC, W, MINB>;
+    const size_t smem = make_row_layout(m, n, NC, W).total;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 0;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, W * 32, smem) != cudaSuccess) return 0;
+    return per_sm;
+}
 
 template <int NC, int W, int MINB>
 cudaError_t launch_row_variant(const SolveArgs& a, int sm_count, cudaStream_t st) {
@@ -745,14 +824,14 @@ cudaError_t launch_row_variant(const SolveArgs& a, int sm_count, cudaStream_t st
 
 // (columns incl. rhs, warps, min CTAs/SM).  Picked: smallest NC >= n + 1, then smallest W with 32 W >= max(n, m - n).
 const RowVariant kRowVariants[] = {
-    {8, 1, 32, launch_row_variant<8, 1, 32>},
-    {24, 1, 16, launch_row_variant<24, 1, 16>},
-    {24, 2, 8, launch_row_variant<24, 2, 8>},
-    {48, 2, 5, launch_row_variant<48, 2, 5>},
-    {48, 4, 3, launch_row_variant<48, 4, 3>},
-    {72, 4, 2, launch_row_variant<72, 4, 2>},
-    {101, 4, 2, launch_row_variant<101, 4, 2>},
-    {101, 8, 1, launch_row_variant<101, 8, 1>},
+    {8, 1, 32, launch_row_variant<8, 1, 32>, row_variant_ctas_per_sm<8, 1, 32>},
+    {24, 1, 16, launch_row_variant<24, 1, 16>, row_variant_ctas_per_sm<24, 1, 16>},
+    {24, 2, 8, launch_row_variant<24, 2, 8>, row_variant_ctas_per_sm<24, 2, 8>},
+    {48, 2, 5, launch_row_variant<48, 2, 5>, row_variant_ctas_per_sm<48, 2, 5>},
+    {48, 4, 3, launch_row_variant<48, 4, 3>, row_variant_ctas_per_sm<48, 4, 3>},
+    {72, 4, 2, launch_row_variant<72, 4, 2>, row_variant_ctas_per_sm<72, 4, 2>},
+    {101, 4, 2, launch_row_variant<101, 4, 2>, row_variant_ctas_per_sm<101, 4, 2>},
+    {101, 8, 1, launch_row_variant<101, 8, 1>, row_variant_ctas_per_sm<101, 8, 1>},
 };
 
 const RowVariant* pick_row_variant(int m, int n) {
@@ -764,6 +843,14 @@ const RowVariant* pick_row_variant(int m, int n) {
 }  // namespace
 
 bool rowreg_supported(int m, int n) { return m >= n && pick_row_variant(m, n) != nullptr; }
+
+// per-CTA scratch: one saved tableau row per thread (stage 4 parks the rows there before T becomes a streaming buffer)
+size_t rowreg_scratch_bytes(int m, int n, int sm_count) {
+    const RowVariant* v = pick_row_variant(m, n);
+    if (!v) return 0;
+    const int per_sm = v->ctas_per_sm(m, n);      // the same occupancy query the launch sizes its grid with
+    return (size_t)sm_count * (per_sm > 0 ? per_sm : 1) * (size_t)(v->W * 32) * row_pitch(v->NC) * sizeof(double);
+}
 
 cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st) {
     const RowVariant* v = pick_row_variant(a.m, a.n);

@@ -19,7 +19,11 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&A, B * m * n * 8)); CK(cudaMalloc(&b, B * m * 8)); CK(cudaMalloc(&c, B * n * 8));
     CK(cudaMalloc(&x, B * n * 8)); CK(cudaMalloc(&obj, B * 8)); CK(cudaMalloc(&status, B * 4)); CK(cudaMalloc(&nact, B * 4));
     CK(cudaMalloc(&piv, B * 16)); CK(cudaMalloc(&ties, B * 4)); CK(cudaMalloc(&viol, B * 4)); CK(cudaMalloc(&labels, B * m));
-    CK(cudaMalloc(&counter, 64)); CK(cudaMalloc(&dbg, B * 8 * 8)); CK(cudaMemset(dbg, 0, B * 8 * 8));
+    CK(cudaMalloc(&counter, 64));
+    size_t dbg_bytes = ddb::rowreg_scratch_bytes(m, n, prop.multiProcessorCount);
+    const size_t save_bytes = dbg_bytes;                 // rowreg: saved rows first, stage timers behind them
+    dbg_bytes += (size_t)B * 8 * 8;
+    CK(cudaMalloc(&dbg, dbg_bytes)); CK(cudaMemset(dbg, 0, dbg_bytes));
     int launches = 0;
     CK(ddb::launch_generate(42, 0, B, m, n, 1.0, A, b, c, nullptr, prop.multiProcessorCount, 0, &launches));
     ddb::SolveArgs a{};
@@ -47,7 +51,7 @@ int main(int argc, char** argv) {
         printf("optimal %.3f flagged %lld mean pivots crash %.1f p1 %.1f p2 %.1f\n", (double)nopt / B, flagged, pc / B, p1 / B, p2 / B);
 #ifdef DDB_TIMING
         std::vector<double> hd(B * 8);
-        cudaMemcpy(hd.data(), dbg, B * 8 * 8, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hd.data(), reinterpret_cast<char*>(dbg) + (which == 0 ? save_bytes : 0), B * 8 * 8, cudaMemcpyDeviceToHost);
         const char* names[6] = {"stage 0 (scores, ranking)", "crash", "dump + GEMM", "phase 1", "phase 2", "stage 4 (x, labels)"};
         double tot[6] = {0}, all = 0;
         for (long long i = 0; i < B; ++i) for (int q = 0; q < 6; ++q) { tot[q] += hd[i * 8 + q]; all += hd[i * 8 + q]; }
