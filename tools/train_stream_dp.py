@@ -17,7 +17,9 @@ if world > 1:
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
 torch.manual_seed(0)
 model = Model('bipartite', 40, 3, on_cuda=True, verbose_init=False)
-opt = torch.optim.SGD(model.parameters(), lr=1e-6, momentum=0.9)
+# the criterion is SUM-reduced as in the reference (benchmark.py:75): keep the step per instance constant across world sizes
+lr = float(os.environ.get("DDB_LR", "1e-6")) / world
+opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=0.9)
 res = {}
 for overlap in (False, True):
     tr.train_on_device_stream(model, opt, m, n, 5, B, key=5, weight=(0.25, 0.75), overlap=overlap)      # warm-up
@@ -34,6 +36,6 @@ else:
     in_sync = True
 if rank == 0:
     print(json.dumps({'config': 'DP training fed by on-GPU generation (BASELINE.json configs[4])', 'm': m, 'n': n, 'n_gpus': world,
-                      'batch_per_rank': B, 'steps': steps, 'model': 'bipartite p=40 T=3', 'replicas_in_sync': in_sync, **res}))
+                      'batch_per_rank': B, 'steps': steps, 'model': 'bipartite p=40 T=3', 'replicas_in_sync': in_sync, 'params_finite': bool(torch.isfinite(flat).all().item()), 'lr': lr, **res}))
 if world > 1:
     dist.destroy_process_group()
