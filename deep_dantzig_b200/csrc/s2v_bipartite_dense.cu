@@ -174,14 +174,12 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
     if (tid == 0)
         for (; issued < kStages && issued < total_chunks; ++issued) issue(issued);
 
-    // static column validity of my U columns (1 / 0) and how many are padding
+    // static column validity of my U columns (1 / 0)
     float cm[U];
-    int npad = 0;
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const bool ok = (4 * u + as < SL) && (col0 + 4 * u < n);
         cm[u] = ok ? 1.f : 0.f;
-        npad += ok ? 0 : 1;
     }
 
     for (long long k = 0; k < my_count; ++k) {
@@ -193,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
         if (tid == 0) *sflag = 0;
         __syncthreads();
         float ccol[U];              // my columns of c
-        float accp[U], accs[U];     // column sums of relu(a') and of a' (relu(-a') = relu(a') - a')
+        float accp[U], accs[U];     // column sums of |a'| and of a'  (relu(+-a') = (|a'| +- a') / 2)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             ccol[u] = (cm[u] != 0.f) ? cj[col0 + 4 * u] : 0.f;
@@ -211,37 +209,45 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
             const double* rp = ring + (size_t)s * kChunkRows * n + (size_t)(rowok ? arow : 0) * n;
             const float rmask = rowok ? 1.f : 0.f;
             float x[U];
-            float ss = 0.f, cs = 0.f, sp = 0.f, sx = 0.f;
-            int nzero = 0;
+            float ss = 0.f, cs = 0.f, sa = 0.f, sx = 0.f;      // sums of v^2, v c_j, |v|, v:  relu(+-v) = (|v| +- v) / 2
+            float amin = 3.0e38f;                              // smallest |v| over my valid columns (0 <=> a zero coefficient)
 #pragma unroll
             for (int u = 0; u < U; ++u) {
+                // columns that are valid for every thread need no mask (compile-time when the shape is specialised);
                 // padding columns read a valid entry (the row's first) and are multiplied by 0
-                const float v = (float)rp[(cm[u] != 0.f) ? col0 + 4 * u : 0] * cm[u];
+                const bool always = (CN != 0) && (4 * u + 3 < SL) && (SL + 4 * u + 3 < CN);
+                float v;
+                if (always) {
+                    v = (float)rp[col0 + 4 * u];
+                    amin = fminf(amin, fabsf(v));
+                } else {
+                    v = (float)rp[(cm[u] != 0.f) ? col0 + 4 * u : 0] * cm[u];
+                    amin = fminf(amin, fabsf(v) + (1.f - cm[u]));          // padding never counts as a zero
+                }
                 x[u] = v;
                 ss = fmaf(v, v, ss);
                 cs = fmaf(v, ccol[u], cs);
-                sp += relu(v);
+                sa += fabsf(v);
                 sx += v;
-                nzero += (v == 0.f) ? 1 : 0;
             }
-            sparse |= (rowok && nzero != npad);
+            sparse |= (rowok && amin == 0.f);
             // the 8 threads of a row are lanes {as, ag} of one warp: xor 1, 2, 16
 #pragma unroll
             for (int off = 1; off <= 16; off = (off == 2) ? 16 : off * 2) {
                 ss += __shfl_xor_sync(0xffffffffu, ss, off);
                 cs += __shfl_xor_sync(0xffffffffu, cs, off);
-                sp += __shfl_xor_sync(0xffffffffu, sp, off);
+                sa += __shfl_xor_sync(0xffffffffu, sa, off);
                 sx += __shfl_xor_sync(0xffffffffu, sx, off);
             }
+            const float sp = 0.5f * (sa + sx);                 // sum_j relu(a_ij)
             const float bi = bsm[rowok ? i : 0];
             ss = fmaf(bi, bi, ss);                                // ||[a_i | -b_i]||^2   (s2v.py:292)
             const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);      // F.normalize eps
             const float invm = inv * rmask;                        // rows beyond m contribute nothing
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const float xs = x[u] * invm;
-                accp[u] += relu(xs);
-                accs[u] += xs;
+                accp[u] = fmaf(fabsf(x[u]), invm, accp[u]);        // column sums of |a'|
+                accs[u] = fmaf(x[u], invm, accs[u]);               // and of a'
             }
             if (rowok && as == 0 && ag == 0) {
                 rb[i] = bi * inv;          // c_feats[:, 1] <- -(-b_i / norm)   (s2v.py:293)
@@ -254,7 +260,11 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
         }
         float accn[U];
 #pragma unroll
-        for (int u = 0; u < U; ++u) accn[u] = accp[u] - accs[u];
+        for (int u = 0; u < U; ++u) {
+            const float aabs = accp[u], asum = accs[u];
+            accp[u] = 0.5f * (aabs + asum);                        // sum_i relu(a'_ij)
+            accn[u] = 0.5f * (aabs - asum);                        // sum_i relu(-a'_ij)
+        }
         // column statistics: reduce over the 4 rows of a warp (lane bits 2, 3), then over the 8 warps through shared memory
 #pragma unroll
         for (int u = 0; u < U; ++u) {
