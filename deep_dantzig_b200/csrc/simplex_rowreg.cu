@@ -650,8 +650,20 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             }
             // my row goes to the per-CTA scratch (fire-and-forget stores) before T becomes a streaming buffer: the rare
             // ill-conditioned instance reloads it for one step of iterative refinement
+            // (stores carry an L2 evict_last policy: the 30 MB of per-CTA scratch are rewritten by every LP and should
+            // stay in the 126 MB L2 instead of being written back to HBM behind the streaming reads of A)
             double* tsave = a.gtab + ((size_t)blockIdx.x * NT + tid) * PD;
-            if (tid < nN) publish(tsave);
+            if (tid < nN) {
+                uint64_t pol;
+                asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#pragma unroll
+                for (int c2 = 0; c2 < NC / 2; ++c2)
+                    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(tsave + 2 * c2), "d"(T[2 * c2]),
+                                 "d"(T[2 * c2 + 1]), "l"(pol)
+                                 : "memory");
+                if constexpr (NC & 1)
+                    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(tsave + NC - 1), "d"(T[NC - 1]), "l"(pol) : "memory");
+            }
             auto write_x_obj = [&]() {
                 if (warp == 0) {
                     double acc = 0.0;
