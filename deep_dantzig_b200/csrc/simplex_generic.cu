@@ -31,7 +31,7 @@ struct Sel {
 };
 
 struct Layout {
-    size_t tab, s, g, gh, colbuf, xbuf, sig, rowvar, colvar, colvar0, where, order, rowfree, rowstate, red, sel, bar, total;
+    size_t tab, s, g, gh, colbuf, xbuf, sig, rowvar, colvar, colvar0, where, order, rowfree, liveidx, rowstate, red, cands, sel, bar, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -52,8 +52,10 @@ __host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
     L.where = off;    off += align_up((size_t)m * 4, 16);
     L.order = off;    off += align_up((size_t)m * 4, 16);
     L.rowfree = off;  off += align_up((size_t)m * 4, 16);
+    L.liveidx = off;  off += align_up((size_t)m * 4, 16);
     L.rowstate = off; off += align_up((size_t)m, 16);
     L.red = off;      off += 3 * 32 * 4;
+    L.cands = off;    off += align_up(32 * sizeof(Cand), 16);
     L.sel = off;      off += align_up(sizeof(Sel), 16);
     L.bar = off;      off += 16;
     L.total = off;
@@ -81,6 +83,9 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
     int* where = reinterpret_cast<int*>(smem_raw + L.where);
     int* order = reinterpret_cast<int*>(smem_raw + L.order);
     int* rowfree = reinterpret_cast<int*>(smem_raw + L.rowfree);
+    int* liveidx = reinterpret_cast<int*>(smem_raw + L.liveidx);      // live rows after the crash (phases 1 / 2 iterate over these)
+    Cand* cands = reinterpret_cast<Cand*>(smem_raw + L.cands);         // per-warp candidates of the block-wide ratio test
+    __shared__ int nlive_sm;
     uint8_t* rowstate = smem_raw + L.rowstate;
     Sel* sel = reinterpret_cast<Sel*>(smem_raw + L.sel);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
@@ -99,18 +104,29 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
     }
 
     // One pivot on (r, k).  Every thread calls it with the same arguments (read from *sel after a barrier).
-    auto do_pivot = [&](int r, int k, double p, bool crash_mode) {
+    // One pivot on (r, k).  Every thread calls it with the same arguments (read from *sel after a barrier).
+    // have_col: colbuf already holds column k of the live rows (the block-wide ratio test of phase 2 gathered it), so the
+    // strided re-read of the column is skipped.
+    auto do_pivot = [&](int r, int k, double p, bool crash_mode, bool have_col) {
         const double rp = 1.0 / p;
         // B: normalise the pivot row, pull the pivot column out into colbuf and zero it in place
         for (int j = tid; j < n; j += nt) P[(size_t)r * n + j] = (j == k) ? rp : P[(size_t)r * n + j] * rp;
-        for (int i = tid; i < m; i += nt) {
-            double f = 0.0;
-            const uint8_t st = rowstate[i];
-            if (i != r && (st == ROW_LIVE || (crash_mode && st == ROW_CRASHED))) {
-                f = P[(size_t)i * n + k];
-                P[(size_t)i * n + k] = 0.0;
+        if (have_col) {
+            const int nl = nlive_sm;
+            for (int q = tid; q < nl; q += nt) {
+                const int i = liveidx[q];
+                if (i != r) P[(size_t)i * n + k] = 0.0; else colbuf[i] = 0.0;
             }
-            colbuf[i] = f;
+        } else {
+            for (int i = tid; i < m; i += nt) {
+                double f = 0.0;
+                const uint8_t st = rowstate[i];
+                if (i != r && (st == ROW_LIVE || (crash_mode && st == ROW_CRASHED))) {
+                    f = P[(size_t)i * n + k];
+                    P[(size_t)i * n + k] = 0.0;
+                }
+                colbuf[i] = f;
+            }
         }
         if (tid == 0) {
             s[r] *= rp;
@@ -128,16 +144,68 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
             pr[q] = (j < n) ? P[(size_t)r * n + j] : 0.0;
         }
         const double sr = s[r];
-        for (int i = warp; i < m; i += nw) {
-            const double f = colbuf[i];
-            if (f != 0.0) {
-                double* Pi = P + (size_t)i * n;
+        if (crash_mode) {
+            for (int i = warp; i < m; i += nw) {
+                const double f = colbuf[i];
+                if (f != 0.0) {
+                    double* Pi = P + (size_t)i * n;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
+                    }
+                    if (lane == 0) s[i] = fma(-f, sr, s[i]);
+                }
+            }
+        } else if constexpr (CPL <= 4) {
+            // phases 1 / 2: only the live rows, two rows per step so that 2 * CPL loads are in flight per lane
+            const int nl = nlive_sm;
+            for (int q0 = warp; q0 < nl; q0 += 2 * nw) {
+                const int ia = liveidx[q0];
+                const int ib = (q0 + nw < nl) ? liveidx[q0 + nw] : ia;
+                const double fa = colbuf[ia];
+                const double fb = (q0 + nw < nl) ? colbuf[ib] : 0.0;
+                double* Pa = P + (size_t)ia * n;
+                double* Pb = P + (size_t)ib * n;
+                double va[CPL], vb[CPL];
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                     const int j = lane + 32 * q;
-                    if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
+                    va[q] = (j < n && fa != 0.0) ? Pa[j] : 0.0;
+                    vb[q] = (j < n && fb != 0.0) ? Pb[j] : 0.0;
                 }
-                if (lane == 0) s[i] = fma(-f, sr, s[i]);
+                if (fa != 0.0) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < n) Pa[j] = fma(-fa, pr[q], va[q]);
+                    }
+                    if (lane == 0) s[ia] = fma(-fa, sr, s[ia]);
+                }
+                if (fb != 0.0) {
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < n) Pb[j] = fma(-fb, pr[q], vb[q]);
+                    }
+                    if (lane == 0) s[ib] = fma(-fb, sr, s[ib]);
+                }
+            }
+        } else {
+            // wide rows (n > 128): the 64-register budget of a 1024-thread CTA holds one row's loads at a time
+            const int nl = nlive_sm;
+            for (int q0 = warp; q0 < nl; q0 += nw) {
+                const int i = liveidx[q0];
+                const double f = colbuf[i];
+                if (f != 0.0) {
+                    double* Pi = P + (size_t)i * n;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
+                    }
+                    if (lane == 0) s[i] = fma(-f, sr, s[i]);
+                }
             }
         }
         {
@@ -240,9 +308,17 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
             if (rowstate[r] == ROW_EXCLUDED) break;   // uniform: shared memory read after a barrier
             if (warp == 0) {
                 Cand cd{kInf, kBigVar, -1};
-                for (int j = lane; j < n; j += 32) {
-                    if (colvar[j] < 0) {
-                        const double v = -fabs(P[(size_t)r * n + j]);
+                double er[CPL];                    // the row's entries first: independent loads, one round trip
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int j = lane + 32 * q;
+                    er[q] = (j < n) ? P[(size_t)r * n + j] : 0.0;
+                }
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < n && colvar[j] < 0) {
+                        const double v = -fabs(er[q]);
                         if (cand_better(v, j, cd.val, cd.var)) cd = Cand{v, j, j};
                     }
                 }
@@ -263,7 +339,7 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
             const double p = sel->p;
             __syncthreads();   // everyone has read *sel before anyone rewrites it
             if (flag == 3) continue;
-            do_pivot(r, k, p, true);
+            do_pivot(r, k, p, true, false);
             if (tid == 0) {
                 rowstate[r] = ROW_CRASHED;
                 rowfree[r] = k;
@@ -276,6 +352,12 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
         for (int j = tid; j < n; j += nt) {
             colvar0[j] = colvar[j];
             gh[j] = 1.0;
+        }
+        if (tid == 0) {
+            int nl = 0;
+            for (int i = 0; i < m; ++i)
+                if (rowstate[i] == ROW_LIVE) liveidx[nl++] = i;
+            nlive_sm = nl;
         }
         __syncthreads();
 
@@ -296,9 +378,17 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
                 } else {
                     const int r = cr.idx;
                     Cand ck{kInf, kBigVar, -1};
-                    for (int j = lane; j < n; j += 32) {
-                        const double e = P[(size_t)r * n + j];
-                        if (colvar[j] >= 0 && e < -kTolPivot) {
+                    double er[CPL];                // the row's entries first: independent loads, one round trip
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        er[q] = (j < n) ? P[(size_t)r * n + j] : 0.0;
+                    }
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        const double e = er[q];
+                        if (j < n && colvar[j] >= 0 && e < -kTolPivot) {
                             const double ratio = fmax(gh[j], 0.0) / (-e);
                             if (cand_better(ratio, colvar[j], ck.val, ck.var)) ck = Cand{ratio, colvar[j], j};
                         }
@@ -321,7 +411,7 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
             if (flag == 1) break;
             if (flag == 2) { status = ST_INFEASIBLE; break; }
             if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
-            do_pivot(r, k, p, false);
+            do_pivot(r, k, p, false, false);
             if (tid == 0) {
                 const int vr = rowvar[r], vk = colvar[k];
                 rowvar[r] = vk;
@@ -334,6 +424,9 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
         }
 
         // ---- stage 3: phase 2 (column-first Dantzig pivots until g >= 0) -----------------------------------
+        // Pricing (argmin g, shared memory) by warp 0; the ratio test by the WHOLE block: every thread reads the entry of
+        // its live row(s) in column k -- one round trip to the tableau instead of m / 32 sequential ones for one warp --
+        // and leaves it in colbuf for the pivot, then a two-level argmin (warp, block) with the same Bland tie-break.
         while (status == ST_OPTIMAL) {
             if (warp == 0) {
                 Cand ck{kInf, kBigVar, -1};
@@ -348,42 +441,50 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
                 }
                 ck = warp_argmin(ck);
                 free_unbounded = __any_sync(0xffffffffu, free_unbounded);
-                int flag = 0, rr = -1;
-                if (free_unbounded) {
-                    flag = 2;
-                } else if (ck.idx < 0 || ck.val >= -kTolFeas) {
-                    flag = 1;
-                } else {
-                    const int k = ck.idx;
-                    Cand cr{kInf, kBigVar, -1};
-                    for (int i = lane; i < m; i += 32) {
-                        if (rowstate[i] == ROW_LIVE) {
-                            const double e = P[(size_t)i * n + k];
-                            if (e > kTolPivot) {
-                                const double ratio = fmax(s[i], 0.0) / e;
-                                if (cand_better(ratio, rowvar[i], cr.val, cr.var)) cr = Cand{ratio, rowvar[i], i};
-                            }
-                        }
-                    }
-                    cr = warp_argmin(cr);
-                    rr = cr.idx;
-                    if (rr < 0) flag = 2;
-                }
+                int flag = 0;
+                if (free_unbounded) flag = 2;
+                else if (ck.idx < 0 || ck.val >= -kTolFeas) flag = 1;
                 if (lane == 0) {
                     sel->flag = flag;
-                    sel->r = rr;
                     sel->k = ck.idx;
-                    if (flag == 0) sel->p = P[(size_t)rr * n + ck.idx];
                 }
             }
             __syncthreads();
-            const int flag = sel->flag, r = sel->r, k = sel->k;
+            const int flag0 = sel->flag, k = sel->k;
+            if (flag0 == 1) break;
+            if (flag0 == 2) { status = ST_UNBOUNDED; break; }
+            {
+                Cand cr{kInf, kBigVar, -1};
+                const int nl = nlive_sm;
+                for (int q = tid; q < nl; q += nt) {
+                    const int i = liveidx[q];
+                    const double e = P[(size_t)i * n + k];
+                    colbuf[i] = e;
+                    if (e > kTolPivot) {
+                        const double ratio = fmax(s[i], 0.0) / e;
+                        if (cand_better(ratio, rowvar[i], cr.val, cr.var)) cr = Cand{ratio, rowvar[i], i};
+                    }
+                }
+                cr = warp_argmin(cr);
+                if (lane == 0) cands[warp] = cr;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                Cand cr = (lane < nw) ? cands[lane] : Cand{kInf, kBigVar, -1};
+                cr = warp_argmin(cr);
+                if (lane == 0) {
+                    sel->r = cr.idx;
+                    sel->flag = (cr.idx < 0) ? 2 : 0;
+                    if (cr.idx >= 0) sel->p = colbuf[cr.idx];
+                }
+            }
+            __syncthreads();
+            const int flag = sel->flag, r = sel->r;
             const double p = sel->p;
             __syncthreads();
-            if (flag == 1) break;
             if (flag == 2) { status = ST_UNBOUNDED; break; }
             if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
-            do_pivot(r, k, p, false);
+            do_pivot(r, k, p, false, true);
             if (tid == 0) {
                 const int vr = rowvar[r], vk = colvar[k];
                 rowvar[r] = vk;
