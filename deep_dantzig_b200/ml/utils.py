@@ -6,32 +6,32 @@ import numpy as np
 import torch
 
 
+def _pick(t, k):
+    """k-th instance of a collated tensor; a tensor without a real batch axis is shared by every instance."""
+    if t.dim() > 1 and t.shape[0] > 1:
+        return t[k]
+    return t.squeeze(0) if t.dim() > 1 else t
+
+
 def batched(data, batch_size, graph_structure):
-    if graph_structure == 'complete':
-        for batch in range(batch_size):
-            x = {}
-            x['A'] = data['lp']['A'][batch, :, :].unsqueeze(0)
-            x['b'] = data['lp']['b'][batch, :].unsqueeze(0)
-            x['c'] = data['lp']['c'][batch, :].unsqueeze(0)
-            x['node_features'] = data['node_features']
-            x['in_loss'] = [int(p) for p in data['in_loss']]
-            labels = data['node_labels']
-            labels = labels[batch] if labels.dim() > 1 and labels.shape[0] > 1 else labels.squeeze(0)
-            yield x, labels[x['in_loss']]
-    elif graph_structure == 'bipartite':
-        for batch in range(batch_size):
-            pick = (lambda t: t[batch] if t.dim() > 2 and t.shape[0] > 1 else t.squeeze(0))
-            x = {}
-            x['c_feats'] = pick(data['c_feats'])
-            x['v_feats'] = pick(data['v_feats'])
-            x['e_feats'] = data['e_feats']
-            x['dims'] = data['dims']
-            x['in_loss'] = [int(p) for p in data['in_loss']]
-            labels = data['c_labels']
-            labels = labels[batch] if labels.dim() > 1 and labels.shape[0] > 1 else labels.squeeze(0)
-            yield x, labels[x['in_loss']]
-    else:
-        raise(ValueError('graph_structure not recognised'))
+    """Yield one ``(x, y)`` per instance of a collated DataLoader item, in the item layouts ``Model.forward`` takes
+    (reference src/ml/utils.py:3-25; the bipartite branch honours the batch index)."""
+    if graph_structure not in ('complete', 'bipartite'):
+        raise ValueError('graph_structure not recognised')
+    in_loss = [int(q) for q in data['in_loss']]
+    for k in range(batch_size):
+        if graph_structure == 'complete':
+            lp = data['lp']
+            x = {'A': lp['A'][k].unsqueeze(0), 'b': lp['b'][k].unsqueeze(0), 'c': lp['c'][k].unsqueeze(0),
+                 'node_features': data['node_features'], 'in_loss': in_loss}
+            labels = _pick(data['node_labels'], k)
+        else:
+            cf, vf = data['c_feats'], data['v_feats']
+            x = {'c_feats': cf[k] if cf.dim() > 2 and cf.shape[0] > 1 else (cf.squeeze(0) if cf.dim() > 2 else cf),
+                 'v_feats': vf[k] if vf.dim() > 2 and vf.shape[0] > 1 else (vf.squeeze(0) if vf.dim() > 2 else vf),
+                 'e_feats': data['e_feats'], 'dims': data['dims'], 'in_loss': in_loss}
+            labels = _pick(data['c_labels'], k)
+        yield x, labels[in_loss]
 
 
 def collate_randomlp(items):

@@ -116,3 +116,43 @@ def test_batched_autograd_matches_reference_gradients(golden_dir, graph):
                 assert q.grad is None or float(q.grad.abs().max()) == 0.0
                 continue
             assert grads_close(q.grad.numpy(), G[k], scale), (graph, dims, k)
+
+
+@pytest.mark.parametrize('graph', ['complete', 'bipartite'])
+def test_batched_adapter_yields_reference_items(graph):
+    """``ml.utils.batched`` (reference src/ml/utils.py:3-25) turns a collated DataLoader item into per-instance items that
+    ``Model.forward`` accepts; the result equals the batched forward on the same instances."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml.utils import batched
+    from oracle import randomlp as orl
+    torch.manual_seed(3)
+    m, n, B = 12, 5, 3
+    insts = [orl.generate_instance(m, n, 40 + k) for k in range(B)]
+    labels = torch.randint(0, 2, (B, m))
+    model = Model(graph, 6, 2, verbose_init=False)
+    model.force_torch = True
+    A = torch.from_numpy(np.stack([i[0] for i in insts])); b = torch.from_numpy(np.stack([i[1] for i in insts]))
+    c = torch.from_numpy(np.stack([i[2] for i in insts]))
+    with torch.no_grad():
+        want = model.forward_batch(A, b, c)
+    if graph == 'complete':
+        data = {'lp': {'A': A, 'b': b, 'c': c}, 'node_features': torch.cat((torch.ones(1, m), torch.zeros(1, 1)), 1),
+                'in_loss': list(range(m)), 'node_labels': torch.cat((labels, torch.zeros(B, 1, dtype=torch.long)), 1)}
+        got = list(batched(data, B, 'complete'))
+        assert len(got) == B
+        for k, (x, y) in enumerate(got):
+            with torch.no_grad():
+                lp = model(x)
+            assert torch.allclose(lp, want[k], atol=1e-6) and torch.equal(y, labels[k])
+    else:
+        # the reference's bipartite item carries one instance per DataLoader item (batch_size 1)
+        for k in range(B):
+            it = oc.item_bipartite(*insts[k], labels=labels[k].tolist())
+            data = {'c_feats': it['c_feats'].unsqueeze(0), 'v_feats': it['v_feats'].unsqueeze(0), 'e_feats': it['e_feats'],
+                    'dims': it['dims'], 'in_loss': it['in_loss'], 'c_labels': it['c_labels'].unsqueeze(0)}
+            (x, y), = list(batched(data, 1, 'bipartite'))
+            with torch.no_grad():
+                lp = model(x)
+            assert torch.allclose(lp, want[k], atol=1e-5) and torch.equal(y.long(), labels[k])
+    with pytest.raises(ValueError):
+        list(batched({'in_loss': []}, 1, 'hypergraph'))
