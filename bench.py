@@ -204,6 +204,8 @@ def run_ours(args):
         raise SystemExit('bench.py needs a CUDA device; there is no CPU fallback')
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from deep_dantzig_b200 import parallel
+    numa_node = parallel.bind_to_gpu_numa_node(local) if world > 1 else None      # one process per GPU, next to its GPU
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
@@ -411,7 +413,8 @@ def run_ours(args):
         'roofline': roofline, 'roofline_onchip': onchip, 'cpu_baseline': cpu, 'label_match': match,
         'classifier': classifier,
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
-                'lps_per_step': Be, 'steps': e2e_steps, 'api': 'ddb_solve_label_host (pinned host buffers)'},
+                'lps_per_step': Be, 'steps': e2e_steps, 'api': 'ddb_solve_label_host (pinned host buffers)',
+                'rank0_numa_node': numa_node},
         'gpu_launches': int(launches), 'kernel_ms_per_step': statistics.mean(kern_ms), 'clocks': clocks,
     }
     emit(line)

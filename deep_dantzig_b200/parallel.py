@@ -5,6 +5,33 @@ import torch
 import torch.distributed as dist
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, so that pinned host buffers are
+    first-touched on that node and host<->device copies do not cross the socket interconnect.  Best effort: returns the
+    node number, or None when the topology cannot be read (single-socket host, container without sysfs, ...)."""
+    import os
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        bdf = '%04x:%02x:%02x.0' % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        with open('/sys/bus/pci/devices/%s/numa_node' % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open('/sys/devices/system/node/node%d/cpulist' % node) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except (OSError, ValueError, AttributeError):
+        return None
+
+
 def world():
     if dist.is_available() and dist.is_initialized():
         return dist.get_rank(), dist.get_world_size()
