@@ -248,11 +248,19 @@ def test_full_size_properties(cuda_device):
     assert slack.min().item() >= -1e-7
     assert ((slack.abs() <= 1e-7) == lab[okt].bool()).all()
     assert torch.allclose((c * x).sum(1), r['obj'][okt], rtol=1e-12, atol=0)
-    # dual certificate: c = -A_B' y with y >= 0 on the active rows  (solve the n x n system with torch)
-    sub = torch.arange(0, int(okt.sum().item()), 97, device='cuda')[:64]
-    AB = torch.stack([A[i][lab[okt][i].bool()] for i in sub.tolist()])
-    y = torch.linalg.solve(AB.transpose(1, 2), -c[sub].unsqueeze(2)).squeeze(2)
+    # full optimality certificate on EVERY optimal instance, independent of any solver: with B = the labelled rows,
+    #   dual:   c = -A_B' y with y >= 0            primal: x is the vertex A_B x = b_B (and feasible, above)
+    K = int(okt.sum().item())
+    rows = lab[okt].bool().nonzero()[:, 1].reshape(K, n)                       # exactly n labelled rows per instance
+    AB = torch.gather(A, 1, rows.unsqueeze(2).expand(K, n, n))
+    bB = torch.gather(b, 1, rows)
+    y = torch.linalg.solve(AB.transpose(1, 2), -c.unsqueeze(2)).squeeze(2)
     assert y.min().item() >= -1e-7
+    xv = torch.linalg.solve(AB, bB.unsqueeze(2)).squeeze(2)
+    xv = xv + torch.linalg.solve(AB, (bB - torch.bmm(AB, xv.unsqueeze(2)).squeeze(2)).unsqueeze(2)).squeeze(2)   # one refinement step
+    relv = ((x - xv).abs().amax(1) / xv.abs().amax(1))
+    print('optimal instances %d: max relative distance of x from the vertex of its labelled rows %.2e' % (K, relv.max().item()))
+    assert relv.max().item() <= 1e-9
     # linearity: scaling the objective scales the optimum, labels unchanged; row permutation permutes labels
     r2 = solver.solve_label(r['A'][:512], r['b'][:512], (r['c'][:512] * 3.0).contiguous())
     assert (r2['labels'] == lab[:512]).all()
