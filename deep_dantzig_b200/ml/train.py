@@ -127,8 +127,19 @@ def recall_one_threshold(loader, model):
     return float(thresholds[idx[0]])
 
 
+def plot_roc(model, epoch, trainloader=None, testloader=None):
+    """Reference signature and return value (train.py:118-172: ``(p_train, p_test)``, the recall-1 thresholds of the two
+    loaders); the visdom plot itself is out of scope."""
+    p_train = recall_one_threshold(trainloader, model) if trainloader is not None else None
+    p_test = recall_one_threshold(testloader, model) if testloader is not None else None
+    return p_train, p_test
+
+
 def get_prob_recall_one(loader, model):
     """train.py:102-116: smallest predicted probability of a positive."""
+    if _on_device(model):
+        r = device_metrics(model, loader)
+        return float(r[4]) if r[6] > 0 else 0.5
     y_true, y_prob = _probs_and_labels(loader, model)
     return float(y_prob[y_true == 1].min()) if (y_true == 1).any() else 0.5
 

@@ -100,3 +100,27 @@ def test_train_net_mirror_learns_on_cpu():
     assert set(hist['train'][0]) == {'total_loss', 'accuracy', 'precision', 'recall', 'y_pos', 'y_neg', 'pred_pos', 'pred_neg'}
     assert hist['train'][-1]['total_loss'] < before['total_loss']
     assert hist['train'][-1]['recall'] == 1.0                     # metrics are taken at the recall-1 threshold
+
+
+def test_evaluation_entry_points_on_cpu():
+    """get_accuracy (ml/test.py:10-54), plot_roc's return value (train.py:118-172) and get_prob_recall_one (:102-116)
+    keep the reference's signatures; on the CPU path the threshold comes from sklearn's ROC exactly as in the reference."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml.train import plot_roc, get_prob_recall_one, performance
+    from deep_dantzig_b200.ml.test import get_accuracy
+    from deep_dantzig_b200.ml.utils import collate_randomlp
+    from torch.utils.data import DataLoader
+    from oracle import randomlp as orl
+    ds = orl.RandomLPDataset(10, 5, num_lps=16, seed=3)
+    loader = DataLoader(ds, batch_size=8, shuffle=False, collate_fn=collate_randomlp)
+    torch.manual_seed(2)
+    model = Model('bipartite', 6, 2, verbose_init=False)
+    model.force_torch = True
+    p_train, p_test = plot_roc(model, 0, trainloader=loader, testloader=None)
+    assert p_test is None and 0.0 < p_train < 1.0
+    assert p_train == get_prob_recall_one(loader, model)           # first ROC point with TPR 1 == min prob of a positive
+    acc = get_accuracy(loader, model, p_train)
+    assert set(acc) == {'accuracy', 'precision', 'recall', 'y_pos', 'y_neg', 'pred_pos', 'pred_neg'} and acc['recall'] == 1.0
+    crit = torch.nn.NLLLoss(weight=torch.tensor([0.5, 0.5]), reduction='sum')
+    perf = performance(loader, model, crit, p_train)
+    assert all(abs(perf[k] - acc[k]) < 1e-12 for k in acc)
