@@ -41,8 +41,6 @@ class LinProg(object):
             for op in ops:
                 if op not in ('<', '>', '='):
                     raise ValueError                            # gurobi_lp.py:409
-                if op == '=':
-                    raise NotImplementedError("equality rows are outside the random-LP hot path (SURVEY.md 8(f) rank 4)")
         self.obj, self.ops = obj, ops
         self.x = None
         self.model = _ModelView()
@@ -50,14 +48,19 @@ class LinProg(object):
         self._res = None
 
     def _canonical(self):
-        """min c'x, Ax <= b: '>' rows and 'max' objectives are sign flips."""
+        """min c'x, Ax <= b: '>' rows and 'max' objectives are sign flips; an '=' row a.x = b_i becomes the pair
+        a.x <= b_i, -a.x <= -b_i (the second halves are appended behind the m original rows, so the first m labels the
+        device returns are the labels of the caller's rows: |b_i - a_i.x| does not depend on the sign)."""
         A, b, c = self.A, self.b, self.c
         if self.ops is not None and any(op == '>' for op in self.ops):
             sign = np.array([-1.0 if op == '>' else 1.0 for op in self.ops])
             A, b = A * sign[:, None], b * sign
+        if self.ops is not None and any(op == '=' for op in self.ops):
+            eq = [i for i, op in enumerate(self.ops) if op == '=']
+            A, b = np.vstack((A, -A[eq])), np.concatenate((b, -b[eq]))
         if self.obj == 'max':
             c = -c
-        return A, b, c
+        return np.ascontiguousarray(A), np.ascontiguousarray(b), c
 
     def optimize(self):
         A, b, c = self._canonical()
@@ -71,7 +74,7 @@ class LinProg(object):
 
     def get_active_constraints(self):
         """gurobi_lp.py:435-443: indices with |b - A x| <= 1e-7 (computed on the device from the same A, b, x)."""
-        return np.flatnonzero(self._res['labels'][0]).astype(np.int64)
+        return np.flatnonzero(self._res['labels'][0][:self.m]).astype(np.int64)
 
     def get_statuscode(self):
         s = self.model.status

@@ -351,3 +351,38 @@ def test_singular_crash_basis_is_handed_to_the_generic_kernel(cuda_device):
     ok = ref['status'] == 2
     assert (r['labels'][ok] == ref['labels'][ok]).all()
     assert np.abs(r['obj'][ok] - ref['obj'][ok]).max() <= 1e-9 * np.abs(ref['obj'][ok]).max()
+
+
+def test_linprog_ops_and_objective_sense(cuda_device):
+    """LinProg(A, b, c, obj, ops) with '<', '>', '=' rows and 'min' / 'max' (reference gurobi_lp.py:392-426) against the
+    oracle's LinProg (HiGHS with A_eq): status, objective, x and active rows."""
+    from deep_dantzig_b200.data.gurobi_lp import LinProg
+    # min -x s.t. x + y = 1, y >= 0, x <= 0.7  ->  x = 0.7, y = 0.3; active: the equality and x <= 0.7
+    A = np.array([[1.0, 1.0], [0.0, 1.0], [1.0, 0.0]]); b = np.array([1.0, 0.0, 0.7]); c = np.array([-1.0, 0.0])
+    lp = LinProg(A, b, c, 'min', ['=', '>', '<']); lp.optimize()
+    assert lp.get_statuscode() == 2 and lp.x == pytest.approx([0.7, 0.3]) and lp.model.objVal == pytest.approx(-0.7)
+    assert list(lp.get_active_constraints()) == [0, 2]
+    lp = LinProg(A, b, -c, 'max', ['=', '>', '<']); lp.optimize()
+    assert lp.get_statuscode() == 2 and lp.model.objVal == pytest.approx(0.7) and list(lp.get_active_constraints()) == [0, 2]
+    # random instances with mixed senses
+    rs = np.random.RandomState(5)
+    checked = 0
+    for trial in range(40):
+        m, n = 14, 5
+        A = rs.randn(m, n); x0 = rs.randn(n); cc = np.abs(rs.randn(n))
+        ops = ['<'] * m
+        slack = np.abs(rs.randn(m))
+        for i in rs.choice(m, 4, replace=False):
+            ops[i] = '>'
+        eqs = rs.choice([i for i in range(m) if ops[i] == '<'], 2, replace=False)
+        for i in eqs:
+            ops[i] = '='
+        bb = A.dot(x0) + np.array([0.0 if ops[i] == '=' else (slack[i] if ops[i] == '<' else -slack[i]) for i in range(m)])
+        ours = LinProg(A, bb, cc, 'min', ops); ours.optimize()
+        ref = oracle.LinProg(A, bb, cc, 'min', ops); ref.optimize()
+        assert (ours.model.status == 2) == (ref.model.status == 2), trial
+        if ref.model.status == 2:
+            assert ours.model.objVal == pytest.approx(ref.model.objVal, rel=1e-8, abs=1e-9)
+            assert list(ours.get_active_constraints()) == list(ref.get_active_constraints()), trial
+            checked += 1
+    assert checked >= 10
