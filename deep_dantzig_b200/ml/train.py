@@ -35,10 +35,16 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
         for data in trainloader:
             A, b, c, y = _to_device(data, dev)
             optimizer.zero_grad()
+            loss = None
             if _device_backward_ok(model, criterion, A):
                 # hand-written loss + gradient kernel (csrc/s2v_backward.cu): one launch per batch
-                loss = model.loss_and_grad_batch(A, b, c, y, [float(criterion.weight[0]), float(criterion.weight[1])])
-            else:
+                try:
+                    loss = model.loss_and_grad_batch(A, b, c, y, [float(criterion.weight[0]), float(criterion.weight[1])])
+                except _lib.DdbError as exc:
+                    if 'do not fit' not in str(exc):
+                        raise
+                    model._no_device_backward = True          # shape / embedding size beyond the kernel: autograd from now on
+            if loss is None:
                 fx = model.forward_batch(A, b, c)                         # [B,m,2] log-probs
                 loss = criterion(fx.reshape(-1, 2), y.reshape(-1))        # summed over the batch (benchmark.py:75)
                 loss.backward()
@@ -57,7 +63,8 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
 def _device_backward_ok(model, criterion, A):
     """The device backward implements the reference's criterion (weighted NLL, summed: benchmark.py:70-75) for the
     bipartite model on dense instances; anything else goes through autograd."""
-    return (hasattr(model, 'device_backward_supported') and model.device_backward_supported(A)
+    return (hasattr(model, 'device_backward_supported') and not getattr(model, '_no_device_backward', False)
+            and model.device_backward_supported(A)
             and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum'
             and criterion.weight is not None and criterion.ignore_index < 0 and bool((A != 0).all()))
 
