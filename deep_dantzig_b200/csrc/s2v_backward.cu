@@ -61,6 +61,8 @@ __device__ __forceinline__ void matvec_gT(const float* __restrict__ W, int p, co
     }
 }
 
+constexpr int kGradThreads = 512;   // 16 warps per CTA (one CTA per SM: the shared-memory footprint is the limit)
+
 struct GradLayout {          // offsets in floats
     size_t t7T, t7N, mu, zr, dmu, gacc, mask, part, vecs, total;
 };
@@ -76,7 +78,7 @@ __host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, in
     L.gacc = off; off += (size_t)((npar + 3) & ~3);
     off = (off + 1) & ~(size_t)1;
     L.mask = off; off += (size_t)2 * T * NP;                       // one 64-bit mask per (round, node)
-    L.part = off; off += (size_t)12 * (256 / (p < 1 ? 1 : p) + 1) * PP;   // [group][12 sums][l]: register-path round reductions
+    L.part = off; off += (size_t)12 * (kGradThreads / (p < 1 ? 1 : p) + 1) * PP;   // [group][12 sums][l]: register-path round reductions
     L.vecs = off;
     off += (size_t)8 * m + 5 * n + (size_t)(24 + 4 * T) * PP + 64;
     L.total = off;
@@ -85,7 +87,9 @@ __host__ __device__ inline GradLayout grad_layout(int m, int n, int p, int T, in
 
 constexpr int AU = 16;   // columns per thread of the streaming A pass (n <= 128)
 
-__global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, int npar) {
+// NT = 512 (one CTA per SM, big shapes whose shared-memory footprint allows only one anyway) or 256 (two CTAs per SM)
+template <int NT>
+__global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1) s2v_bipartite_grad_kernel(S2vGradArgs a, int npar) {
     extern __shared__ __align__(16) float sm[];
     const int m = a.m, n = a.n, p = a.p, T = a.T, PP = bpad4(p), NP = m + n;
     const GradLayout L = grad_layout(m, n, p, T, npar);
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
     __syncthreads();
     double loss_cta = 0.0;
     // register path of the rounds: thread (l, group); RC / RV node slots per thread
-    constexpr int RC = 36, RV = 20;
+    constexpr int RC = 20, RV = 12;
     const int G = nt / p;
     const int rl = tid % p, rgrp = tid / p;
     const bool ractive = rgrp < G;
@@ -191,10 +195,11 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
                 accp[u] = 0.f;
                 accs[u] = 0.f;
             }
-            const int nchunk = (m + 31) / 32;
+            const int crow = 4 * nw;                  // rows per chunk: four per warp
+            const int nchunk = (m + crow - 1) / crow;
             double xn[AU];
             auto load_chunk = [&](int ci) {
-                const int i = ci * 32 + arow;
+                const int i = ci * crow + arow;
                 const double* rp = Ag + (size_t)(i < m ? i : 0) * n;
 #pragma unroll
                 for (int u = 0; u < AU; ++u) xn[u] = __ldg(rp + ((cmk[u] != 0.f) ? col0 + 4 * u : 0));
@@ -206,7 +211,7 @@ __global__ void __launch_bounds__(256) s2v_bipartite_grad_kernel(S2vGradArgs a, 
 #pragma unroll
                 for (int u = 0; u < AU; ++u) x[u] = (float)xn[u] * cmk[u];
                 if (ci + 1 < nchunk) load_chunk(ci + 1);
-                const int i = ci * 32 + arow;
+                const int i = ci * crow + arow;
                 const bool rowok = i < m;
                 float ss = 0.f, cs = 0.f, sp = 0.f, sx = 0.f;
                 int nzero = 0;
@@ -797,14 +802,18 @@ cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_cou
     if (a.p > 64) { *why = "classifier backward: p > 64 is not supported (one 64-bit activity mask per node)"; return cudaErrorInvalidValue; }
     const size_t smem = s2v_grad_smem_bytes(a.m, a.n, a.p, a.T, npar);
     if ((long long)smem > smem_optin) { *why = "classifier backward: embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
-    cudaError_t e = cudaFuncSetAttribute(s2v_bipartite_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // two 256-thread CTAs per SM when two footprints fit in shared memory, else one 512-thread CTA
+    const bool two = 2 * (smem + 1024) <= (size_t)smem_optin;
+    auto kern = two ? s2v_bipartite_grad_kernel<256> : s2v_bipartite_grad_kernel<512>;
+    const int nthreads = two ? 256 : 512;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, s2v_bipartite_grad_kernel, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, nthreads, smem);
     if (e != cudaSuccess) return e;
     long long grid = (long long)sm_count * (per_sm > 0 ? per_sm : 1);
     if (grid > a.B) grid = a.B;
-    s2v_bipartite_grad_kernel<<<(int)grid, 256, smem, st>>>(a, npar);
+    kern<<<(int)grid, nthreads, smem, st>>>(a, npar);
     return cudaGetLastError();
 }
 
