@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
 struct CmpLayout {
     size_t t2rr, t7, G, mu, mu2, vecs, total;   // floats
 };
-__host__ __device__ inline CmpLayout cmp_layout(int m, int n, int p) {
+// with_G = false when the Gram row sums come from the tensor-core kernel: G is not staged and two CTAs fit per SM
+__host__ __device__ inline CmpLayout cmp_layout(int m, int n, int p, bool with_G) {
     const int PP = pad4(p);
     int PG = n + 1;
     if ((PG & 1) == 0) PG += 1;                 // odd pitch: conflict-free column walks
@@ -354,21 +355,21 @@ __host__ __device__ inline CmpLayout cmp_layout(int m, int n, int p) {
     size_t off = 0;
     L.t2rr = off; off += (size_t)p * PP;
     L.t7 = off;   off += (size_t)p * PP;
-    L.G = off;    off += (size_t)(m + 1) * PG;
+    L.G = off;    off += with_G ? (size_t)(m + 1) * PG : 0;
     L.mu = off;   off += (size_t)p * (m + 1);
     L.mu2 = off;  off += (size_t)p * (m + 1);
     L.vecs = off; off += (size_t)3 * (m + 1) + 16 * PP + 64;
     L.total = off;
     return L;
 }
-size_t s2v_complete_smem_bytes(int m, int n, int p) { return cmp_layout(m, n, p).total * 4; }
+size_t s2v_complete_smem_bytes(int m, int n, int p, bool with_G) { return cmp_layout(m, n, p, with_G).total * 4; }
 
 __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int m = a.m, n = a.n, p = a.p, PP = pad4(p), M1 = m + 1;
     int PG = n + 1;
     if ((PG & 1) == 0) PG += 1;
-    const CmpLayout L = cmp_layout(m, n, p);
+    const CmpLayout L = cmp_layout(m, n, p, a.gram == nullptr);
     float* t2rrT = sm + L.t2rr;
     float* t7T = sm + L.t7;
     float* G = sm + L.G;
@@ -605,7 +606,7 @@ cudaError_t launch_s2v_forward(const S2vArgs& a0, int sm_count, long long smem_o
         if (grid > a.B) grid = a.B;
         s2v_bipartite_kernel<<<(int)grid, 256, smem, st>>>(a);
     } else {
-        const size_t smem = s2v_complete_smem_bytes(a.m, a.n, a.p);
+        const size_t smem = s2v_complete_smem_bytes(a.m, a.n, a.p, a.gram == nullptr);
         if ((long long)smem > smem_optin) { *why = "complete forward: G and embeddings do not fit in shared memory"; return cudaErrorInvalidValue; }
         cudaError_t e = cudaFuncSetAttribute(s2v_complete_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
