@@ -141,17 +141,47 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     const uint32_t hi_s = smem_u32(hi), lo_s = smem_u32(lo);
 
+    // software-pipelined producer: the global loads of chunk k + 1 are issued before chunk k is converted, stored and
+    // multiplied (RPW rows per warp and chunk, one column per lane)
+    constexpr int RPW = 256 / (GT / 32);
+    double vnext[RPW];
+    auto load_chunk = [&](long long lpq, int kc) {
+        const double* Ag = a.A + (size_t)lpq * m * n;
+        const double* bg = a.b + (size_t)lpq * m;
+        const double* cg = a.c + (size_t)lpq * n;
+        const int kabs = kc * KC + lane;
+#pragma unroll
+        for (int q = 0; q < RPW; ++q) {
+            const int r = warp + q * (GT / 32);
+            double v = 0.0;
+            if (r < m) {
+                if (kabs < n) v = __ldg(Ag + (size_t)r * n + kabs);
+                else if (kabs == n) v = __ldg(bg + r);
+            } else if (r == m) {
+                if (kabs < n) v = __ldg(cg + kabs);
+            }
+            vnext[q] = v;
+        }
+    };
+    if ((long long)blockIdx.x < a.B) load_chunk(blockIdx.x, 0);
+
     for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
-        const double* Ag = a.A + (size_t)lp * m * n;
-        const double* bg = a.b + (size_t)lp * m;
-        const double* cg = a.c + (size_t)lp * n;
 
         // The product runs on the UNNORMALISED rows G' = [[A | b] ; [c, 0]]: W'_ii is the squared row norm, so the
         // normalisation of the reference (s2v.py:145) becomes a row / column scaling of the accumulators in the
         // epilogue and A is read exactly once.
         for (int kc = 0; kc < nkc; ++kc) {
-            const int kabs = kc * KC + lane;
             const int stg = kc & 1;
+            // this chunk's values were loaded one chunk ago (vnext); start the loads of the NEXT chunk (the next
+            // instance's first one after the last) now, so that they fly during the convert / store / MMA issue below
+            double vcur[RPW];
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) vcur[q] = vnext[q];
+            {
+                const bool wrap = (kc + 1 == nkc);
+                const long long lpn = wrap ? lp + gridDim.x : lp;
+                if (lpn < a.B) load_chunk(lpn, wrap ? 0 : kc + 1);
+            }
             // the MMAs that read this stage two chunks ago must have finished before it is overwritten
             if (stg == 0 && pend0) { mbar_wait(bar, par0); par0 ^= 1; pend0 = false; }
             if (stg == 1 && pend1) { mbar_wait(bar + 1, par1); par1 ^= 1; pend1 = false; }
@@ -159,21 +189,17 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
             unsigned char* ls = lo + (size_t)stg * L.stage;
             // ---- produce the chunk: rows of G' -> (hi, lo) tf32 in the canonical UMMA layout -------------------------------
             const uint32_t coff = (uint32_t)(lane >> 2) * L.PLB + (lane & 3) * 4;
-#pragma unroll 16
-            for (int r = warp; r < rows_pl; r += GT / 32) {
-                double v = 0.0;
-                if (r < m) {
-                    if (kabs < n) v = __ldg(Ag + (size_t)r * n + kabs);
-                    else if (kabs == n) v = __ldg(bg + r);
-                } else if (r == m) {
-                    if (kabs < n) v = __ldg(cg + kabs);
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                const int r = warp + q * (GT / 32);
+                if (r < rows_pl) {
+                    const float g = (float)vcur[q];
+                    const uint32_t h = to_tf32(g);
+                    const uint32_t l = to_tf32(g - __uint_as_float(h));
+                    const uint32_t off = coff + (uint32_t)(r >> 3) * 128 + (r & 7) * 16;
+                    *reinterpret_cast<uint32_t*>(hs + off) = h;
+                    *reinterpret_cast<uint32_t*>(ls + off) = l;
                 }
-                const float g = (float)v;
-                const uint32_t h = to_tf32(g);
-                const uint32_t l = to_tf32(g - __uint_as_float(h));
-                const uint32_t off = coff + (uint32_t)(r >> 3) * 128 + (r & 7) * 16;
-                *reinterpret_cast<uint32_t*>(hs + off) = h;
-                *reinterpret_cast<uint32_t*>(ls + off) = l;
             }
             fence_proxy_async();
             __syncthreads();
