@@ -80,7 +80,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
 struct GramLayout {
     int RG;            // 8-row groups per plane
     int PLB;           // plane pitch in bytes
-    size_t hi, lo, stage, inv, bar, slot, total;   // hi / lo of stage 0; stage = byte offset between the two stages
+    size_t hi, lo, stage, inv, rowacc, bar, slot, total;   // hi / lo of stage 0; stage = byte offset between the two stages
 };
 __host__ __device__ inline GramLayout gram_layout(int m) {
     GramLayout L;
@@ -96,6 +96,8 @@ __host__ __device__ inline GramLayout gram_layout(int m) {
     off *= 2;                                  // second stage: produce chunk k+1 while the tensor core reads chunk k
     off = (off + 15) / 16 * 16;
     L.inv = off;  off += (size_t)(M1 + 16) * 4;
+    off = (off + 15) / 16 * 16;
+    L.rowacc = off; off += (size_t)4 * 3 * 256 * 4;      // epilogue: per-row partial sums of the four column groups
     off = (off + 15) / 16 * 16;
     L.bar = off;  off += 32;
     L.slot = off; off += 16;
@@ -114,6 +116,7 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
     const GramLayout L = gram_layout(m);
     unsigned char* hi = smem_raw + L.hi;
     unsigned char* lo = smem_raw + L.lo;
+    float* rowacc = reinterpret_cast<float*>(smem_raw + L.rowacc);   // [4 column groups][3: Wp, Wn, wc][256 rows]
     float* inv = reinterpret_cast<float*>(smem_raw + L.inv);       // 1 / |[a_i, b_i]| per row (1 for the cost node)
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + L.slot);
@@ -254,14 +257,17 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
             }
         }
         __syncthreads();
-        // pass 2: W_ij = W'_ij inv_i inv_j, relu row sums
-        if (warp < 4) {
+        // pass 2: W_ij = W'_ij inv_i inv_j, relu row sums.  All 16 warps: warp w reads the TMEM lanes of its quadrant
+        // (w % 4, the hardware's lane restriction) and every fourth 16-column chunk (w / 4); the four partial sums of a
+        // row meet in shared memory.
+        {
+            const int wq = warp & 3, wg = warp >> 2;
             for (int mt = 0; mt < MT; ++mt) {
-                const int i = mt * 128 + tid;
+                const int i = mt * 128 + wq * 32 + lane;
                 const float ii = (i < M1) ? inv[i] : 0.f;
                 float sp = 0.f, sn = 0.f, wl = 0.f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NN);
-                for (int c0 = 0; c0 < NN; c0 += 16) {
+                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * NN);
+                for (int c0 = 16 * wg; c0 < NN; c0 += 64) {
                     float v[16];
                     tmem_ld16(taddr + c0, v);
 #pragma unroll
@@ -274,13 +280,20 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
                         }
                     }
                 }
-                if (i < M1) {
-                    float* o = a.out + (size_t)lp * 3 * a.MP;
-                    o[i] = sp;
-                    o[a.MP + i] = sn;
-                    o[2 * a.MP + i] = wl;
-                }
+                float* ra = rowacc + (size_t)wg * 3 * 256 + (mt * 128 + wq * 32 + lane);
+                ra[0] = sp;
+                ra[256] = sn;
+                ra[512] = wl;
             }
+        }
+        tc_fence_before();
+        __syncthreads();
+        for (int i = tid; i < M1; i += GT) {
+            float* o = a.out + (size_t)lp * 3 * a.MP;
+            // fixed summation order over the four column groups: the result does not depend on warp timing
+            o[i] = (rowacc[i] + rowacc[768 + i]) + (rowacc[1536 + i] + rowacc[2304 + i]);
+            o[a.MP + i] = (rowacc[256 + i] + rowacc[1024 + i]) + (rowacc[1792 + i] + rowacc[2560 + i]);
+            o[2 * a.MP + i] = (rowacc[512 + i] + rowacc[1280 + i]) + (rowacc[2048 + i] + rowacc[2816 + i]);
         }
         tc_fence_before();
         __syncthreads();
