@@ -27,9 +27,11 @@ namespace ddb {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunkRows = 32;
 constexpr int kStages = 2;
-constexpr int kMaxU = 16;          // most columns per thread in the A pass (template parameter U <= kMaxU): n <= 128
+constexpr int kMaxU = 16;          // most columns per thread in the A pass (template parameter U <= kMaxU)
+// GB = column groups per row (2 for n <= 128, 4 for n <= 256): a row is shared by 4 * GB lanes of one warp, a warp
+// holds 8 / GB rows of a chunk and a chunk 64 / GB rows
+__host__ __device__ constexpr int chunk_rows(int GB) { return 64 / GB; }
 
 __host__ __device__ inline int dpad4(int v) { return (v + 3) & ~3; }
 __host__ __device__ inline int dpad8(int v) { return (v + 7) & ~7; }
@@ -37,19 +39,19 @@ __host__ __device__ inline int dpad8(int v) { return (v + 7) & ~7; }
 struct DenseLayout {   // byte offsets
     size_t ring, bars, mu, t7T, feat, part, yv, small, total;
 };
-__host__ __device__ inline DenseLayout dense_layout(int m, int n, int p) {
+__host__ __device__ inline DenseLayout dense_layout(int m, int n, int p, int GB) {
     const int MP = dpad4(m), PP8 = dpad8(p);
     const int G = kThreads / p;
     DenseLayout L;
     size_t off = 0;
-    L.ring = off;  off += (size_t)kStages * kChunkRows * n * 8;  off = (off + 15) & ~(size_t)15;
+    L.ring = off;  off += (size_t)kStages * chunk_rows(GB) * n * 8;  off = (off + 15) & ~(size_t)15;
     L.bars = off;  off += 64;
     L.mu = off;    off += (size_t)p * MP * 4;                    // final-round constraint embeddings [l][i]
     L.t7T = off;   off += (size_t)p * PP8 * 4;                   // t7T[l][k] = t7[k][l]
     L.feat = off;  off += (size_t)(5 * MP + 3 * dpad4(n)) * 4;   // rb, cos, Sp, Sn, b [m]; cj, Cp, Cn [n]
     L.part = off;                                                // scratch: column partials / round partials / head partials
     {
-        size_t a = (size_t)8 * 2 * 8 * kMaxU * 4;                // A pass: [warp][Cp|Cn][column slot]
+        size_t a = (size_t)8 * 2 * 4 * GB * kMaxU * 4;           // A pass: [warp][Cp|Cn][column slot]
         size_t b = (size_t)(G > 0 ? G : 1) * 2 * PP8 * 4;        // rounds: [group][c|v][l]
         size_t c = (size_t)(PP8 / 8) * MP * 2 * 4;               // head: [kgroup][node][2]
         size_t mx = a > b ? a : b;
@@ -66,12 +68,14 @@ __device__ __forceinline__ float relu(float v) { return fmaxf(v, 0.f); }
 
 // CM, CN, CP: compile-time (m, n, p) of a specialised instantiation (0 = take them from the arguments); the headline
 // shapes get one, which turns every shared-memory offset into an immediate and every node loop into straight-line code.
-template <int U, int CM, int CN, int CP>
-__global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArgs a) {
+template <int U, int CM, int CN, int CP, int GB>
+__global__ void __launch_bounds__(kThreads, (GB == 2) ? 2 : 1) s2v_bipartite_dense_kernel(S2vArgs a) {
     extern __shared__ __align__(128) unsigned char smraw[];
     const int m = CM ? CM : a.m, n = CN ? CN : a.n, p = CP ? CP : a.p, T = a.T;
     const int MP = dpad4(m), NP4 = dpad4(n), PP8 = dpad8(p);
-    const DenseLayout L = dense_layout(m, n, p);
+    constexpr int kChunkRows = chunk_rows(GB);
+    constexpr int RW = 8 / GB;                        // rows of a chunk per warp
+    const DenseLayout L = dense_layout(m, n, p, GB);
     double* ring = reinterpret_cast<double*>(smraw + L.ring);
     uint64_t* full = reinterpret_cast<uint64_t*>(smraw + L.bars);
     float* mu = reinterpret_cast<float*>(smraw + L.mu);
@@ -146,9 +150,9 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
     __syncthreads();
 
     // ---- A-pass roles -------------------------------------------------------------------------------------------------
-    const int SL = ((n + 1) / 2 + 3) & ~3;            // columns per half (multiple of 4)
-    const int as = lane & 3, ar = (lane >> 2) & 3, ag = lane >> 4;
-    const int arow = warp * 4 + ar;                   // my row inside a chunk
+    const int SL = ((n + GB - 1) / GB + 3) & ~3;      // columns per group (multiple of 4)
+    const int as = lane & 3, ar = (lane >> 2) & (RW - 1), ag = lane / (4 * RW);
+    const int arow = warp * RW + ar;                  // my row inside a chunk
     const int col0 = ag * SL + as;                    // my columns: col0 + 4u
     const int nchunk = (m + kChunkRows - 1) / kChunkRows;
     const size_t row_bytes = (size_t)n * 8;
@@ -215,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
             for (int u = 0; u < U; ++u) {
                 // columns that are valid for every thread need no mask (compile-time when the shape is specialised);
                 // padding columns read a valid entry (the row's first) and are multiplied by 0
-                const bool always = (CN != 0) && (4 * u + 3 < SL) && (SL + 4 * u + 3 < CN);
+                const bool always = (CN != 0) && (4 * u + 3 < SL) && ((GB - 1) * SL + 4 * u + 3 < CN);
                 float v;
                 if (always) {
                     v = (float)rp[col0 + 4 * u];
@@ -231,13 +235,15 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
                 sx += v;
             }
             sparse |= (rowok && amin == 0.f);
-            // the 8 threads of a row are lanes {as, ag} of one warp: xor 1, 2, 16
+            // the 4 * GB threads of a row are lanes {as, ag} of one warp: xor 1, 2 and the group bits
 #pragma unroll
-            for (int off = 1; off <= 16; off = (off == 2) ? 16 : off * 2) {
-                ss += __shfl_xor_sync(0xffffffffu, ss, off);
-                cs += __shfl_xor_sync(0xffffffffu, cs, off);
-                sa += __shfl_xor_sync(0xffffffffu, sa, off);
-                sx += __shfl_xor_sync(0xffffffffu, sx, off);
+            for (int off = 1; off <= 16; off *= 2) {
+                if (off == 1 || off == 2 || off >= 4 * RW) {       // lane bits of the column phase and of the column group
+                    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+                    cs += __shfl_xor_sync(0xffffffffu, cs, off);
+                    sa += __shfl_xor_sync(0xffffffffu, sa, off);
+                    sx += __shfl_xor_sync(0xffffffffu, sx, off);
+                }
             }
             const float sp = 0.5f * (sa + sx);                 // sum_j relu(a_ij)
             const float bi = bsm[rowok ? i : 0];
@@ -270,15 +276,17 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
         for (int u = 0; u < U; ++u) {
             accp[u] += __shfl_xor_sync(0xffffffffu, accp[u], 4);
             accn[u] += __shfl_xor_sync(0xffffffffu, accn[u], 4);
-            accp[u] += __shfl_xor_sync(0xffffffffu, accp[u], 8);
-            accn[u] += __shfl_xor_sync(0xffffffffu, accn[u], 8);
+            if (RW == 4) {
+                accp[u] += __shfl_xor_sync(0xffffffffu, accp[u], 8);
+                accn[u] += __shfl_xor_sync(0xffffffffu, accn[u], 8);
+            }
         }
         if (ar == 0) {
-            // slot = (ag, as, u) -> [warp][2][8 * kMaxU]
+            // slot = (ag, as, u) -> [warp][2][4 * GB * kMaxU]
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                part[(warp * 2 + 0) * 8 * kMaxU + (ag * 4 + as) * kMaxU + u] = accp[u];
-                part[(warp * 2 + 1) * 8 * kMaxU + (ag * 4 + as) * kMaxU + u] = accn[u];
+                part[(warp * 2 + 0) * 4 * GB * kMaxU + (ag * 4 + as) * kMaxU + u] = accp[u];
+                part[(warp * 2 + 1) * 4 * GB * kMaxU + (ag * 4 + as) * kMaxU + u] = accn[u];
             }
         }
         if (__syncthreads_or(sparse)) {
@@ -294,8 +302,8 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
             float sp2 = 0.f, sn2 = 0.f;
 #pragma unroll
             for (int w = 0; w < 8; ++w) {
-                sp2 += part[(w * 2 + 0) * 8 * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
-                sn2 += part[(w * 2 + 1) * 8 * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
+                sp2 += part[(w * 2 + 0) * 4 * GB * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
+                sn2 += part[(w * 2 + 1) * 4 * GB * kMaxU + (g2 * 4 + s2) * kMaxU + u2];
             }
             Cp[j] = sp2;
             Cn[j] = sn2;
@@ -514,19 +522,23 @@ __global__ void __launch_bounds__(kThreads, 2) s2v_bipartite_dense_kernel(S2vArg
 }  // namespace
 
 // Shapes the dense kernel covers; everything else (and every instance with a zero coefficient) goes to the general kernel.
-static int dense_u(int n) { return ((((n + 1) / 2 + 3) & ~3) + 3) / 4; }   // columns per thread: ceil(SL / 4)
-
-bool s2v_bipartite_dense_supported(int m, int n, int p, const void* A, long long smem_optin) {
-    if (dense_u(n) > kMaxU || p > kThreads || p < 1) return false;
-    if (((size_t)m * n * 8) % 16 != 0 || ((size_t)n * 8 * kChunkRows) % 16 != 0) return false;   // bulk-copy alignment
-    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
-    return (long long)dense_layout(m, n, p).total <= smem_optin;
+static int dense_groups(int n) { return n <= 128 ? 2 : 4; }
+static int dense_u(int n) {                       // columns per thread: ceil(SL / 4)
+    const int GB = dense_groups(n);
+    return ((((n + GB - 1) / GB + 3) & ~3) + 3) / 4;
 }
 
-template <int U, int CM, int CN, int CP>
+bool s2v_bipartite_dense_supported(int m, int n, int p, const void* A, long long smem_optin) {
+    if (n > 256 || dense_u(n) > kMaxU || p > kThreads || p < 1) return false;
+    if (((size_t)m * n * 8) % 16 != 0) return false;                                  // bulk-copy alignment of every instance
+    if ((reinterpret_cast<uintptr_t>(A) & 15) != 0) return false;
+    return (long long)dense_layout(m, n, p, dense_groups(n)).total <= smem_optin;
+}
+
+template <int U, int CM, int CN, int CP, int GB>
 static cudaError_t launch_dense_u(const S2vArgs& a, int sm_count, cudaStream_t st) {
-    auto kern = s2v_bipartite_dense_kernel<U, CM, CN, CP>;
-    const size_t smem = dense_layout(a.m, a.n, a.p).total;
+    auto kern = s2v_bipartite_dense_kernel<U, CM, CN, CP, GB>;
+    const size_t smem = dense_layout(a.m, a.n, a.p, GB).total;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
@@ -542,13 +554,14 @@ static cudaError_t launch_dense_u(const S2vArgs& a, int sm_count, cudaStream_t s
 cudaError_t launch_s2v_bipartite_dense(const S2vArgs& a, int sm_count, cudaStream_t st) {
     // specialised instantiations: BASELINE.json configs[1] shape with the reference's benchmark model (p = 40,
     // benchmark.py:166-167) and configs[0] shape with the run.py / phase_transitions model sizes (p = 12, 13)
-    if (a.m == 200 && a.n == 100 && a.p == 40) return launch_dense_u<13, 200, 100, 40>(a, sm_count, st);
-    if (a.m == 50 && a.n == 20 && a.p == 12) return launch_dense_u<3, 50, 20, 12>(a, sm_count, st);
+    if (a.m == 200 && a.n == 100 && a.p == 40) return launch_dense_u<13, 200, 100, 40, 2>(a, sm_count, st);
+    if (a.m == 50 && a.n == 20 && a.p == 12) return launch_dense_u<3, 50, 20, 12, 2>(a, sm_count, st);
     const int u = dense_u(a.n);
-    if (u <= 3) return launch_dense_u<3, 0, 0, 0>(a, sm_count, st);
-    if (u <= 7) return launch_dense_u<7, 0, 0, 0>(a, sm_count, st);
-    if (u <= 13) return launch_dense_u<13, 0, 0, 0>(a, sm_count, st);
-    return launch_dense_u<kMaxU, 0, 0, 0>(a, sm_count, st);
+    if (dense_groups(a.n) == 4) return launch_dense_u<kMaxU, 0, 0, 0, 4>(a, sm_count, st);   // 128 < n <= 256, e.g. (500,250)
+    if (u <= 3) return launch_dense_u<3, 0, 0, 0, 2>(a, sm_count, st);
+    if (u <= 7) return launch_dense_u<7, 0, 0, 0, 2>(a, sm_count, st);
+    if (u <= 13) return launch_dense_u<13, 0, 0, 0, 2>(a, sm_count, st);
+    return launch_dense_u<kMaxU, 0, 0, 0, 2>(a, sm_count, st);
 }
 
 }  // namespace ddb
