@@ -44,6 +44,35 @@ __device__ __forceinline__ void node_matvec(const float* __restrict__ Wt, int PP
     }
 }
 
+// out[k][q] = sum_l Wt[l][k] * X[l][q]: register tile, thread = 4 nodes x 4 outputs (two LDS.128 per 16 FMAs).  The pitches
+// px / po are multiples of 4 floats, nq4 = number of nodes rounded up to 4 (the padding nodes hold garbage: never read).
+__device__ __forceinline__ void node_matmul_tiled(const float* __restrict__ Wt, int PP, int p, const float* X, int px,
+                                                  float* out, int po, int nq4, int tid, int nt) {
+    const int NG = nq4 / 4, KG = PP / 4;
+    for (int w = tid; w < NG * KG; w += nt) {
+        const int ng = w % NG, kg = w / NG;
+        float acc[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+        for (int l = 0; l < p; ++l) {
+            const float4 xv = *reinterpret_cast<const float4*>(X + l * px + 4 * ng);
+            const float4 wv = *reinterpret_cast<const float4*>(Wt + l * PP + 4 * kg);
+            const float xq[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(wr[r], xq[q], acc[q][r]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (4 * kg + r < p)
+                *reinterpret_cast<float4*>(out + (4 * kg + r) * po + 4 * ng) = make_float4(acc[0][r], acc[1][r], acc[2][r], acc[3][r]);
+    }
+}
+
 // y[k] = sum_l W[k][l] x[l] (row-major W in global memory), one warp per output.
 __device__ __forceinline__ void small_matvec(const float* __restrict__ W, int p, const float* x, float* y, int warp,
                                              int lane, int nw) {
@@ -356,8 +385,9 @@ __host__ __device__ inline CmpLayout cmp_layout(int m, int n, int p, bool with_G
     L.t2rr = off; off += (size_t)p * PP;
     L.t7 = off;   off += (size_t)p * PP;
     L.G = off;    off += with_G ? (size_t)(m + 1) * PG : 0;
-    L.mu = off;   off += (size_t)p * (m + 1);
-    L.mu2 = off;  off += (size_t)p * (m + 1);
+    off = (off + 3) & ~(size_t)3;
+    L.mu = off;   off += (size_t)p * pad4(m + 1);      // pitch pad4(m + 1): float4 rows for the register-tiled products
+    L.mu2 = off;  off += (size_t)p * pad4(m + 1);
     L.vecs = off; off += (size_t)3 * (m + 1) + 16 * PP + 64;
     L.total = off;
     return L;
@@ -366,7 +396,7 @@ size_t s2v_complete_smem_bytes(int m, int n, int p, bool with_G) { return cmp_la
 
 __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
     extern __shared__ __align__(16) float sm[];
-    const int m = a.m, n = a.n, p = a.p, PP = pad4(p), M1 = m + 1;
+    const int m = a.m, n = a.n, p = a.p, PP = pad4(p), M1 = m + 1, MP = pad4(m + 1);
     int PG = n + 1;
     if ((PG & 1) == 0) PG += 1;
     const CmpLayout L = cmp_layout(m, n, p, a.gram == nullptr);
@@ -433,7 +463,7 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
                 Wn[i] = __ldg(gr + a.gram_pitch + i);
                 wc[i] = __ldg(gr + 2 * a.gram_pitch + i);
             }
-            for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
+            for (int e = tid; e < p * MP; e += nt) mu[e] = 0.f;
             __syncthreads();
         } else {
             // ---- G = [normalize([A | b]) ; [c, 0]]  (normalisation in fp64 as the reference does, s2v.py:145) ----------------
@@ -450,7 +480,7 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
                 if (lane == 0) G[i * PG + n] = (float)(bi * inv);
             }
             for (int j = tid; j <= n; j += nt) G[m * PG + j] = (j < n) ? (float)cg[j] : 0.f;
-            for (int e = tid; e < p * M1; e += nt) mu[e] = 0.f;
+            for (int e = tid; e < p * MP; e += nt) mu[e] = 0.f;
             __syncthreads();
 
             // ---- fused Gram + relu row sums: W_ij = <G_i, G_j>, never stored ----------------------------------------------------
@@ -516,17 +546,18 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
         for (int t = 0; t < a.T; ++t) {
             for (int l = warp; l < p; l += nw) {
                 float sr = 0.f;
-                for (int i = lane; i < m; i += 32) sr += mu[l * M1 + i];
+                for (int i = lane; i < m; i += 32) sr += mu[l * MP + i];
                 sr = warp_sumf(sr);
-                if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * M1 + m]; }
+                if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * MP + m]; }
             }
             __syncthreads();
             small_matvec(t2rc, p, muc, y1, warp, lane, nw);
             small_matvec(t2cr, p, meanr, y2, warp, lane, nw);
-            node_matvec(t2rrT, PP, p, mu, M1, mu2, M1, m, tid, nt);          // t2rr . mu_r
+            node_matmul_tiled(t2rrT, PP, p, mu, MP, mu2, MP, pad4(m), tid, nt);   // t2rr . mu_r
             __syncthreads();
-            for (int e = tid; e < p * M1; e += nt) {
-                const int l = e / M1, q = e - l * M1;
+            for (int e = tid; e < p * MP; e += nt) {
+                const int l = e / MP, q = e - l * MP;
+                if (q >= M1) continue;
                 float val;
                 if (q < m) {
                     val = __ldg(t0 + l) + __ldg(t1 + l) + mu2[e] + y1[l] + w3p[l] * Wp[q] + w3n[l] * Wn[q] + scal[0];
@@ -541,9 +572,9 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
         // ---- head -----------------------------------------------------------------------------------------------------------------
         for (int l = warp; l < p; l += nw) {
             float sr = 0.f;
-            for (int i = lane; i < m; i += 32) sr += mu[l * M1 + i];
+            for (int i = lane; i < m; i += 32) sr += mu[l * MP + i];
             sr = warp_sumf(sr);
-            if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * M1 + m]; }
+            if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * MP + m]; }
         }
         __syncthreads();
         small_matvec(t6r, p, meanr, tmp1, warp, lane, nw);
@@ -552,27 +583,18 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
         for (int l = tid; l < p; l += nt) u6[l] = fmaxf(tmp1[l] + tmp2[l], 0.f);
         __syncthreads();
         const int W8 = 2 * p;
+        node_matmul_tiled(t7T, PP, p, mu, MP, mu2, MP, pad4(m), tid, nt);     // t7 . mu_r (the head's only p x p x m product)
+        __syncthreads();
         for (int i = tid; i < m; i += nt) {
             float s0 = 0.f, s1 = 0.f;
             for (int l = 0; l < p; ++l) {
                 s0 = fmaf(__ldg(t8 + l), u6[l], s0);
                 s1 = fmaf(__ldg(t8 + W8 + l), u6[l], s1);
             }
-            for (int kb = 0; kb < PP; kb += 4) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                for (int l = 0; l < p; ++l) {
-                    const float x = mu[l * M1 + i];
-                    const float4 w = *reinterpret_cast<const float4*>(t7T + l * PP + kb);
-                    a0 = fmaf(w.x, x, a0); a1 = fmaf(w.y, x, a1); a2 = fmaf(w.z, x, a2); a3 = fmaf(w.w, x, a3);
-                }
-                const float r[4] = {fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f)};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (kb + u < p) {
-                        s0 = fmaf(__ldg(t8 + p + kb + u), r[u], s0);
-                        s1 = fmaf(__ldg(t8 + W8 + p + kb + u), r[u], s1);
-                    }
-                }
+            for (int kk = 0; kk < p; ++kk) {
+                const float z = fmaxf(mu2[kk * MP + i], 0.f);          // relu(t7 mu_i), product computed above
+                s0 = fmaf(__ldg(t8 + p + kk), z, s0);
+                s1 = fmaf(__ldg(t8 + W8 + p + kk), z, s1);
             }
             const float mx = fmaxf(s0, s1);
             const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
