@@ -28,7 +28,7 @@ def bind_to_gpu_numa_node(device_index):
             return None
         os.sched_setaffinity(0, allowed)
         return node
-    except (OSError, ValueError, AttributeError):
+    except Exception:        # no CUDA device, no sysfs, unknown torch attribute, ...: placement is best effort
         return None
 
 

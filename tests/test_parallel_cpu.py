@@ -124,3 +124,12 @@ def test_evaluation_entry_points_on_cpu():
     crit = torch.nn.NLLLoss(weight=torch.tensor([0.5, 0.5]), reduction='sum')
     perf = performance(loader, model, crit, p_train)
     assert all(abs(perf[k] - acc[k]) < 1e-12 for k in acc)
+
+
+def test_numa_binding_is_best_effort():
+    """Without a GPU (or without a readable topology) the helper changes nothing and reports None."""
+    before = os.sched_getaffinity(0)
+    node = parallel.bind_to_gpu_numa_node(0)
+    assert node is None or isinstance(node, int)
+    if not torch.cuda.is_available():
+        assert node is None and os.sched_getaffinity(0) == before
