@@ -10,6 +10,7 @@
 
 namespace ddb {
 size_t generic_smem_bytes(int m, int n, bool smem_tab);
+int generic_block_threads(int m, int n, bool smem_tab);
 cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, int block, cudaStream_t st);
 cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, int n, double density, double* A,
                             double* b, double* c, double* x0, int sm_count, cudaStream_t st, int* launches);
@@ -228,18 +229,11 @@ extern "C" int ddb_generate_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instan
     return DDB_OK;
 }
 
-static int pick_block(int m, int n) {
-    const long long e = (long long)m * n;
-    if (e <= 2048) return 128;
-    if (e <= 8192) return 256;
-    if (e <= 16384) return 512;
-    return 1024;
-}
 
 static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_t st) {
     const int m = a.m, n = a.n;
     const bool smem_tab = (plan == 1);
-    const int block = pick_block(m, n);
+    const int block = ddb::generic_block_threads(m, n, smem_tab);
     const size_t smem = ddb::generic_smem_bytes(m, n, smem_tab);
     // persistent grid: as many CTAs as are co-resident (bounded by shared memory and threads), never more than B
     int per_sm = (int)((size_t)ctx->smem_optin / (smem + 1024));

@@ -64,8 +64,10 @@ __host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
 
 size_t generic_smem_bytes(int m, int n, bool smem_tab) { return make_layout(m, n, smem_tab).total; }
 
-template <bool kSmemTab, int CPL>
-__global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
+// NTMAX: largest block the instantiation is launched with (1024, or 512 for the wide global-memory shapes, which trades
+// warps for registers: more loads in flight per lane)
+template <bool kSmemTab, int CPL, int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = a.m, n = a.n;
     const Layout L = make_layout(m, n, kSmemTab);
@@ -144,67 +146,40 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
             pr[q] = (j < n) ? P[(size_t)r * n + j] : 0.0;
         }
         const double sr = s[r];
-        if (crash_mode) {
-            for (int i = warp; i < m; i += nw) {
-                const double f = colbuf[i];
-                if (f != 0.0) {
-                    double* Pi = P + (size_t)i * n;
+        // RB rows per step, so that RB * CPL loads are in flight per lane (the global-memory tableau is bound by L2
+        // round-trip latency): the register budget decides RB -- 64 registers at 1024 threads, 128 at 512
+        constexpr int RB = (NTMAX <= 512) ? ((CPL <= 8) ? 4 : 2) : ((CPL <= 2) ? 2 : 1);
+        const int nrows = crash_mode ? m : nlive_sm;           // the crash updates every row, phases 1 / 2 the live ones
+        for (int q0 = warp; q0 < nrows; q0 += RB * nw) {
+            int ix[RB];
+            double fx[RB];
+            double vx[RB][CPL];
 #pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const int j = lane + 32 * q;
-                        if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
-                    }
-                    if (lane == 0) s[i] = fma(-f, sr, s[i]);
-                }
+            for (int b = 0; b < RB; ++b) {
+                const int qq = q0 + b * nw;
+                const bool ok = qq < nrows;
+                ix[b] = ok ? (crash_mode ? qq : liveidx[qq]) : 0;
+                fx[b] = ok ? colbuf[ix[b]] : 0.0;
             }
-        } else if constexpr (CPL <= 4) {
-            // phases 1 / 2: only the live rows, two rows per step so that 2 * CPL loads are in flight per lane
-            const int nl = nlive_sm;
-            for (int q0 = warp; q0 < nl; q0 += 2 * nw) {
-                const int ia = liveidx[q0];
-                const int ib = (q0 + nw < nl) ? liveidx[q0 + nw] : ia;
-                const double fa = colbuf[ia];
-                const double fb = (q0 + nw < nl) ? colbuf[ib] : 0.0;
-                double* Pa = P + (size_t)ia * n;
-                double* Pb = P + (size_t)ib * n;
-                double va[CPL], vb[CPL];
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                const double* Pi = P + (size_t)ix[b] * n;
 #pragma unroll
                 for (int q = 0; q < CPL; ++q) {
                     const int j = lane + 32 * q;
-                    va[q] = (j < n && fa != 0.0) ? Pa[j] : 0.0;
-                    vb[q] = (j < n && fb != 0.0) ? Pb[j] : 0.0;
-                }
-                if (fa != 0.0) {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const int j = lane + 32 * q;
-                        if (j < n) Pa[j] = fma(-fa, pr[q], va[q]);
-                    }
-                    if (lane == 0) s[ia] = fma(-fa, sr, s[ia]);
-                }
-                if (fb != 0.0) {
-#pragma unroll
-                    for (int q = 0; q < CPL; ++q) {
-                        const int j = lane + 32 * q;
-                        if (j < n) Pb[j] = fma(-fb, pr[q], vb[q]);
-                    }
-                    if (lane == 0) s[ib] = fma(-fb, sr, s[ib]);
+                    vx[b][q] = (j < n && fx[b] != 0.0) ? Pi[j] : 0.0;
                 }
             }
-        } else {
-            // wide rows (n > 128): the 64-register budget of a 1024-thread CTA holds one row's loads at a time
-            const int nl = nlive_sm;
-            for (int q0 = warp; q0 < nl; q0 += nw) {
-                const int i = liveidx[q0];
-                const double f = colbuf[i];
-                if (f != 0.0) {
-                    double* Pi = P + (size_t)i * n;
+#pragma unroll
+            for (int b = 0; b < RB; ++b) {
+                if (fx[b] != 0.0) {
+                    double* Pi = P + (size_t)ix[b] * n;
 #pragma unroll
                     for (int q = 0; q < CPL; ++q) {
                         const int j = lane + 32 * q;
-                        if (j < n) Pi[j] = fma(-f, pr[q], Pi[j]);
+                        if (j < n) Pi[j] = fma(-fx[b], pr[q], vx[b][q]);
                     }
-                    if (lane == 0) s[i] = fma(-f, sr, s[i]);
+                    if (lane == 0) s[ix[b]] = fma(-fx[b], sr, s[ix[b]]);
                 }
             }
         }
@@ -634,30 +609,47 @@ __global__ void __launch_bounds__(1024, 1) simplex_generic_kernel(SolveArgs a) {
 // ---------------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------------
-template <bool kSmemTab, int CPL>
+template <bool kSmemTab, int CPL, int NTMAX>
 static cudaError_t launch_one(const SolveArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = simplex_generic_kernel<kSmemTab, CPL>;
+    auto kern = simplex_generic_kernel<kSmemTab, CPL, NTMAX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<grid, block, smem, st>>>(a);
     return cudaGetLastError();
 }
 
+// block size of the generic kernel for a shape: the wide global-memory shapes run 512 threads (see NTMAX)
+int generic_block_threads(int m, int n, bool smem_tab) {
+    const long long e = (long long)m * n;
+    if (e <= 2048) return 128;
+    if (e <= 8192) return 256;
+    if (e <= 16384) return 512;
+    if (!smem_tab && n > 128) return 512;
+    return 1024;
+}
+
 cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, int block, cudaStream_t st) {
     const size_t smem = generic_smem_bytes(a.m, a.n, smem_tab);
     const int cpl = (a.n + 31) / 32;
-#define DDB_DISPATCH(T)                                                        \
-    do {                                                                       \
-        if (cpl <= 1) return launch_one<T, 1>(a, grid, block, smem, st);       \
-        if (cpl <= 2) return launch_one<T, 2>(a, grid, block, smem, st);       \
-        if (cpl <= 4) return launch_one<T, 4>(a, grid, block, smem, st);       \
-        if (cpl <= 8) return launch_one<T, 8>(a, grid, block, smem, st);       \
-        if (cpl <= 16) return launch_one<T, 16>(a, grid, block, smem, st);     \
-        return cudaErrorInvalidValue;                                          \
-    } while (0)
-    if (smem_tab) DDB_DISPATCH(true);
-    DDB_DISPATCH(false);
-#undef DDB_DISPATCH
+    if (smem_tab) {
+        if (cpl <= 1) return launch_one<true, 1, 1024>(a, grid, block, smem, st);
+        if (cpl <= 2) return launch_one<true, 2, 1024>(a, grid, block, smem, st);
+        if (cpl <= 4) return launch_one<true, 4, 1024>(a, grid, block, smem, st);
+        if (cpl <= 8) return launch_one<true, 8, 1024>(a, grid, block, smem, st);
+        if (cpl <= 16) return launch_one<true, 16, 1024>(a, grid, block, smem, st);
+        return cudaErrorInvalidValue;
+    }
+    if (cpl <= 1) return launch_one<false, 1, 1024>(a, grid, block, smem, st);
+    if (cpl <= 2) return launch_one<false, 2, 1024>(a, grid, block, smem, st);
+    if (cpl <= 4) return launch_one<false, 4, 1024>(a, grid, block, smem, st);
+    if (block <= 512) {
+        if (cpl <= 8) return launch_one<false, 8, 512>(a, grid, block, smem, st);
+        if (cpl <= 16) return launch_one<false, 16, 512>(a, grid, block, smem, st);
+        return cudaErrorInvalidValue;
+    }
+    if (cpl <= 8) return launch_one<false, 8, 1024>(a, grid, block, smem, st);
+    if (cpl <= 16) return launch_one<false, 16, 1024>(a, grid, block, smem, st);
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace ddb
