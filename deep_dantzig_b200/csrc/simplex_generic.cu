@@ -618,13 +618,13 @@ static cudaError_t launch_one(const SolveArgs& a, int grid, int block, size_t sm
     return cudaGetLastError();
 }
 
-// block size of the generic kernel for a shape: the wide global-memory shapes run 512 threads (see NTMAX)
+// block size of the generic kernel for a shape: the large global-memory shapes run 512 threads (see NTMAX)
 int generic_block_threads(int m, int n, bool smem_tab) {
     const long long e = (long long)m * n;
     if (e <= 2048) return 128;
     if (e <= 8192) return 256;
     if (e <= 16384) return 512;
-    if (!smem_tab && n > 128) return 512;
+    if (!smem_tab) return 512;          // global-memory tableau: trade warps for registers (loads in flight)
     return 1024;
 }
 
@@ -639,14 +639,15 @@ cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, 
         if (cpl <= 16) return launch_one<true, 16, 1024>(a, grid, block, smem, st);
         return cudaErrorInvalidValue;
     }
-    if (cpl <= 1) return launch_one<false, 1, 1024>(a, grid, block, smem, st);
-    if (cpl <= 2) return launch_one<false, 2, 1024>(a, grid, block, smem, st);
-    if (cpl <= 4) return launch_one<false, 4, 1024>(a, grid, block, smem, st);
-    if (block <= 512) {
+    if (block <= 512 && (long long)a.m * a.n > 16384) {      // generic_block_threads(): large global-memory shapes
+        if (cpl <= 4) return launch_one<false, 4, 512>(a, grid, block, smem, st);
         if (cpl <= 8) return launch_one<false, 8, 512>(a, grid, block, smem, st);
         if (cpl <= 16) return launch_one<false, 16, 512>(a, grid, block, smem, st);
         return cudaErrorInvalidValue;
     }
+    if (cpl <= 1) return launch_one<false, 1, 1024>(a, grid, block, smem, st);
+    if (cpl <= 2) return launch_one<false, 2, 1024>(a, grid, block, smem, st);
+    if (cpl <= 4) return launch_one<false, 4, 1024>(a, grid, block, smem, st);
     if (cpl <= 8) return launch_one<false, 8, 1024>(a, grid, block, smem, st);
     if (cpl <= 16) return launch_one<false, 16, 1024>(a, grid, block, smem, st);
     return cudaErrorInvalidValue;

@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from deep_dantzig_b200 import solver, _lib
 
-cases = [(500, 250, 592, -1), (300, 150, 1184, -1), (50, 20, 65536, -1), (200, 100, 4736, 1), (100, 50, 16384, -1)]
+cases = [(500, 250, 592, -1), (300, 150, 1184, -1), (400, 100, 2368, -1), (50, 20, 65536, -1), (200, 100, 4736, 1), (200, 100, 4736, 2), (100, 50, 16384, -1)]
 ctx = _lib.context(0)
 for m, n, B, plan in cases:
     ctx.set_solve_plan(plan)
