@@ -32,7 +32,13 @@ struct Sel {
 
 struct Layout {
     size_t tab, s, g, gh, colbuf, xbuf, sig, rowvar, colvar, colvar0, where, order, rowfree, liveidx, rowstate, red, cands, sel, bar, total;
+    size_t ring, rbar;   // global-memory plan, 512-thread instantiation: per-warp ring of tableau rows filled by bulk TMA
+    int ring_k;          // slots per warp (0: no ring -- odd n or no room -- the update loads rows through registers)
 };
+
+constexpr int kRingWarps = 16;        // warps of the 512-thread instantiation
+constexpr int kRingMaxSlots = 8;
+constexpr size_t kSmemBudget = 232448 - 1024 - 64;   // 227 KB opt-in minus the launcher's margin and the static variables
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -58,6 +64,21 @@ __host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
     L.cands = off;    off += align_up(32 * sizeof(Cand), 16);
     L.sel = off;      off += align_up(sizeof(Sel), 16);
     L.bar = off;      off += 16;
+    L.ring = L.rbar = 0;
+    L.ring_k = 0;
+    if (!smem_tab && (long long)m * n > 16384 && n % 2 == 0) {
+        const size_t base = align_up(off, 128);
+        const size_t bars = (size_t)kRingWarps * kRingMaxSlots * 8;
+        const size_t row = (size_t)n * 8;
+        if (base + bars + 2 * kRingWarps * row <= kSmemBudget) {
+            size_t k = (kSmemBudget - base - bars) / (kRingWarps * row);
+            if (k > (size_t)kRingMaxSlots) k = kRingMaxSlots;
+            L.ring_k = (int)k;
+            L.rbar = base;
+            L.ring = base + bars;
+            off = L.ring + (size_t)kRingWarps * k * row;
+        }
+    }
     L.total = off;
     return L;
 }
@@ -104,6 +125,22 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
         }
         __syncthreads();
     }
+    // Streaming update of the global-memory plan: every warp owns ring_k row slots and one mbarrier per slot; its lane 0
+    // bulk-copies (cp.async.bulk, SASS UBLKCP) the next rows of the warp's share into free slots while the warp runs the
+    // FMAs of the oldest one out of shared memory and stores the result straight back to the slab.  The copies need no
+    // registers, so ring_k rows (up to 16 KB) per warp are in flight instead of the 32 loads per lane of the register path.
+    constexpr bool kRing = !kSmemTab && NTMAX <= 512;
+    const int ring_k = (kRing && nw == kRingWarps) ? L.ring_k : 0;
+    double* wring = reinterpret_cast<double*>(smem_raw + L.ring) + (size_t)warp * ring_k * n;
+    uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + L.rbar) + warp * kRingMaxSlots;
+    unsigned r_issued = 0, r_done = 0;     // rows this warp has requested / consumed since the kernel started (warp-uniform)
+    if (kRing && ring_k > 0) {
+        if (lane == 0) {
+            for (int q = 0; q < ring_k; ++q) mbar_init(&wbar[q], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
 
     // One pivot on (r, k).  Every thread calls it with the same arguments (read from *sel after a barrier).
     // One pivot on (r, k).  Every thread calls it with the same arguments (read from *sel after a barrier).
@@ -137,6 +174,9 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
             g[k] = 0.0;
             gh[k] = 0.0;
         }
+        // every generic-proxy store of this thread to the slab (this step's and the previous update's) is ordered before
+        // the bulk copies (async proxy) that are issued after the barrier
+        if (kRing && ring_k > 0) fence_proxy_async_all();
         __syncthreads();
         // C: rank-1 update of every other row, of s, g and ghat
         double pr[CPL];
@@ -150,6 +190,39 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
         // round-trip latency): the register budget decides RB -- 64 registers at 1024 threads, 128 at 512
         constexpr int RB = (NTMAX <= 512) ? ((CPL <= 8) ? 4 : 2) : ((CPL <= 2) ? 2 : 1);
         const int nrows = crash_mode ? m : nlive_sm;           // the crash updates every row, phases 1 / 2 the live ones
+        if (kRing && ring_k > 0) {
+            const uint32_t rowbytes = (uint32_t)n * 8u;
+            int tp = warp;                                     // producer cursor over this warp's share of the row list
+            for (int q0 = warp; q0 < nrows; q0 += nw) {
+                const int ix = crash_mode ? q0 : liveidx[q0];
+                const double f = colbuf[ix];
+                if (f == 0.0) continue;                        // warp-uniform
+                while ((int)(r_issued - r_done) < ring_k && tp < nrows) {
+                    const int ixp = crash_mode ? tp : liveidx[tp];
+                    tp += nw;
+                    if (colbuf[ixp] != 0.0) {
+                        const unsigned sl = r_issued % (unsigned)ring_k;
+                        if (lane == 0) {
+                            mbar_expect_tx(&wbar[sl], rowbytes);
+                            tma_load_1d(wring + (size_t)sl * n, P + (size_t)ixp * n, rowbytes, &wbar[sl]);
+                        }
+                        ++r_issued;
+                    }
+                }
+                const unsigned sl = r_done % (unsigned)ring_k;
+                mbar_wait(&wbar[sl], (r_done / (unsigned)ring_k) & 1u);
+                const double* src = wring + (size_t)sl * n;
+                double* Pi = P + (size_t)ix * n;
+#pragma unroll
+                for (int q = 0; q < CPL; ++q) {
+                    const int j = lane + 32 * q;
+                    if (j < n) Pi[j] = fma(-f, pr[q], src[j]);
+                }
+                if (lane == 0) s[ix] = fma(-f, sr, s[ix]);
+                __syncwarp();                                  // every lane has read the slot before lane 0 refills it
+                ++r_done;
+            }
+        } else
         for (int q0 = warp; q0 < nrows; q0 += RB * nw) {
             int ix[RB];
             double fx[RB];
