@@ -128,6 +128,29 @@ def test_plans_agree_bit_for_bit(cuda_device):
     assert (r1['x'][ok] == r2['x'][ok]).all() and (r1['obj'][ok] == r2['obj'][ok]).all()
 
 
+@pytest.mark.parametrize('density', [1.0, 0.1])
+def test_streamed_global_tableau_agrees_bit_for_bit(cuda_device, density):
+    """(200,100) is a shape where the global-memory plan streams the tableau through its bulk-TMA row ring
+    (m n > 16384, even n) while the shared-memory plan still fits: same arithmetic, bit for bit -- dense instances and
+    sparse ones (entries of the entering column that are exactly zero: rows the ring skips, requested-ahead rows it
+    discards), Philox batches of 600 so that persistent CTAs run several instances through the same ring."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    dA, db, dc = solver.generate(91, 0, 600, 200, 100, density=density)
+    try:
+        ctx.set_solve_plan(1)
+        r1 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(2)
+        r2 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    assert (r1['status'] == 2).sum() > 100
+    for k in ('status', 'labels', 'pivots', 'n_active', 'ties'):
+        assert (r1[k] == r2[k]).all(), k
+    ok = r1['status'] == 2
+    assert (r1['x'][ok] == r2['x'][ok]).all() and (r1['obj'][ok] == r2['obj'][ok]).all()
+
+
 def test_host_and_device_flavours_agree(cuda_device):
     from deep_dantzig_b200 import solver
     A, b, c = _numpy_batch(50, 20, list(range(3000)))            # > one host chunk boundary is exercised below
