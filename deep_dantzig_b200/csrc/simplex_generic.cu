@@ -18,6 +18,7 @@
 // (4) x from the rows frozen at the end of the crash, one step of iterative refinement on the final active set when
 //     its residual is not negligible, slack = b - A x recomputed from the caller's A, labels = |slack| <= threshold
 //     exactly as gurobi_lp.py:435-443.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace ddb {
@@ -88,7 +89,7 @@ size_t generic_smem_bytes(int m, int n, bool smem_tab) { return make_layout(m, n
 // NTMAX: largest block the instantiation is launched with (1024, or 512 for the wide global-memory shapes, which trades
 // warps for registers: more loads in flight per lane)
 template <bool kSmemTab, int CPL, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, int ring_mode) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = a.m, n = a.n;
     const Layout L = make_layout(m, n, kSmemTab);
@@ -130,10 +131,13 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
     // FMAs of the oldest one out of shared memory and stores the result straight back to the slab.  The copies need no
     // registers, so ring_k rows (up to 16 KB) per warp are in flight instead of the 32 loads per lane of the register path.
     constexpr bool kRing = !kSmemTab && NTMAX <= 512;
-    const int ring_k = (kRing && nw == kRingWarps) ? L.ring_k : 0;
+    int ring_k = 0;
+    if (kRing && nw == kRingWarps && ring_mode > 0) ring_k = L.ring_k;
+    const bool ring_ahead = ring_mode > 1;   // request the leading rows of the next pivot at the end of this one
     double* wring = reinterpret_cast<double*>(smem_raw + L.ring) + (size_t)warp * ring_k * n;
     uint64_t* wbar = reinterpret_cast<uint64_t*>(smem_raw + L.rbar) + warp * kRingMaxSlots;
     unsigned r_issued = 0, r_done = 0;     // rows this warp has requested / consumed since the kernel started (warp-uniform)
+    int npre = 0;                          // leading rows of this warp's share already requested for the NEXT pivot
     if (kRing && ring_k > 0) {
         if (lane == 0) {
             for (int q = 0; q < ring_k; ++q) mbar_init(&wbar[q], 1);
@@ -154,7 +158,8 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
             const int nl = nlive_sm;
             for (int q = tid; q < nl; q += nt) {
                 const int i = liveidx[q];
-                if (i != r) P[(size_t)i * n + k] = 0.0; else colbuf[i] = 0.0;
+                // (ring mode: the update takes column k of a row as 0 itself, see below, so it is not zeroed in place)
+                if (i == r) colbuf[i] = 0.0; else if (!(kRing && ring_k > 0)) P[(size_t)i * n + k] = 0.0;
             }
         } else {
             for (int i = tid; i < m; i += nt) {
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
                 const uint8_t st = rowstate[i];
                 if (i != r && (st == ROW_LIVE || (crash_mode && st == ROW_CRASHED))) {
                     f = P[(size_t)i * n + k];
-                    P[(size_t)i * n + k] = 0.0;
+                    if (!(kRing && ring_k > 0)) P[(size_t)i * n + k] = 0.0;
                 }
                 colbuf[i] = f;
             }
@@ -190,13 +195,21 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
         // round-trip latency): the register budget decides RB -- 64 registers at 1024 threads, 128 at 512
         constexpr int RB = (NTMAX <= 512) ? ((CPL <= 8) ? 4 : 2) : ((CPL <= 2) ? 2 : 1);
         const int nrows = crash_mode ? m : nlive_sm;           // the crash updates every row, phases 1 / 2 the live ones
-        if (kRing && ring_k > 0) {
+        bool streamed = false;
+        if constexpr (kRing) {
+        if (ring_k > 0) {
+            streamed = true;
+            // Rows of this warp's share: list positions warp, warp + nw, ...  The first npre of them were requested at the
+            // end of the previous pivot (their copies predate this pivot's step B, which only touched column k -- taken as 0
+            // here for every row -- and the pivot row, which is skipped); the others are requested as slots free up.
             const uint32_t rowbytes = (uint32_t)n * 8u;
-            int tp = warp;                                     // producer cursor over this warp's share of the row list
-            for (int q0 = warp; q0 < nrows; q0 += nw) {
+            int tp = warp + npre * nw;                         // producer cursor over this warp's share of the row list
+            int t = 0;
+            for (int q0 = warp; q0 < nrows; q0 += nw, ++t) {
                 const int ix = crash_mode ? q0 : liveidx[q0];
                 const double f = colbuf[ix];
-                if (f == 0.0) continue;                        // warp-uniform
+                const bool pre = t < npre;
+                if (f == 0.0 && !pre) continue;                // warp-uniform
                 while ((int)(r_issued - r_done) < ring_k && tp < nrows) {
                     const int ixp = crash_mode ? tp : liveidx[tp];
                     tp += nw;
@@ -211,18 +224,35 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
                 }
                 const unsigned sl = r_done % (unsigned)ring_k;
                 mbar_wait(&wbar[sl], (r_done / (unsigned)ring_k) & 1u);
-                const double* src = wring + (size_t)sl * n;
-                double* Pi = P + (size_t)ix * n;
+                if (f != 0.0) {
+                    const double* src = wring + (size_t)sl * n;
+                    double* Pi = P + (size_t)ix * n;
 #pragma unroll
-                for (int q = 0; q < CPL; ++q) {
-                    const int j = lane + 32 * q;
-                    if (j < n) Pi[j] = fma(-f, pr[q], src[j]);
+                    for (int q = 0; q < CPL; ++q) {
+                        const int j = lane + 32 * q;
+                        if (j < n) Pi[j] = fma(-f, pr[q], (j == k) ? 0.0 : src[j]);
+                    }
+                    if (lane == 0) s[ix] = fma(-f, sr, s[ix]);
                 }
-                if (lane == 0) s[ix] = fma(-f, sr, s[ix]);
                 __syncwarp();                                  // every lane has read the slot before lane 0 refills it
                 ++r_done;
             }
-        } else
+            // request the leading rows of the share for the next pivot now: the copies travel while the block selects it
+            fence_proxy_async_all();                           // my stores above before the async-proxy reads below
+            __syncwarp();
+            npre = 0;
+            for (int q0 = warp; ring_ahead && q0 < nrows && npre < ring_k; q0 += nw, ++npre) {
+                const int ixp = crash_mode ? q0 : liveidx[q0];
+                const unsigned sl = r_issued % (unsigned)ring_k;
+                if (lane == 0) {
+                    mbar_expect_tx(&wbar[sl], rowbytes);
+                    tma_load_1d(wring + (size_t)sl * n, P + (size_t)ixp * n, rowbytes, &wbar[sl]);
+                }
+                ++r_issued;
+            }
+        }
+        }
+        if (!streamed)
         for (int q0 = warp; q0 < nrows; q0 += RB * nw) {
             int ix[RB];
             double fx[RB];
@@ -265,6 +295,17 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
             }
         }
         __syncthreads();
+    };
+
+    // the rows requested ahead for a pivot that never came (end of a stage: the row list changes, or the LP is finished)
+    auto drain_ring = [&]() {
+        if constexpr (kRing) {
+            while (r_done != r_issued) {
+                mbar_wait(&wbar[r_done % (unsigned)ring_k], (r_done / (unsigned)ring_k) & 1u);
+                ++r_done;
+            }
+            npre = 0;
+        }
     };
 
     if (a.only_flagged && *a.flag_count == 0) return;   // nothing was handed over by the register-tiled kernel
@@ -397,6 +438,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
             ++npiv_crash;
             __syncthreads();
         }
+        drain_ring();
         for (int j = tid; j < n; j += nt) {
             colvar0[j] = colvar[j];
             gh[j] = 1.0;
@@ -544,6 +586,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a) 
             __syncthreads();
         }
 
+        drain_ring();
         // ---- stage 4: x, objective, slacks, labels ---------------------------------------------------------
         uint8_t* lab = a.labels + (size_t)lp * m;
         int nact = 0, nties = 0, nviol = 0;
@@ -687,7 +730,9 @@ static cudaError_t launch_one(const SolveArgs& a, int grid, int block, size_t sm
     auto kern = simplex_generic_kernel<kSmemTab, CPL, NTMAX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<grid, block, smem, st>>>(a);
+    // DDB_PLAN2_RING: 0 = rows through registers, 1 = bulk-TMA ring, 2 (default) = ring + rows of the next pivot requested ahead
+    static const int ring_mode = [] { const char* e = getenv("DDB_PLAN2_RING"); return e ? atoi(e) : 0; }();   // TODO flip to 2 once verified on the GPU
+    kern<<<grid, block, smem, st>>>(a, ring_mode);
     return cudaGetLastError();
 }
 
