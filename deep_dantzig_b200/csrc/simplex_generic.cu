@@ -23,6 +23,10 @@
 
 namespace ddb {
 
+__device__ __forceinline__ void fence_proxy_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
 struct Sel {
     double p;      // pivot element
     double gk;     // g[k] before the pivot
@@ -43,7 +47,7 @@ constexpr size_t kSmemBudget = 232448 - 1024 - 64;   // 227 KB opt-in minus the 
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-__host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
+__host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab, int ring_slots = 0) {
     Layout L;
     size_t off = 0;
     L.tab = off;      off += smem_tab ? align_up((size_t)m * n * 8, 16) : 0;
@@ -67,13 +71,14 @@ __host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
     L.bar = off;      off += 16;
     L.ring = L.rbar = 0;
     L.ring_k = 0;
-    if (!smem_tab && (long long)m * n > 16384 && n % 2 == 0) {
+    if (ring_slots > 0 && !smem_tab && (long long)m * n > 16384 && n % 2 == 0) {
         const size_t base = align_up(off, 128);
         const size_t bars = (size_t)kRingWarps * kRingMaxSlots * 8;
         const size_t row = (size_t)n * 8;
         if (base + bars + 2 * kRingWarps * row <= kSmemBudget) {
             size_t k = (kSmemBudget - base - bars) / (kRingWarps * row);
             if (k > (size_t)kRingMaxSlots) k = kRingMaxSlots;
+            if (k > (size_t)ring_slots) k = ring_slots;
             L.ring_k = (int)k;
             L.rbar = base;
             L.ring = base + bars;
@@ -84,15 +89,26 @@ __host__ __device__ inline Layout make_layout(int m, int n, bool smem_tab) {
     return L;
 }
 
-size_t generic_smem_bytes(int m, int n, bool smem_tab) { return make_layout(m, n, smem_tab).total; }
+// DDB_PLAN2_RING (experiment, default 0): 0 = rows through registers, 1 = bulk-TMA row ring, 2 = ring + the leading rows of the
+// next pivot requested ahead, 3 = as 2 with state-space-qualified proxy fences; DDB_PLAN2_RING_K caps the slots per warp.
+// The ring is only laid out when it is used: its shared memory comes out of the L1 carve-out, which the register path wants.
+static int generic_ring_mode() {
+    static const int v = [] { const char* e = getenv("DDB_PLAN2_RING"); return e ? atoi(e) : 0; }();
+    return v;
+}
+static int generic_ring_slots() {
+    static const int v = [] { const char* e = getenv("DDB_PLAN2_RING_K"); const int k = e ? atoi(e) : kRingMaxSlots; return k < 2 ? 2 : k; }();
+    return generic_ring_mode() > 0 ? v : 0;
+}
+size_t generic_smem_bytes(int m, int n, bool smem_tab) { return make_layout(m, n, smem_tab, generic_ring_slots()).total; }
 
 // NTMAX: largest block the instantiation is launched with (1024, or 512 for the wide global-memory shapes, which trades
 // warps for registers: more loads in flight per lane)
-template <bool kSmemTab, int CPL, int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, int ring_mode) {
+template <bool kSmemTab, int CPL, int NTMAX, bool kRing>
+__global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, int ring_mode, int ring_slots) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int m = a.m, n = a.n;
-    const Layout L = make_layout(m, n, kSmemTab);
+    const Layout L = make_layout(m, n, kSmemTab, ring_slots);
     double* P = kSmemTab ? reinterpret_cast<double*>(smem_raw + L.tab)
                          : a.gtab + (size_t)blockIdx.x * ((size_t)m * n);
     double* s = reinterpret_cast<double*>(smem_raw + L.s);
@@ -130,7 +146,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
     // bulk-copies (cp.async.bulk, SASS UBLKCP) the next rows of the warp's share into free slots while the warp runs the
     // FMAs of the oldest one out of shared memory and stores the result straight back to the slab.  The copies need no
     // registers, so ring_k rows (up to 16 KB) per warp are in flight instead of the 32 loads per lane of the register path.
-    constexpr bool kRing = !kSmemTab && NTMAX <= 512;
+    static_assert(!kRing || (!kSmemTab && NTMAX <= 512), "the row ring belongs to the 512-thread global-memory instantiation");
     int ring_k = 0;
     if (kRing && nw == kRingWarps && ring_mode > 0) ring_k = L.ring_k;
     const bool ring_ahead = ring_mode > 1;   // request the leading rows of the next pivot at the end of this one
@@ -181,7 +197,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
         }
         // every generic-proxy store of this thread to the slab (this step's and the previous update's) is ordered before
         // the bulk copies (async proxy) that are issued after the barrier
-        if (kRing && ring_k > 0) fence_proxy_async_all();
+        if (kRing && ring_k > 0) { if (ring_mode == 3) fence_proxy_async_global(); else fence_proxy_async_all(); }
         __syncthreads();
         // C: rank-1 update of every other row, of s, g and ghat
         double pr[CPL];
@@ -238,7 +254,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
                 ++r_done;
             }
             // request the leading rows of the share for the next pivot now: the copies travel while the block selects it
-            fence_proxy_async_all();                           // my stores above before the async-proxy reads below
+            if (ring_mode == 3) fence_proxy_async_global(); else fence_proxy_async_all();   // my stores above before the async-proxy reads below
             __syncwarp();
             npre = 0;
             for (int q0 = warp; ring_ahead && q0 < nrows && npre < ring_k; q0 += nw, ++npre) {
@@ -725,14 +741,12 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
 // ---------------------------------------------------------------------------------------------------------
 // host-side launcher
 // ---------------------------------------------------------------------------------------------------------
-template <bool kSmemTab, int CPL, int NTMAX>
+template <bool kSmemTab, int CPL, int NTMAX, bool kRing = false>
 static cudaError_t launch_one(const SolveArgs& a, int grid, int block, size_t smem, cudaStream_t st) {
-    auto kern = simplex_generic_kernel<kSmemTab, CPL, NTMAX>;
+    auto kern = simplex_generic_kernel<kSmemTab, CPL, NTMAX, kRing>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    // DDB_PLAN2_RING: 0 = rows through registers, 1 = bulk-TMA ring, 2 (default) = ring + rows of the next pivot requested ahead
-    static const int ring_mode = [] { const char* e = getenv("DDB_PLAN2_RING"); return e ? atoi(e) : 0; }();   // TODO flip to 2 once verified on the GPU
-    kern<<<grid, block, smem, st>>>(a, ring_mode);
+    kern<<<grid, block, smem, st>>>(a, generic_ring_mode(), generic_ring_slots());
     return cudaGetLastError();
 }
 
@@ -758,6 +772,12 @@ cudaError_t launch_simplex_generic(const SolveArgs& a, bool smem_tab, int grid, 
         return cudaErrorInvalidValue;
     }
     if (block <= 512 && (long long)a.m * a.n > 16384) {      // generic_block_threads(): large global-memory shapes
+        if (generic_ring_mode() > 0) {                        // experiment: rows streamed through a bulk-TMA ring
+            if (cpl <= 4) return launch_one<false, 4, 512, true>(a, grid, block, smem, st);
+            if (cpl <= 8) return launch_one<false, 8, 512, true>(a, grid, block, smem, st);
+            if (cpl <= 16) return launch_one<false, 16, 512, true>(a, grid, block, smem, st);
+            return cudaErrorInvalidValue;
+        }
         if (cpl <= 4) return launch_one<false, 4, 512>(a, grid, block, smem, st);
         if (cpl <= 8) return launch_one<false, 8, 512>(a, grid, block, smem, st);
         if (cpl <= 16) return launch_one<false, 16, 512>(a, grid, block, smem, st);
