@@ -415,8 +415,12 @@ extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t 
     if (B == 0) return DDB_OK;
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
-    // chunk sized so the generated instances are still in the 126 MB L2 when the solver reads them
-    int64_t chunk = (int64_t)((size_t)(64u << 20) / per_lp);
+    // chunk = instances generated into scratch per solver launch (DDB_FUSED_CHUNK_MB of instance data).  Measured at
+    // (200,100), 262 144 instances: 64 MB (two instances per persistent CTA: the launch tails dominate) 377 k LP/s,
+    // 512 MB 402 k, 2 GB 400 k, 6 GB 398 k (profiles/fused_chunk_r01.txt) -- a few launches' worth of L2-warm instances
+    // beats both extremes.
+    static const long long chunk_mb = [] { const char* e = getenv("DDB_FUSED_CHUNK_MB"); return e ? atoll(e) : 512ll; }();
+    int64_t chunk = (int64_t)((size_t)(chunk_mb << 20) / per_lp);
     const int64_t min_chunk = (int64_t)ctx->sm_count * 4;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > B) chunk = B;
