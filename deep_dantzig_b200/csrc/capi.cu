@@ -91,7 +91,9 @@ struct ddb_ctx {
     DevBuf scratch;            // global tableau slabs / register-tile scratch
     cudaEvent_t scratch_free = nullptr;
     bool scratch_in_use = false;
-    DevBuf genA, genb, genc;   // fused generate->solve chunk buffers
+    DevBuf genA, genb, genc;   // fused generate->solve chunk buffers (two halves: chunk i + 1 is generated while chunk i is solved)
+    cudaStream_t gen_stream = nullptr;
+    cudaEvent_t gen_done[2] = {nullptr, nullptr}, solve_done[2] = {nullptr, nullptr}, gen_fork = nullptr;
     DevBuf gram;               // classifier: per-instance Gram row sums from the tensor-core kernel
     DevBuf s2vflag;            // classifier: per-instance "has a zero coefficient" flags of the dense bipartite kernel
     Slot slots[kSlots];
@@ -136,6 +138,12 @@ extern "C" int ddb_create(int device, ddb_ctx** out) {
                     prop.major, prop.minor);
     CUDA_TRY(cudaMalloc(&ctx->counters, 3 * kCounters * sizeof(unsigned long long)));
     CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gen_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->solve_done[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < kSlots; ++i) {
         CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming));
@@ -168,6 +176,12 @@ extern "C" int ddb_destroy(ddb_ctx* ctx) {
     release(ctx->gram);
     release(ctx->s2vflag);
     if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
+    if (ctx->gen_stream) cudaStreamDestroy(ctx->gen_stream);
+    if (ctx->gen_fork) cudaEventDestroy(ctx->gen_fork);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->gen_done[i]) cudaEventDestroy(ctx->gen_done[i]);
+        if (ctx->solve_done[i]) cudaEventDestroy(ctx->solve_done[i]);
+    }
     if (ctx->counters) cudaFree(ctx->counters);
     delete ctx;
     return DDB_OK;
@@ -425,26 +439,46 @@ extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t 
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > B) chunk = B;
     const bool keep = A_out && b_out && c_out;
+    // DDB_FUSED_OVERLAP (default 1): chunk i + 1 is generated on a side stream while chunk i is solved -- the solver's
+    // persistent CTAs fill the register files, so the generator's blocks land on the SMs its tail leaves idle
+    static const bool overlap = [] { const char* e = getenv("DDB_FUSED_OVERLAP"); return !(e && e[0] == '0'); }();
+    cudaStream_t st = (cudaStream_t)stream;
+    const int halves = overlap ? 2 : 1;
     int rc;
     if (!keep) {
-        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));   // scratch reuse across calls
-        if ((rc = ensure(ctx->genA, (size_t)chunk * m * n * 8))) return rc;
-        if ((rc = ensure(ctx->genb, (size_t)chunk * m * 8))) return rc;
-        if ((rc = ensure(ctx->genc, (size_t)chunk * n * 8))) return rc;
+        CUDA_TRY(cudaStreamSynchronize(st));   // scratch reuse across calls
+        if ((rc = ensure(ctx->genA, (size_t)halves * chunk * m * n * 8))) return rc;
+        if ((rc = ensure(ctx->genb, (size_t)halves * chunk * m * 8))) return rc;
+        if ((rc = ensure(ctx->genc, (size_t)halves * chunk * n * 8))) return rc;
     }
-    for (int64_t off = 0; off < B; off += chunk) {
+    if (overlap) {                              // the side stream starts after whatever the caller has queued so far
+        CUDA_TRY(cudaEventRecord(ctx->gen_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->gen_fork, 0));
+    }
+    int64_t idx = 0;
+    for (int64_t off = 0; off < B; off += chunk, ++idx) {
         const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
-        double* Ap = keep ? A_out + (size_t)off * m * n : (double*)ctx->genA.p;
-        double* bp = keep ? b_out + (size_t)off * m : (double*)ctx->genb.p;
-        double* cp = keep ? c_out + (size_t)off * n : (double*)ctx->genc.p;
-        rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, stream);
-        if (rc) return rc;
+        const int h = overlap ? (int)(idx & 1) : 0;
+        double* Ap = keep ? A_out + (size_t)off * m * n : (double*)ctx->genA.p + (size_t)h * chunk * m * n;
+        double* bp = keep ? b_out + (size_t)off * m : (double*)ctx->genb.p + (size_t)h * chunk * m;
+        double* cp = keep ? c_out + (size_t)off * n : (double*)ctx->genc.p + (size_t)h * chunk * n;
+        if (overlap) {
+            if (!keep && idx >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->solve_done[h], 0));   // half h is free again
+            rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, ctx->gen_stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(ctx->gen_done[h], ctx->gen_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, ctx->gen_done[h], 0));
+        } else {
+            rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, stream);
+            if (rc) return rc;
+        }
         rc = ddb_solve_label_dev(ctx, nb, m, n, Ap, bp, cp, threshold, nullptr, status + off,
                                  x ? x + (size_t)off * n : nullptr, obj ? obj + off : nullptr,
                                  labels + (size_t)off * m, n_active ? n_active + off : nullptr,
                                  pivots ? pivots + (size_t)off * 4 : nullptr, ties ? ties + off : nullptr, nullptr,
                                  stream);
         if (rc) return rc;
+        if (overlap && !keep) CUDA_TRY(cudaEventRecord(ctx->solve_done[h], st));
     }
     return DDB_OK;
 }
