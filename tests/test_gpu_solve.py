@@ -130,10 +130,12 @@ def test_plans_agree_bit_for_bit(cuda_device):
 
 @pytest.mark.parametrize('density', [1.0, 0.1])
 def test_streamed_global_tableau_agrees_bit_for_bit(cuda_device, density):
-    """(200,100) is a shape where the global-memory plan streams the tableau through its bulk-TMA row ring
-    (m n > 16384, even n) while the shared-memory plan still fits: same arithmetic, bit for bit -- dense instances and
-    sparse ones (entries of the entering column that are exactly zero: rows the ring skips, requested-ahead rows it
-    discards), Philox batches of 600 so that persistent CTAs run several instances through the same ring."""
+    """(200,100) is a shape where the global-memory plan runs its 512-thread streaming instantiation (m n > 16384)
+    while the shared-memory plan still fits: same arithmetic, bit for bit -- dense instances and sparse ones (entries
+    of the entering column that are exactly zero: rows the update skips), Philox batches of 600 so that persistent
+    CTAs run several instances each.  With DDB_PLAN2_RING=1|2|3 in the environment the same test covers the bulk-TMA
+    row-ring variant of that instantiation (even n), including the requested-ahead rows it discards (recorded green
+    in gpurun_out/pytest_solve_ring.log / profiles/plan2_tma_ring_r01.txt)."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
     dA, db, dc = solver.generate(91, 0, 600, 200, 100, density=density)
