@@ -41,7 +41,9 @@ SIGNATURES = {
     'ddb_solve_label_host': (C.c_int, [_vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _f64, _vp,
                                        _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_generate_solve_label_dev': (C.c_int, [_vp, _u64, _i64, _i64, C.c_int, C.c_int, _f64, _f64,
-                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                               _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'ddb_generate_solve_label_host': (C.c_int, [_vp, _u64, _i64, _i64, C.c_int, C.c_int, _f64, _f64,
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_s2v_param_count': (C.c_int, [C.c_int, C.c_int]),
     'ddb_s2v_forward_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_s2v_loss_grad_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,

@@ -3,7 +3,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "../../include/ddb200.h"
 #include "common.cuh"
@@ -17,13 +20,25 @@ cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, i
 bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
+#ifdef DDB_EXPERIMENTS   // `make experiments`: the measured negative results of round 1, not in the shipped library
 bool tile2d_supported(int m, int n);
 cudaError_t launch_simplex_tile2d(const SolveArgs& a, int sm_count, cudaStream_t st);
-bool rowreg_supported(int m, int n);
-size_t rowreg_scratch_bytes(int m, int n, int sm_count);
-cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool rowpipe_supported(int m, int n);
 cudaError_t launch_simplex_rowpipe(const SolveArgs& a, int sm_count, cudaStream_t st);
+#else
+inline bool tile2d_supported(int, int) { return false; }
+inline cudaError_t launch_simplex_tile2d(const SolveArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+inline bool rowpipe_supported(int, int) { return false; }
+inline cudaError_t launch_simplex_rowpipe(const SolveArgs&, int, cudaStream_t) { return cudaErrorNotSupported; }
+#endif
+bool rowreg_supported(int m, int n);
+int rowreg_grid(int m, int n, int sm_count);
+size_t rowreg_rows_scratch_bytes(int m, int n, int grid);
+size_t rowreg_d_scratch_bytes(int m, int n, int grid);
+cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t st);
+bool rowreg_gen_supported(int m, int n);
+int rowreg_gen_grid(int m, int n, int sm_count);
+cudaError_t launch_simplex_rowreg_gen(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool s2v_gram_tc_supported(int m, int n);
 size_t s2v_gram_out_floats(int m);
 cudaError_t launch_s2v_gram_tc(long long B, int m, int n, const double* A, const double* b, const double* c, float* out,
@@ -68,17 +83,30 @@ static int fail(int code, const char* fmt, ...) {
 
 namespace {
 constexpr int kCounters = 64;
-constexpr int kSlots = 2;   // double buffering of the host-buffer flavours
+constexpr int kSlots = 3;   // chunks in flight in the host-buffer flavours (stage-in / H2D / solve + D2H overlap)
 
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
 };
 
+struct HostBuf {             // pinned staging memory (cudaHostAlloc)
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct Retire {              // staged output: copy `bytes` from pinned `src` to the caller's pageable `dst` once the slot is done
+    void* dst;
+    const void* src;
+    size_t bytes;
+};
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     DevBuf A, b, c, mask, status, x, obj, labels, nact, piv, ties, viol;
+    HostBuf in, out;         // pinned staging for pageable caller buffers
+    std::vector<Retire> retire;
 };
 }  // namespace
 
@@ -86,14 +114,20 @@ struct ddb_ctx {
     int device = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     int64_t smem_optin = 0;
+    std::mutex mu;             // entry points that touch per-context state are serialised (one context per device per process)
     unsigned long long* counters = nullptr;   // kCounters work-queue counters followed by kCounters flag counters
     int next_counter = 0;
-    DevBuf scratch;            // global tableau slabs / register-tile scratch
-    cudaEvent_t scratch_free = nullptr;
+    DevBuf scratch;            // global tableau slabs / parked rows of the register kernels
+    DevBuf dscr;               // row-per-thread kernel, hybrid rows: per-CTA global home of the crash inverse
+    DevBuf slab;               // fused generate -> solve: per-CTA instance slabs (L2-resident)
+    cudaEvent_t scratch_free = nullptr;   // recorded after every launch that uses scratch / dscr / slab: the next one waits
     bool scratch_in_use = false;
-    DevBuf genA, genb, genc;   // fused generate->solve chunk buffers (two halves: chunk i + 1 is generated while chunk i is solved)
+    DevBuf genA, genb, genc;   // unfused fallback of the fused call (odd n, shapes outside plan 0): chunk buffers
+    cudaEvent_t gen_free = nullptr;       // last solve that read the chunk buffers
+    bool gen_in_use = false;
     cudaStream_t gen_stream = nullptr;
     cudaEvent_t gen_done[2] = {nullptr, nullptr}, solve_done[2] = {nullptr, nullptr}, gen_fork = nullptr;
+    cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
     DevBuf gram;               // classifier: per-instance Gram row sums from the tensor-core kernel
     DevBuf s2vflag;            // classifier: per-instance "has a zero coefficient" flags of the dense bipartite kernel
     Slot slots[kSlots];
@@ -115,6 +149,26 @@ static int ensure(DevBuf& buf, size_t bytes) {
 extern "C" int ddb_abi_version(void) { return DDB_ABI_VERSION; }
 extern "C" const char* ddb_last_error(void) { return g_err; }
 
+static int create_resources(ddb_ctx* ctx) {
+    CUDA_TRY(cudaMalloc(&ctx->counters, 3 * kCounters * sizeof(unsigned long long)));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_free, cudaEventDisableTiming));
+    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gen_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->solve_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->chunk_ev[i], cudaEventDisableTiming));
+    }
+    for (int i = 0; i < kSlots; ++i) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming));
+    }
+    return DDB_OK;
+}
+
+extern "C" int ddb_destroy(ddb_ctx* ctx);
+
 extern "C" int ddb_create(int device, ddb_ctx** out) {
     if (!out) return fail(DDB_EINVAL, "ddb_create: out is NULL");
     int ndev = 0;
@@ -124,29 +178,22 @@ extern "C" int ddb_create(int device, ddb_ctx** out) {
                     cudaGetErrorString(e));
     if (device < 0 || device >= ndev) return fail(DDB_EINVAL, "ddb_create: device %d out of range", device);
     CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DDB_EUNSUPPORTED, "ddb_create: device is sm_%d%d; this library is built for sm_100a only",
+                    prop.major, prop.minor);
     ddb_ctx* ctx = new (std::nothrow) ddb_ctx();
     if (!ctx) return fail(DDB_ENOMEM, "ddb_create: out of host memory");
     ctx->device = device;
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     ctx->cc_major = prop.major;
     ctx->cc_minor = prop.minor;
     ctx->smem_optin = (int64_t)prop.sharedMemPerBlockOptin;
-    if (prop.major != 10)
-        return fail(DDB_EUNSUPPORTED, "ddb_create: device is sm_%d%d; this library is built for sm_100a only",
-                    prop.major, prop.minor);
-    CUDA_TRY(cudaMalloc(&ctx->counters, 3 * kCounters * sizeof(unsigned long long)));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->scratch_free, cudaEventDisableTiming));
-    CUDA_TRY(cudaStreamCreateWithFlags(&ctx->gen_stream, cudaStreamNonBlocking));
-    CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_fork, cudaEventDisableTiming));
-    for (int i = 0; i < 2; ++i) {
-        CUDA_TRY(cudaEventCreateWithFlags(&ctx->gen_done[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ctx->solve_done[i], cudaEventDisableTiming));
-    }
-    for (int i = 0; i < kSlots; ++i) {
-        CUDA_TRY(cudaStreamCreateWithFlags(&ctx->slots[i].stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&ctx->slots[i].done, cudaEventDisableTiming));
+    const int rc = create_resources(ctx);
+    if (rc != DDB_OK) {            // nothing leaks on a half-built context
+        ddb_destroy(ctx);
+        return rc;
     }
     *out = ctx;
     return DDB_OK;
@@ -166,21 +213,27 @@ extern "C" int ddb_destroy(ddb_ctx* ctx) {
         Slot& s = ctx->slots[i];
         DevBuf* all[] = {&s.A, &s.b, &s.c, &s.mask, &s.status, &s.x, &s.obj, &s.labels, &s.nact, &s.piv, &s.ties, &s.viol};
         for (DevBuf* d : all) release(*d);
+        if (s.in.p) cudaFreeHost(s.in.p);
+        if (s.out.p) cudaFreeHost(s.out.p);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.done) cudaEventDestroy(s.done);
     }
     release(ctx->scratch);
+    release(ctx->dscr);
+    release(ctx->slab);
     release(ctx->genA);
     release(ctx->genb);
     release(ctx->genc);
     release(ctx->gram);
     release(ctx->s2vflag);
     if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
+    if (ctx->gen_free) cudaEventDestroy(ctx->gen_free);
     if (ctx->gen_stream) cudaStreamDestroy(ctx->gen_stream);
     if (ctx->gen_fork) cudaEventDestroy(ctx->gen_fork);
     for (int i = 0; i < 2; ++i) {
         if (ctx->gen_done[i]) cudaEventDestroy(ctx->gen_done[i]);
         if (ctx->solve_done[i]) cudaEventDestroy(ctx->solve_done[i]);
+        if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     }
     if (ctx->counters) cudaFree(ctx->counters);
     delete ctx;
@@ -199,7 +252,7 @@ extern "C" int ddb_device_info(ddb_ctx* ctx, int* sm_count, int* cc_major, int* 
 extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static int auto_plan(const ddb_ctx* ctx, int m, int n) {
-    if (ddb::tile2d_supported(m, n) || ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
+    if (ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
     if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
     return 2;
 }
@@ -209,7 +262,7 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
     if (m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_plan: m=%d n=%d", m, n);
     if (n > 512) return fail(DDB_EUNSUPPORTED, "ddb_solve_plan: n=%d > 512 is not supported yet", n);
     int plan = ctx->forced_plan >= 0 ? ctx->forced_plan : auto_plan(ctx, m, n);
-    if (plan == 0 && !ddb::tile2d_supported(m, n) && !ddb::rowreg_supported(m, n) && !ddb::regtile_supported(m, n))
+    if (plan == 0 && !ddb::rowreg_supported(m, n) && !ddb::regtile_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "register-tiled kernel does not cover m=%d n=%d", m, n);
     if (plan == 1 && (int64_t)ddb::generic_smem_bytes(m, n, true) > ctx->smem_optin)
         return fail(DDB_EUNSUPPORTED, "shared-memory tableau does not fit for m=%d n=%d", m, n);
@@ -235,6 +288,7 @@ extern "C" int ddb_generate_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instan
     if (B < 0 || m < 1 || n < 1 || !(density > 0.0 && density <= 1.0))
         return fail(DDB_EINVAL, "ddb_generate_dev: B=%lld m=%d n=%d density=%g", (long long)B, m, n, density);
     if (B == 0) return DDB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     int launches = 0;
     CUDA_TRY(ddb::launch_generate(key, first_instance, B, m, n, density, A, b, c, x0, ctx->sm_count,
@@ -244,8 +298,27 @@ extern "C" int ddb_generate_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instan
 }
 
 
-static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_t st) {
-    const int m = a.m, n = a.n;
+// ---------------------------------------------------------------------------------------------------------
+// per-context scratch (parked rows / global tableau slabs, crash inverses, fused-mode instance slabs): one launch at a
+// time uses it, whatever stream it runs on -- every launch waits for the previous one's event
+// ---------------------------------------------------------------------------------------------------------
+static int scratch_acquire(ddb_ctx* ctx, cudaStream_t st, size_t need_scratch, size_t need_dscr, size_t need_slab) {
+    if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
+    if (need_scratch > ctx->scratch.cap || need_dscr > ctx->dscr.cap || need_slab > ctx->slab.cap)
+        CUDA_TRY(cudaDeviceSynchronize());          // growing: nothing may still be running on the old block
+    int rc;
+    if ((rc = ensure(ctx->scratch, need_scratch))) return rc;
+    if ((rc = ensure(ctx->dscr, need_dscr))) return rc;
+    if ((rc = ensure(ctx->slab, need_slab))) return rc;
+    return DDB_OK;
+}
+static int scratch_release(ddb_ctx* ctx, cudaStream_t st) {
+    CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
+    ctx->scratch_in_use = true;
+    return DDB_OK;
+}
+
+static long long generic_grid(const ddb_ctx* ctx, int m, int n, int plan, long long B) {
     const bool smem_tab = (plan == 1);
     const int block = ddb::generic_block_threads(m, n, smem_tab);
     const size_t smem = ddb::generic_smem_bytes(m, n, smem_tab);
@@ -266,22 +339,104 @@ static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_
             if (grid > cap) grid = cap;
         }
     }
-    if (grid > a.B) grid = a.B;
-    if (!smem_tab) {
-        const size_t need = (size_t)grid * m * n * sizeof(double);
-        if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
-        if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
-        int rc = ensure(ctx->scratch, need);
-        if (rc) return rc;
-        a.gtab = (double*)ctx->scratch.p;
-    }
+    if (grid > B) grid = B;
+    return grid;
+}
+
+// scratch must have been acquired by the caller (generic_scratch_bytes / slab for a.gen)
+static size_t generic_scratch_bytes(const ddb_ctx* ctx, int m, int n, int plan, long long B) {
+    return plan == 1 ? 0 : (size_t)generic_grid(ctx, m, n, plan, B) * m * n * sizeof(double);
+}
+
+static int launch_generic(ddb_ctx* ctx, ddb::SolveArgs& a, int plan, cudaStream_t st) {
+    const bool smem_tab = (plan == 1);
+    const int block = ddb::generic_block_threads(a.m, a.n, smem_tab);
+    const long long grid = generic_grid(ctx, a.m, a.n, plan, a.B);
+    if (!smem_tab) a.gtab = (double*)ctx->scratch.p;
     CUDA_TRY(ddb::launch_simplex_generic(a, smem_tab, (int)grid, block, st));
-    if (!smem_tab) {
-        CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
-        ctx->scratch_in_use = true;
-    }
     ctx->launches += 1;
     return DDB_OK;
+}
+
+struct GenSpec {              // fused mode: draw the instances inside the solver kernels
+    uint64_t key;
+    int64_t first;
+    double density;
+};
+
+// Common body of ddb_solve_label_dev and the fused call.  gen == nullptr: A, b, c are the caller's instances.
+// gen != nullptr: the solver CTAs draw instance gen->first + i themselves; A / b / c (all or none) receive them.
+static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b, const double* c,
+                        double threshold, const uint8_t* row_mask, int32_t* status, double* x, double* obj, uint8_t* labels,
+                        int32_t* n_active, int32_t* pivots, int32_t* ties, int32_t* violations, const GenSpec* gen,
+                        cudaStream_t st) {
+    const int plan = ddb_solve_plan(ctx, m, n);
+    if (plan < 0) return plan;
+
+    ddb::SolveArgs a;
+    a.m = m; a.n = n; a.B = B;
+    a.A = A; a.b = b; a.c = c; a.row_mask = row_mask; a.thr = threshold;
+    a.status = status; a.x = x; a.obj = obj; a.labels = labels; a.n_active = n_active;
+    a.pivots = pivots; a.ties = ties; a.violations = violations;
+    a.max_iter = 50 * (m + n);
+    a.gtab = nullptr; a.dscr = nullptr; a.slab = nullptr;
+    a.gen = gen ? 1 : 0;
+    a.gen_key = gen ? gen->key : 0; a.gen_first = gen ? gen->first : 0; a.gen_density = gen ? gen->density : 1.0;
+    const int slot = ctx->next_counter;
+    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
+    a.counter = ctx->counters + 3 * slot;               // [0] plan-0 queue, [1] fix-up queue, [2] flag count
+    a.flag_count = reinterpret_cast<int*>(ctx->counters + 3 * slot + 2);
+    a.only_flagged = 0;
+    CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
+    const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
+    int rc;
+
+    if (plan == 0 || plan == 3 || plan == 4 || plan == 5) {
+        // Register-resident kernels: row-per-thread (plan 0 default; hybrid register + shared-memory rows at (200,100)) and
+        // the warp-tiled kernel (plan 4, the fallback of plan 0 for shapes the row kernel does not cover).  Plans 3 / 5
+        // (2-D tile, software-pipelined rows) exist only in the `make experiments` build.
+        int which = ddb::rowreg_supported(m, n) ? 1 : 2;
+        if (plan == 3) which = 0;
+        if (plan == 4) which = 2;
+        if (plan == 5) which = 3;
+        if (gen) which = 1;                              // the caller checked rowreg_gen_supported
+        const int grid = gen ? ddb::rowreg_gen_grid(m, n, ctx->sm_count) : ddb::rowreg_grid(m, n, ctx->sm_count);
+        const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
+        const long long fgrid = generic_grid(ctx, m, n, fplan, B);
+        size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count)
+                                   : (which == 1 ? ddb::rowreg_rows_scratch_bytes(m, n, grid) : 0);
+        const size_t fneed = generic_scratch_bytes(ctx, m, n, fplan, B);
+        if (fneed > need) need = fneed;
+        const size_t need_d = (which == 1) ? ddb::rowreg_d_scratch_bytes(m, n, grid) : 0;
+        const size_t need_slab = (gen && !A) ? (size_t)(grid > fgrid ? grid : fgrid) * per_lp : 0;
+        if ((rc = scratch_acquire(ctx, st, need, need_d, need_slab))) return rc;
+        a.gtab = (double*)ctx->scratch.p;
+        a.dscr = (double*)ctx->dscr.p;
+        a.slab = (double*)ctx->slab.p;
+        if (gen)
+            CUDA_TRY(ddb::launch_simplex_rowreg_gen(a, ctx->sm_count, st));
+        else if (which == 0)
+            CUDA_TRY(ddb::launch_simplex_tile2d(a, ctx->sm_count, st));
+        else if (which == 1)
+            CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
+        else if (which == 3)
+            CUDA_TRY(ddb::launch_simplex_rowpipe(a, ctx->sm_count, st));
+        else
+            CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
+        ctx->launches += 1;
+        // fix-up pass: instances the tile could not hold / whose static crash basis was singular were flagged
+        // status = -1; the generic kernel re-solves exactly those (it returns at once when none were flagged).
+        a.only_flagged = 1;
+        a.counter = ctx->counters + 3 * slot + 1;
+        rc = launch_generic(ctx, a, fplan, st);
+        if (rc) return rc;
+        return scratch_release(ctx, st);
+    }
+
+    if ((rc = scratch_acquire(ctx, st, generic_scratch_bytes(ctx, m, n, plan, B), 0, 0))) return rc;
+    rc = launch_generic(ctx, a, plan, st);
+    if (rc) return rc;
+    return scratch_release(ctx, st);
 }
 
 extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b,
@@ -292,69 +447,150 @@ extern "C" int ddb_solve_label_dev(ddb_ctx* ctx, int64_t B, int m, int n, const 
     if (B < 0 || m < 1 || n < 1 || !(threshold >= 0.0))
         return fail(DDB_EINVAL, "ddb_solve_label_dev: B=%lld m=%d n=%d threshold=%g", (long long)B, m, n, threshold);
     if (B == 0) return DDB_OK;
-    const int plan = ddb_solve_plan(ctx, m, n);
-    if (plan < 0) return plan;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
-    cudaStream_t st = (cudaStream_t)stream;
-
-    ddb::SolveArgs a;
-    a.m = m; a.n = n; a.B = B;
-    a.A = A; a.b = b; a.c = c; a.row_mask = row_mask; a.thr = threshold;
-    a.status = status; a.x = x; a.obj = obj; a.labels = labels; a.n_active = n_active;
-    a.pivots = pivots; a.ties = ties; a.violations = violations;
-    a.max_iter = 50 * (m + n);
-    a.gtab = nullptr;
-    const int slot = ctx->next_counter;
-    ctx->next_counter = (ctx->next_counter + 1) % kCounters;
-    a.counter = ctx->counters + 3 * slot;               // [0] plan-0 queue, [1] fix-up queue, [2] flag count
-    a.flag_count = reinterpret_cast<int*>(ctx->counters + 3 * slot + 2);
-    a.only_flagged = 0;
-    CUDA_TRY(cudaMemsetAsync(a.counter, 0, 3 * sizeof(unsigned long long), st));
-
-    if (plan == 0 || plan == 3 || plan == 4 || plan == 5) {
-        // Register-resident kernels: row-per-thread (plan 0 default), its software-pipelined variant (plan 5, measured
-        // slower: DESIGN.md), 2-D tile (plan 3), warp-tiled (plan 4, and the fallback of plan 0 for shapes the row
-        // kernels do not cover).
-        int which = ddb::rowreg_supported(m, n) ? 1 : (ddb::tile2d_supported(m, n) ? 0 : 2);
-        if (plan == 3) which = 0;
-        if (plan == 4) which = 2;
-        if (plan == 5) which = 3;
-        const size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count)
-                            : (which == 1 ? ddb::rowreg_scratch_bytes(m, n, ctx->sm_count) : 0);
-        if (need) {
-            if (ctx->scratch_in_use) CUDA_TRY(cudaStreamWaitEvent(st, ctx->scratch_free, 0));
-            if (need > ctx->scratch.cap) CUDA_TRY(cudaDeviceSynchronize());
-            int rc = ensure(ctx->scratch, need);
-            if (rc) return rc;
-            a.gtab = (double*)ctx->scratch.p;
-        }
-        if (which == 0)
-            CUDA_TRY(ddb::launch_simplex_tile2d(a, ctx->sm_count, st));
-        else if (which == 1)
-            CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
-        else if (which == 3)
-            CUDA_TRY(ddb::launch_simplex_rowpipe(a, ctx->sm_count, st));
-        else
-            CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
-        if (need) {
-            CUDA_TRY(cudaEventRecord(ctx->scratch_free, st));
-            ctx->scratch_in_use = true;
-        }
-        ctx->launches += 1;
-        // fix-up pass: instances the tile could not hold / whose static crash basis was singular were flagged
-        // status = -1; the generic kernel re-solves exactly those (it returns at once when none were flagged).
-        a.only_flagged = 1;
-        a.counter = ctx->counters + 3 * slot + 1;
-        const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
-        int rc = launch_generic(ctx, a, fplan, st);
-        return rc;
-    }
-
-    return launch_generic(ctx, a, plan, st);
+    return solve_launch(ctx, B, m, n, A, b, c, threshold, row_mask, status, x, obj, labels, n_active, pivots, ties, violations,
+                        nullptr, (cudaStream_t)stream);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// host-buffer flavour: chunked, two slots in flight (H2D of chunk k+1 overlaps the solve of chunk k)
+// host-buffer plumbing: pinned caller buffers are DMA'd directly; pageable ones go through the context's pinned staging
+// ring (parallel memcpy on a few host threads into the slot's staging block, one cudaMemcpyAsync per array from there)
+// ---------------------------------------------------------------------------------------------------------
+static bool is_pinned(const void* p) {
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+static int ensure_pinned(HostBuf& hb, size_t bytes) {
+    if (bytes <= hb.cap) return DDB_OK;
+    if (hb.p) cudaFreeHost(hb.p);
+    hb.p = nullptr;
+    hb.cap = 0;
+    cudaError_t e = cudaHostAlloc(&hb.p, bytes, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(DDB_ENOMEM, "cudaHostAlloc(%zu): %s", bytes, cudaGetErrorString(e));
+    hb.cap = bytes;
+    return DDB_OK;
+}
+
+static int copy_threads() {
+    static const int v = [] {
+        const char* e = getenv("DDB_COPY_THREADS");
+        int t = e ? atoi(e) : 0;
+        if (t <= 0) {
+            const unsigned hc = std::thread::hardware_concurrency();
+            t = hc >= 16 ? 8 : (hc >= 4 ? (int)hc / 2 : 1);
+        }
+        return t > 32 ? 32 : t;
+    }();
+    return v;
+}
+
+// memcpy split over a few threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~55
+static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    const int nt = copy_threads();
+    if (nt <= 1 || bytes < (size_t)(8u << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes / nt) + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (int t = 0; t < nt; ++t) {
+        const size_t off = (size_t)t * slice;
+        if (off >= bytes) break;
+        const size_t nb = (bytes - off < slice) ? (bytes - off) : slice;
+        th.emplace_back([=] { memcpy((char*)dst + off, (const char*)src + off, nb); });
+    }
+    for (auto& t : th) t.join();
+}
+
+static int slot_wait_and_retire(Slot& s) {
+    CUDA_TRY(cudaEventSynchronize(s.done));
+    for (const Retire& r : s.retire) memcpy(r.dst, r.src, r.bytes);
+    s.retire.clear();
+    return DDB_OK;
+}
+
+// H2D of one array of a chunk: direct when the caller's memory is pinned, else through `stage` (advances stage_off)
+static int h2d(Slot& s, void* dev, const void* host, size_t bytes, bool pinned, size_t& stage_off) {
+    if (bytes == 0) return DDB_OK;
+    if (pinned) {
+        CUDA_TRY(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s.stream));
+    } else {
+        char* st = (char*)s.in.p + stage_off;
+        parallel_memcpy(st, host, bytes);
+        CUDA_TRY(cudaMemcpyAsync(dev, st, bytes, cudaMemcpyHostToDevice, s.stream));
+        stage_off += (bytes + 255) & ~(size_t)255;
+    }
+    return DDB_OK;
+}
+// D2H of one output array of a chunk: direct when pinned, else into the slot's pinned out-block + a retire entry
+static int d2h(Slot& s, cudaStream_t st, void* host, const void* dev, size_t bytes, bool pinned, size_t& stage_off) {
+    if (!host || bytes == 0) return DDB_OK;
+    if (pinned) {
+        CUDA_TRY(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, st));
+    } else {
+        char* stg = (char*)s.out.p + stage_off;
+        CUDA_TRY(cudaMemcpyAsync(stg, dev, bytes, cudaMemcpyDeviceToHost, st));
+        s.retire.push_back({host, stg, bytes});
+        stage_off += (bytes + 255) & ~(size_t)255;
+    }
+    return DDB_OK;
+}
+
+struct HostOut {              // the caller's host output arrays and whether each is page-locked
+    int32_t* status; double* x; double* obj; uint8_t* labels; int32_t* n_active; int32_t* pivots; int32_t* ties;
+    int32_t* violations;
+    bool pinned;              // all of them (one pageable array sends every output through staging: they are small)
+};
+
+static size_t out_bytes_per_lp(int m, int n) { return 4 + (size_t)n * 8 + 8 + m + 4 + 16 + 4 + 4; }   // status x obj labels n_active pivots ties violations
+
+static int ensure_slot_outputs(Slot& s, int64_t nb, int m, int n, const HostOut& o) {
+    int rc;
+    if ((rc = ensure(s.status, (size_t)nb * 4))) return rc;
+    if ((rc = ensure(s.labels, (size_t)nb * m))) return rc;
+    if (o.x && (rc = ensure(s.x, (size_t)nb * n * 8))) return rc;
+    if (o.obj && (rc = ensure(s.obj, (size_t)nb * 8))) return rc;
+    if (o.n_active && (rc = ensure(s.nact, (size_t)nb * 4))) return rc;
+    if (o.pivots && (rc = ensure(s.piv, (size_t)nb * 16))) return rc;
+    if (o.ties && (rc = ensure(s.ties, (size_t)nb * 4))) return rc;
+    if (o.violations && (rc = ensure(s.viol, (size_t)nb * 4))) return rc;
+    if (!o.pinned && (rc = ensure_pinned(s.out, (size_t)nb * (out_bytes_per_lp(m, n) + 8) + 8 * 256))) return rc;
+    return DDB_OK;
+}
+
+static int slot_d2h_outputs(Slot& s, int64_t off, int64_t nb, int m, int n, const HostOut& o) {
+    size_t so = 0;
+    int rc;
+    cudaStream_t st = s.stream;
+    if ((rc = d2h(s, st, o.status + off, s.status.p, (size_t)nb * 4, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.labels + (size_t)off * m, s.labels.p, (size_t)nb * m, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.x ? o.x + (size_t)off * n : nullptr, s.x.p, (size_t)nb * n * 8, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.obj ? o.obj + off : nullptr, s.obj.p, (size_t)nb * 8, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.n_active ? o.n_active + off : nullptr, s.nact.p, (size_t)nb * 4, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.pivots ? o.pivots + (size_t)off * 4 : nullptr, s.piv.p, (size_t)nb * 16, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.ties ? o.ties + off : nullptr, s.ties.p, (size_t)nb * 4, o.pinned, so))) return rc;
+    if ((rc = d2h(s, st, o.violations ? o.violations + off : nullptr, s.viol.p, (size_t)nb * 4, o.pinned, so))) return rc;
+    return DDB_OK;
+}
+
+static HostOut make_host_out(int32_t* status, double* x, double* obj, uint8_t* labels, int32_t* n_active, int32_t* pivots,
+                             int32_t* ties, int32_t* violations) {
+    HostOut o{status, x, obj, labels, n_active, pivots, ties, violations, true};
+    o.pinned = is_pinned(status) && is_pinned(x) && is_pinned(obj) && is_pinned(labels) && is_pinned(n_active) &&
+               is_pinned(pivots) && is_pinned(ties) && is_pinned(violations);
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host-buffer flavour: chunked, kSlots chunks in flight (stage-in and H2D of chunk k+1 overlap the solve of chunk k)
 // ---------------------------------------------------------------------------------------------------------
 extern "C" int ddb_solve_label_host(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, const double* b,
                                     const double* c, double threshold, const uint8_t* row_mask, int32_t* status,
@@ -363,123 +599,176 @@ extern "C" int ddb_solve_label_host(ddb_ctx* ctx, int64_t B, int m, int n, const
     if (!ctx || !A || !b || !c || !status || !labels) return fail(DDB_EINVAL, "ddb_solve_label_host: NULL argument");
     if (B < 0 || m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_solve_label_host: B=%lld m=%d n=%d", (long long)B, m, n);
     if (B == 0) return DDB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
-    // chunks of ~192 MB: the copy engine is the bottleneck (PCIe ~52 GB/s vs 8(mn+m+n) bytes per LP), so the pipeline
-    // fill (first H2D) and drain (last solve) are what chunking can shrink; at least 8 LPs per SM keep the solver's
-    // persistent CTAs balanced
-    int64_t chunk = (int64_t)((size_t)(192u << 20) / per_lp);
+    // chunks of ~192 MB (DDB_HOST_CHUNK_MB): the copy engine is the bottleneck (PCIe ~52 GB/s vs 8(mn+m+n) bytes per LP), so
+    // the pipeline fill (first H2D) and drain (last solve) are what chunking can shrink; at least 8 LPs per SM keep the
+    // solver's persistent CTAs balanced
+    static const long long chunk_mb = [] { const char* e = getenv("DDB_HOST_CHUNK_MB"); return e ? atoll(e) : 192ll; }();
+    int64_t chunk = (int64_t)((size_t)(chunk_mb << 20) / per_lp);
     const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > B) chunk = B;
+    const bool pinA = is_pinned(A), pinb = is_pinned(b), pinc = is_pinned(c), pinm = is_pinned(row_mask);
+    const HostOut o = make_host_out(status, x, obj, labels, n_active, pivots, ties, violations);
     int rc = DDB_OK;
     int k = 0;
     for (int64_t off = 0; off < B; off += chunk, ++k) {
         const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
         Slot& s = ctx->slots[k % kSlots];
-        CUDA_TRY(cudaEventSynchronize(s.done));   // previous use of this slot has drained
+        if ((rc = slot_wait_and_retire(s))) return rc;   // previous use of this slot has drained
         if ((rc = ensure(s.A, (size_t)nb * m * n * 8))) return rc;
         if ((rc = ensure(s.b, (size_t)nb * m * 8))) return rc;
         if ((rc = ensure(s.c, (size_t)nb * n * 8))) return rc;
-        if ((rc = ensure(s.status, (size_t)nb * 4))) return rc;
-        if ((rc = ensure(s.labels, (size_t)nb * m))) return rc;
         if (row_mask && (rc = ensure(s.mask, (size_t)nb * m))) return rc;
-        if (x && (rc = ensure(s.x, (size_t)nb * n * 8))) return rc;
-        if (obj && (rc = ensure(s.obj, (size_t)nb * 8))) return rc;
-        if (n_active && (rc = ensure(s.nact, (size_t)nb * 4))) return rc;
-        if (pivots && (rc = ensure(s.piv, (size_t)nb * 16))) return rc;
-        if (ties && (rc = ensure(s.ties, (size_t)nb * 4))) return rc;
-        if (violations && (rc = ensure(s.viol, (size_t)nb * 4))) return rc;
-        cudaStream_t st = s.stream;
-        CUDA_TRY(cudaMemcpyAsync(s.A.p, A + (size_t)off * m * n, (size_t)nb * m * n * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(s.b.p, b + (size_t)off * m, (size_t)nb * m * 8, cudaMemcpyHostToDevice, st));
-        CUDA_TRY(cudaMemcpyAsync(s.c.p, c + (size_t)off * n, (size_t)nb * n * 8, cudaMemcpyHostToDevice, st));
-        if (row_mask)
-            CUDA_TRY(cudaMemcpyAsync(s.mask.p, row_mask + (size_t)off * m, (size_t)nb * m, cudaMemcpyHostToDevice, st));
-        rc = ddb_solve_label_dev(ctx, nb, m, n, (const double*)s.A.p, (const double*)s.b.p, (const double*)s.c.p,
-                                 threshold, row_mask ? (const uint8_t*)s.mask.p : nullptr, (int32_t*)s.status.p,
-                                 x ? (double*)s.x.p : nullptr, obj ? (double*)s.obj.p : nullptr, (uint8_t*)s.labels.p,
-                                 n_active ? (int32_t*)s.nact.p : nullptr, pivots ? (int32_t*)s.piv.p : nullptr,
-                                 ties ? (int32_t*)s.ties.p : nullptr, violations ? (int32_t*)s.viol.p : nullptr, st);
+        if ((rc = ensure_slot_outputs(s, nb, m, n, o))) return rc;
+        size_t stage_need = 1024;
+        if (!pinA) stage_need += (size_t)nb * m * n * 8 + 256;
+        if (!pinb) stage_need += (size_t)nb * m * 8 + 256;
+        if (!pinc) stage_need += (size_t)nb * n * 8 + 256;
+        if (row_mask && !pinm) stage_need += (size_t)nb * m + 256;
+        if (stage_need > 1024 && (rc = ensure_pinned(s.in, stage_need))) return rc;
+        size_t so = 0;
+        if ((rc = h2d(s, s.A.p, A + (size_t)off * m * n, (size_t)nb * m * n * 8, pinA, so))) return rc;
+        if ((rc = h2d(s, s.b.p, b + (size_t)off * m, (size_t)nb * m * 8, pinb, so))) return rc;
+        if ((rc = h2d(s, s.c.p, c + (size_t)off * n, (size_t)nb * n * 8, pinc, so))) return rc;
+        if (row_mask && (rc = h2d(s, s.mask.p, row_mask + (size_t)off * m, (size_t)nb * m, pinm, so))) return rc;
+        rc = solve_launch(ctx, nb, m, n, (const double*)s.A.p, (const double*)s.b.p, (const double*)s.c.p, threshold,
+                          row_mask ? (const uint8_t*)s.mask.p : nullptr, (int32_t*)s.status.p,
+                          x ? (double*)s.x.p : nullptr, obj ? (double*)s.obj.p : nullptr, (uint8_t*)s.labels.p,
+                          n_active ? (int32_t*)s.nact.p : nullptr, pivots ? (int32_t*)s.piv.p : nullptr,
+                          ties ? (int32_t*)s.ties.p : nullptr, violations ? (int32_t*)s.viol.p : nullptr, nullptr, s.stream);
         if (rc) return rc;
-        CUDA_TRY(cudaMemcpyAsync(status + off, s.status.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaMemcpyAsync(labels + (size_t)off * m, s.labels.p, (size_t)nb * m, cudaMemcpyDeviceToHost, st));
-        if (x) CUDA_TRY(cudaMemcpyAsync(x + (size_t)off * n, s.x.p, (size_t)nb * n * 8, cudaMemcpyDeviceToHost, st));
-        if (obj) CUDA_TRY(cudaMemcpyAsync(obj + off, s.obj.p, (size_t)nb * 8, cudaMemcpyDeviceToHost, st));
-        if (n_active) CUDA_TRY(cudaMemcpyAsync(n_active + off, s.nact.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        if (pivots) CUDA_TRY(cudaMemcpyAsync(pivots + (size_t)off * 4, s.piv.p, (size_t)nb * 16, cudaMemcpyDeviceToHost, st));
-        if (ties) CUDA_TRY(cudaMemcpyAsync(ties + off, s.ties.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        if (violations)
-            CUDA_TRY(cudaMemcpyAsync(violations + off, s.viol.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaEventRecord(s.done, st));
+        if ((rc = slot_d2h_outputs(s, off, nb, m, n, o))) return rc;
+        CUDA_TRY(cudaEventRecord(s.done, s.stream));
     }
-    for (int i = 0; i < kSlots; ++i) CUDA_TRY(cudaEventSynchronize(ctx->slots[i].done));
+    for (int i = 0; i < kSlots; ++i)
+        if ((rc = slot_wait_and_retire(ctx->slots[i]))) return rc;
     return DDB_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// fused generate -> solve -> label on device-resident outputs
+// fused generate -> solve -> label
 // ---------------------------------------------------------------------------------------------------------
-extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
-                                            double density, double threshold, int32_t* status, double* x, double* obj,
-                                            uint8_t* labels, int32_t* n_active, int32_t* pivots, int32_t* ties,
-                                            double* A_out, double* b_out, double* c_out, void* stream) {
-    if (!ctx || !status || !labels) return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: NULL argument");
-    if (B < 0 || m < 1 || n < 1) return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: B=%lld m=%d n=%d", (long long)B, m, n);
-    if (B == 0) return DDB_OK;
-    CUDA_TRY(cudaSetDevice(ctx->device));
+static int fused_launch(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n, double density,
+                        double threshold, int32_t* status, double* x, double* obj, uint8_t* labels, int32_t* n_active,
+                        int32_t* pivots, int32_t* ties, int32_t* violations, double* A_out, double* b_out, double* c_out,
+                        cudaStream_t st) {
+    const bool keep = A_out && b_out && c_out;
+    // TRUE FUSION (even n, shapes of the row-per-thread kernel): ONE launch; every solver CTA draws its instance itself
+    // (Philox, counter = global instance index) into a per-CTA slab that lives in L2 -- A never travels through HBM and no
+    // generator kernel runs.  DDB_FUSED_INKERNEL=0 forces the two-kernel fallback below (A/B measurements).
+    static const bool inkernel = [] { const char* e = getenv("DDB_FUSED_INKERNEL"); return !(e && e[0] == '0'); }();
+    const int plan = ddb_solve_plan(ctx, m, n);
+    if (plan < 0) return plan;
+    if (inkernel && plan == 0 && ctx->forced_plan < 0 && ddb::rowreg_gen_supported(m, n) &&
+        (!keep || (reinterpret_cast<uintptr_t>(A_out) & 15) == 0)) {
+        GenSpec g{key, first_instance, density};
+        return solve_launch(ctx, B, m, n, keep ? A_out : nullptr, keep ? b_out : nullptr, keep ? c_out : nullptr, threshold,
+                            nullptr, status, x, obj, labels, n_active, pivots, ties, violations, &g, st);
+    }
+    // Fallback (odd n, shapes outside plan 0): generator kernel -> chunk buffers in context scratch -> solver, chunk i + 1
+    // generated on a side stream while chunk i is solved.
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
-    // chunk = instances generated into scratch per solver launch (DDB_FUSED_CHUNK_MB of instance data).  Measured at
-    // (200,100), 262 144 instances: 64 MB (two instances per persistent CTA: the launch tails dominate) 377 k LP/s,
-    // 512 MB 402 k, 2 GB 400 k, 6 GB 398 k (profiles/fused_chunk_r01.txt) -- a few launches' worth of L2-warm instances
-    // beats both extremes.
     static const long long chunk_mb = [] { const char* e = getenv("DDB_FUSED_CHUNK_MB"); return e ? atoll(e) : 512ll; }();
     int64_t chunk = (int64_t)((size_t)(chunk_mb << 20) / per_lp);
     const int64_t min_chunk = (int64_t)ctx->sm_count * 4;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > B) chunk = B;
-    const bool keep = A_out && b_out && c_out;
-    // DDB_FUSED_OVERLAP (default 1): chunk i + 1 is generated on a side stream while chunk i is solved -- the solver's
-    // persistent CTAs fill the register files, so the generator's blocks land on the SMs its tail leaves idle
-    static const bool overlap = [] { const char* e = getenv("DDB_FUSED_OVERLAP"); return !(e && e[0] == '0'); }();
-    cudaStream_t st = (cudaStream_t)stream;
-    const int halves = overlap ? 2 : 1;
     int rc;
     if (!keep) {
-        CUDA_TRY(cudaStreamSynchronize(st));   // scratch reuse across calls
-        if ((rc = ensure(ctx->genA, (size_t)halves * chunk * m * n * 8))) return rc;
-        if ((rc = ensure(ctx->genb, (size_t)halves * chunk * m * 8))) return rc;
-        if ((rc = ensure(ctx->genc, (size_t)halves * chunk * n * 8))) return rc;
+        // the chunk buffers are per-context: wait for the last solve that read them, whatever stream it ran on
+        if (ctx->gen_in_use) CUDA_TRY(cudaEventSynchronize(ctx->gen_free));
+        if ((rc = ensure(ctx->genA, (size_t)2 * chunk * m * n * 8))) return rc;
+        if ((rc = ensure(ctx->genb, (size_t)2 * chunk * m * 8))) return rc;
+        if ((rc = ensure(ctx->genc, (size_t)2 * chunk * n * 8))) return rc;
     }
-    if (overlap) {                              // the side stream starts after whatever the caller has queued so far
-        CUDA_TRY(cudaEventRecord(ctx->gen_fork, st));
-        CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->gen_fork, 0));
-    }
+    CUDA_TRY(cudaEventRecord(ctx->gen_fork, st));   // the side stream starts after whatever the caller has queued so far
+    CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->gen_fork, 0));
     int64_t idx = 0;
     for (int64_t off = 0; off < B; off += chunk, ++idx) {
         const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
-        const int h = overlap ? (int)(idx & 1) : 0;
+        const int h = (int)(idx & 1);
         double* Ap = keep ? A_out + (size_t)off * m * n : (double*)ctx->genA.p + (size_t)h * chunk * m * n;
         double* bp = keep ? b_out + (size_t)off * m : (double*)ctx->genb.p + (size_t)h * chunk * m;
         double* cp = keep ? c_out + (size_t)off * n : (double*)ctx->genc.p + (size_t)h * chunk * n;
-        if (overlap) {
-            if (!keep && idx >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->solve_done[h], 0));   // half h is free again
-            rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, ctx->gen_stream);
-            if (rc) return rc;
-            CUDA_TRY(cudaEventRecord(ctx->gen_done[h], ctx->gen_stream));
-            CUDA_TRY(cudaStreamWaitEvent(st, ctx->gen_done[h], 0));
-        } else {
-            rc = ddb_generate_dev(ctx, key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, stream);
-            if (rc) return rc;
-        }
-        rc = ddb_solve_label_dev(ctx, nb, m, n, Ap, bp, cp, threshold, nullptr, status + off,
-                                 x ? x + (size_t)off * n : nullptr, obj ? obj + off : nullptr,
-                                 labels + (size_t)off * m, n_active ? n_active + off : nullptr,
-                                 pivots ? pivots + (size_t)off * 4 : nullptr, ties ? ties + off : nullptr, nullptr,
-                                 stream);
+        if (!keep && idx >= 2) CUDA_TRY(cudaStreamWaitEvent(ctx->gen_stream, ctx->solve_done[h], 0));   // half h is free again
+        int launches = 0;
+        CUDA_TRY(ddb::launch_generate(key, first_instance + off, nb, m, n, density, Ap, bp, cp, nullptr, ctx->sm_count,
+                                      ctx->gen_stream, &launches));
+        ctx->launches += launches;
+        CUDA_TRY(cudaEventRecord(ctx->gen_done[h], ctx->gen_stream));
+        CUDA_TRY(cudaStreamWaitEvent(st, ctx->gen_done[h], 0));
+        rc = solve_launch(ctx, nb, m, n, Ap, bp, cp, threshold, nullptr, status + off, x ? x + (size_t)off * n : nullptr,
+                          obj ? obj + off : nullptr, labels + (size_t)off * m, n_active ? n_active + off : nullptr,
+                          pivots ? pivots + (size_t)off * 4 : nullptr, ties ? ties + off : nullptr,
+                          violations ? violations + off : nullptr, nullptr, st);
         if (rc) return rc;
-        if (overlap && !keep) CUDA_TRY(cudaEventRecord(ctx->solve_done[h], st));
+        if (!keep) CUDA_TRY(cudaEventRecord(ctx->solve_done[h], st));
     }
+    if (!keep) {
+        CUDA_TRY(cudaEventRecord(ctx->gen_free, st));
+        ctx->gen_in_use = true;
+    }
+    return DDB_OK;
+}
+
+extern "C" int ddb_generate_solve_label_dev(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                            double density, double threshold, int32_t* status, double* x, double* obj,
+                                            uint8_t* labels, int32_t* n_active, int32_t* pivots, int32_t* ties,
+                                            int32_t* violations, double* A_out, double* b_out, double* c_out, void* stream) {
+    if (!ctx || !status || !labels) return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: NULL argument");
+    if (B < 0 || m < 1 || n < 1 || !(density > 0.0 && density <= 1.0) || !(threshold >= 0.0))
+        return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: B=%lld m=%d n=%d density=%g threshold=%g", (long long)B, m, n,
+                    density, threshold);
+    if ((A_out || b_out || c_out) && !(A_out && b_out && c_out))
+        return fail(DDB_EINVAL, "ddb_generate_solve_label_dev: A_out, b_out, c_out must be given together");
+    if (B == 0) return DDB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return fused_launch(ctx, key, first_instance, B, m, n, density, threshold, status, x, obj, labels, n_active, pivots, ties,
+                        violations, A_out, b_out, c_out, (cudaStream_t)stream);
+}
+
+// Fused call with HOST outputs: what the reference's generate -> solve -> label loop hands to its caller (labels, status,
+// objective, x, ...) lands in host arrays; nothing travels host -> device.  Chunks of DDB_FUSED_HOST_CHUNK instances:
+// the D2H of chunk k overlaps the solve of chunk k + 1.
+extern "C" int ddb_generate_solve_label_host(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                             double density, double threshold, int32_t* status, double* x, double* obj,
+                                             uint8_t* labels, int32_t* n_active, int32_t* pivots, int32_t* ties,
+                                             int32_t* violations) {
+    if (!ctx || !status || !labels) return fail(DDB_EINVAL, "ddb_generate_solve_label_host: NULL argument");
+    if (B < 0 || m < 1 || n < 1 || !(density > 0.0 && density <= 1.0) || !(threshold >= 0.0))
+        return fail(DDB_EINVAL, "ddb_generate_solve_label_host: B=%lld m=%d n=%d density=%g threshold=%g", (long long)B, m, n,
+                    density, threshold);
+    if (B == 0) return DDB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    static const long long chunk_lps = [] { const char* e = getenv("DDB_FUSED_HOST_CHUNK"); return e ? atoll(e) : 16384ll; }();
+    int64_t chunk = chunk_lps;
+    const int64_t min_chunk = (int64_t)ctx->sm_count * 8;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > B) chunk = B;
+    const HostOut o = make_host_out(status, x, obj, labels, n_active, pivots, ties, violations);
+    int rc = DDB_OK;
+    int k = 0;
+    for (int64_t off = 0; off < B; off += chunk, ++k) {
+        const int64_t nb = (B - off < chunk) ? (B - off) : chunk;
+        Slot& s = ctx->slots[k % kSlots];
+        if ((rc = slot_wait_and_retire(s))) return rc;
+        if ((rc = ensure_slot_outputs(s, nb, m, n, o))) return rc;
+        rc = fused_launch(ctx, key, first_instance + off, nb, m, n, density, threshold, (int32_t*)s.status.p,
+                          x ? (double*)s.x.p : nullptr, obj ? (double*)s.obj.p : nullptr, (uint8_t*)s.labels.p,
+                          n_active ? (int32_t*)s.nact.p : nullptr, pivots ? (int32_t*)s.piv.p : nullptr,
+                          ties ? (int32_t*)s.ties.p : nullptr, violations ? (int32_t*)s.viol.p : nullptr, nullptr, nullptr,
+                          nullptr, s.stream);
+        if (rc) return rc;
+        if ((rc = slot_d2h_outputs(s, off, nb, m, n, o))) return rc;
+        CUDA_TRY(cudaEventRecord(s.done, s.stream));
+    }
+    for (int i = 0; i < kSlots; ++i)
+        if ((rc = slot_wait_and_retire(ctx->slots[i]))) return rc;
     return DDB_OK;
 }
 
@@ -501,6 +790,7 @@ extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, in
     if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
         return fail(DDB_EINVAL, "ddb_s2v_forward_dev: B=%lld m=%d n=%d p=%d T=%d", (long long)B, m, n, p, T);
     if (B == 0) return DDB_OK;
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int slot = ctx->next_counter;
@@ -564,6 +854,7 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
         return fail(DDB_EUNSUPPORTED, "ddb_s2v_loss_grad_dev: only the bipartite variant (graph 1) has a device backward");
     if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
         return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: B=%lld m=%d n=%d p=%d T=%d", (long long)B, m, n, p, T);
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     cudaStream_t st = (cudaStream_t)stream;
     const int npar = ddb_s2v_param_count(graph, p);
@@ -592,6 +883,7 @@ extern "C" int ddb_s2v_metrics_dev(ddb_ctx* ctx, int64_t N, const float* logp, c
                                    float thresh, float w0, float w1, double* out, void* stream) {
     if (!ctx || !probs || !labels || !out) return fail(DDB_EINVAL, "ddb_s2v_metrics_dev: NULL argument");
     if (N < 0) return fail(DDB_EINVAL, "ddb_s2v_metrics_dev: N=%lld", (long long)N);
+    std::lock_guard<std::mutex> lock(ctx->mu);
     CUDA_TRY(cudaSetDevice(ctx->device));
     const int slot = ctx->next_counter;
     ctx->next_counter = (ctx->next_counter + 1) % kCounters;

@@ -37,6 +37,14 @@ struct SolveArgs {
     int max_iter;
     int only_flagged;          // generic kernel: solve only instances whose status is -1 (flagged by plan 0)
     int* flag_count;           // number of instances plan 0 flagged for the generic kernel
+    double* dscr;              // plan 0, hybrid rows: per-CTA global home of the crash inverse D (L2-resident, read back by bulk TMA)
+    // fused generate -> solve -> label (gen != 0): instance lp is drawn inside the solver CTA from (gen_key, gen_first + lp);
+    // A / b / c then point at the caller's output arrays (nullable: the instance lives only in a per-CTA slab in `slab`)
+    int gen;
+    unsigned long long gen_key;
+    long long gen_first;
+    double gen_density;
+    double* slab;              // [grid][m n + m + n] per-CTA instance slabs (used when A is NULL)
 };
 
 // Arguments of the classifier forward kernels (s2v_forward.cu, s2v_bipartite_dense.cu).
@@ -78,6 +86,9 @@ __device__ __forceinline__ void fence_proxy_async() {
 // all state spaces: orders this thread's generic-proxy accesses (global and shared) before later async-proxy ones
 __device__ __forceinline__ void fence_proxy_async_all() {
     asm volatile("fence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)

@@ -26,7 +26,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "common.cuh"
+#include "../common.cuh"
 
 // dev-only stage accounting (tools/rowreg_timing.cu builds with -DDDB_TIMING; never defined in the library build)
 #ifdef DDB_TIMING
@@ -778,7 +778,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowpipe_kernel(SolveArgs
                 const bool excl = mask && mask[i] == 0;
                 if (!excl) tie |= (active != (basic_tile[i] < 0));
                 nties += tie;
-                nviol += (slack < -a.thr * 10.0);
+                nviol += (slack < -a.thr);
                 nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);   // active row with a visible residual
             }
         }

@@ -31,7 +31,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "common.cuh"
+#include "../common.cuh"
 
 namespace ddb {
 
@@ -731,7 +731,7 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_tile2d_kernel(SolveArgs 
                 const bool excl = mask && mask[i] == 0;
                 if (!excl) tie |= (active != (basic_tile[i] < 0));
                 nties += tie;
-                nviol += (slack < -a.thr * 10.0);
+                nviol += (slack < -a.thr);
                 nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);   // active row with a visible residual
             }
         }

@@ -9,49 +9,9 @@
 // Instance i is a pure function of (key, i): Philox4x32-10, key = (key_lo, key_hi),
 // counter = (pair index, stream id, i_lo, i_hi).  One Philox block -> two 53-bit uniforms -> one Box-Muller
 // pair -> normals for elements 2*pair and 2*pair+1 of that stream.
-#include "common.cuh"
+#include "philox.cuh"
 
 namespace ddb {
-
-enum : uint32_t { STREAM_A = 0, STREAM_X0 = 1, STREAM_EPS = 2, STREAM_C = 3, STREAM_MASK = 4 };
-
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
-                                              uint32_t k1, uint32_t out[4]) {
-    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
-        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += W0; k1 += W1;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-
-// (0,1] uniform from two 32-bit words: 27 + 26 = 53 bits, plus one so that log() is finite.
-__device__ __forceinline__ double u53_open0(uint32_t hi, uint32_t lo) {
-    const unsigned long long v = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
-    return (double)(v + 1ull) * 0x1.0p-53;
-}
-// [0,1) uniform.
-__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo) {
-    const unsigned long long v = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
-    return (double)v * 0x1.0p-53;
-}
-
-__device__ __forceinline__ void normal_pair(uint64_t key, uint64_t inst, uint32_t stream, uint32_t pair, double& z0,
-                                            double& z1) {
-    uint32_t o[4];
-    philox4x32_10(pair, stream, (uint32_t)inst, (uint32_t)(inst >> 32), (uint32_t)key, (uint32_t)(key >> 32), o);
-    const double u1 = u53_open0(o[0], o[1]);
-    const double u2 = u53(o[2], o[3]);
-    const double rad = sqrt(-2.0 * log(u1));
-    double sn, cs;
-    sincospi(2.0 * u2, &sn, &cs);
-    z0 = rad * cs;
-    z1 = rad * sn;
-}
 
 // A: one thread per element pair, grid-stride, coalesced 16-byte stores when the pair is aligned.
 __global__ void __launch_bounds__(256) generate_A_kernel(uint64_t key, long long first, long long B, int m, int n,

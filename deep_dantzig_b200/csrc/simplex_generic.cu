@@ -19,7 +19,7 @@
 //     its residual is not negligible, slack = b - A x recomputed from the caller's A, labels = |slack| <= threshold
 //     exactly as gurobi_lp.py:435-443.
 #include <cstdlib>
-#include "common.cuh"
+#include "philox.cuh"
 
 namespace ddb {
 
@@ -338,6 +338,18 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
+        if (a.gen) {
+            // fused generate -> solve -> label: an instance the row-per-thread kernel handed over exists nowhere unless the
+            // caller asked for A -- draw it again (same counters, same bits) into this CTA's slab
+            const size_t per = (size_t)m * n + m + n;
+            double* Aw = a.A ? const_cast<double*>(Ag) : a.slab + (size_t)blockIdx.x * per;
+            double* bw = a.A ? const_cast<double*>(bg) : Aw + (size_t)m * n;
+            double* cw = a.A ? const_cast<double*>(cg) : Aw + (size_t)m * n + m;
+            generate_instance_cta_notile((uint64_t)a.gen_key, (uint64_t)(a.gen_first + lp), m, n, a.gen_density, Aw, bw, cw, xbuf);
+            Ag = Aw; bg = bw; cg = cw;
+            fence_proxy_async_all();       // generic-proxy stores of the slab before the bulk-TMA staging below reads it
+            __syncthreads();
+        }
         const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;
 
         // ---- stage the instance ------------------------------------------------------------------------
@@ -697,7 +709,7 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
                     int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
                     if (rowstate[i] != ROW_EXCLUDED) tie |= (active != (where[i] < 0));
                     nties += tie;
-                    nviol += (slack < -a.thr * 10.0);
+                    nviol += (slack < -a.thr);
                 }
             }
         } else {

@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) simplex_regtile_kernel(SolveArg
                     const bool excl = mask && mask[i] == 0;
                     if (!excl) tie |= (active != (basic_tile[i] < 0));
                     nties += tie;
-                    nviol += (slack < -a.thr * 10.0);
+                    nviol += (slack < -a.thr);
                     nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);   // active row with a visible residual
                 }
             }

@@ -117,8 +117,10 @@ def generate(key, first_instance, B, m, n, density=1.0, device=0, want_x0=False)
 
 def generate_solve_label(key, first_instance, B, m, n, density=1.0, threshold=DEFAULT_THRESHOLD, device=0,
                          keep_instances=False, out=None, instances=None):
-    """Fused generate -> solve -> label; instances are only materialised for the caller when keep_instances (fresh
-    tensors) or when `instances` = (A, b, c) preallocated CUDA tensors are given."""
+    """Fused generate -> solve -> label in one kernel launch (the solver CTA draws its instance itself); instances are
+    only materialised for the caller when keep_instances (fresh tensors) or when `instances` = (A, b, c) preallocated
+    CUDA tensors are given.  Batched replacement of the loop RandomLPDataset._generate_problems -> create_lp_problem
+    (reference src/data/randomlp_dataset.py:58-63, 65-128)."""
     _require_cuda()
     dev = torch.device('cuda', device) if not isinstance(device, torch.device) else device
     res = out if out is not None else _alloc_outputs(B, m, n, dev)
@@ -137,8 +139,37 @@ def generate_solve_label(key, first_instance, B, m, n, density=1.0, threshold=DE
     rc = ctx.lib.ddb_generate_solve_label_dev(ctx.handle, int(key), int(first_instance), B, m, n, float(density),
                                               float(threshold), _ptr(res['status']), _ptr(res['x']), _ptr(res['obj']),
                                               _ptr(res['labels']), _ptr(res['n_active']), _ptr(res['pivots']),
-                                              _ptr(res['ties']), _ptr(A), _ptr(b), _ptr(c), _stream_ptr(dev))
+                                              _ptr(res['ties']), _ptr(res['violations']), _ptr(A), _ptr(b), _ptr(c),
+                                              _stream_ptr(dev))
     _lib.check(rc, 'ddb_generate_solve_label_dev')
     if keep_instances:
         res['A'], res['b'], res['c'] = A, b, c
+    return res
+
+
+def _host_outputs(B, m, n, pinned):
+    if pinned:
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory().numpy()
+        return SolveResult(
+            status=mk((B,), torch.int32), x=mk((B, n), torch.float64), obj=mk((B,), torch.float64),
+            labels=mk((B, m), torch.uint8), n_active=mk((B,), torch.int32), pivots=mk((B, 4), torch.int32),
+            ties=mk((B,), torch.int32), violations=mk((B,), torch.int32))
+    return SolveResult(
+        status=np.empty(B, np.int32), x=np.empty((B, n), np.float64), obj=np.empty(B, np.float64),
+        labels=np.empty((B, m), np.uint8), n_active=np.empty(B, np.int32), pivots=np.empty((B, 4), np.int32),
+        ties=np.empty(B, np.int32), violations=np.empty(B, np.int32))
+
+
+def generate_solve_label_host(key, first_instance, B, m, n, density=1.0, threshold=DEFAULT_THRESHOLD, device=0, out=None,
+                              pinned=False):
+    """Fused generate -> solve -> label with HOST (numpy) outputs: what the reference's dataset loop hands its caller.
+    Nothing travels host -> device; results come back chunk by chunk while the next chunk is being solved."""
+    _require_cuda()
+    ctx = _lib.context(device)
+    res = out if out is not None else _host_outputs(B, m, n, pinned)
+    rc = ctx.lib.ddb_generate_solve_label_host(ctx.handle, int(key), int(first_instance), B, m, n, float(density),
+                                               float(threshold), _np_ptr(res['status']), _np_ptr(res['x']),
+                                               _np_ptr(res['obj']), _np_ptr(res['labels']), _np_ptr(res['n_active']),
+                                               _np_ptr(res['pivots']), _np_ptr(res['ties']), _np_ptr(res['violations']))
+    _lib.check(rc, 'ddb_generate_solve_label_host')
     return res

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define DDB_ABI_VERSION 1
+#define DDB_ABI_VERSION 2
 
 /* return codes */
 #define DDB_OK            0
@@ -48,7 +48,10 @@ typedef struct ddb_ctx ddb_ctx;
 int         ddb_abi_version(void);
 const char *ddb_last_error(void);
 
-/* One context per (process, device): owns the work-queue counter, kernel scratch and pinned staging buffers. */
+/* One context per (process, device): owns the work-queue counters, kernel scratch (parked rows, crash inverses, fused-mode
+ * instance slabs -- all L2-resident) and the pinned staging ring of the *_host entry points.  Entry points that touch this
+ * state take the context's mutex, so a context may be shared between threads and streams: launches that use the scratch
+ * are ordered after one another by an event, whatever stream they were issued on. */
 int ddb_create(int device, ddb_ctx **out);
 int ddb_destroy(ddb_ctx *ctx);
 /* sm_count, compute capability, opt-in shared memory per block (bytes) of the context's device. */
@@ -58,9 +61,9 @@ int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, i
  * (row-per-thread kernel, falling back to the other register kernels for shapes it does not cover),
  * 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau; <0 = error. */
 int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
-/* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 3 = 2-D register-tile kernel,
- * 4 = warp-tiled register kernel, 5 = row-per-thread kernel with software-pipelined pivots (alternatives of
- * plan 0 kept for A/B measurements). */
+/* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 4 = warp-tiled register kernel (the fallback of plan 0
+ * for 100 < n <= 111).  3 (2-D register tile) and 5 (software-pipelined rows) are measured negative results that only the
+ * `make experiments` build of the library contains; the shipped library answers DDB_EUNSUPPORTED for them. */
 int ddb_set_solve_plan(ddb_ctx *ctx, int plan);
 
 /*
@@ -87,8 +90,8 @@ int ddb_generate_dev(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t
  *           |b - A x| <= threshold, all 0 when status != 2 (randomlp_dataset.py:96-102);
  *           n_active[B]; pivots[B,4] = {crash, phase-1, phase-2, total} pivot counts;
  *           ties[B] = rows whose |slack| lies in [threshold/10, threshold*10] plus rows whose label disagrees
- *           with final-basis membership; violations[B] (nullable) = rows with slack < -threshold*10 at the
- *           returned x (non-zero only for reduced LPs).
+ *           with final-basis membership; violations[B] (nullable) = rows with slack < -threshold at the
+ *           returned x (non-zero only for reduced LPs: a certificate that the reduced optimum is the full one).
  * Any output pointer except status and labels may be NULL.
  */
 int ddb_solve_label_dev(ddb_ctx *ctx, int64_t B, int m, int n,
@@ -98,7 +101,11 @@ int ddb_solve_label_dev(ddb_ctx *ctx, int64_t B, int m, int n,
                         int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations,
                         void *stream);
 
-/* Same contract, HOST buffers; H2D / D2H copies are done inside (chunked, pinned, double-buffered). */
+/* Same contract, HOST buffers; H2D / D2H copies are done inside, in chunks of ~192 MB with three chunks in flight.
+ * Page-locked caller memory (cudaHostAlloc / cudaHostRegister) is DMA'd in place.  PAGEABLE caller memory (a plain numpy
+ * array, malloc) is first copied by a few host threads (DDB_COPY_THREADS, default 8) into the context's pinned staging
+ * ring and DMA'd from there, and results come back through pinned staging the same way -- so the copies of one chunk
+ * overlap the solve of another for any caller, not only for one that pinned its buffers. */
 int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
                          const double *A, const double *b, const double *c,
                          double threshold, const uint8_t *row_mask,
@@ -106,15 +113,24 @@ int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
                          int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations);
 
 /*
- * (3) FUSED GENERATE -> SOLVE -> LABEL: same outputs as (2) for instances first_instance..+B of stream `key`
- * without the caller materialising A, b, c (they are produced chunk by chunk into context scratch).
- * A_out/b_out/c_out (nullable, device) receive the instances when the caller asks for them.
+ * (3) FUSED GENERATE -> SOLVE -> LABEL -- the whole loop RandomLPDataset._generate_problems -> create_lp_problem
+ * (src/data/randomlp_dataset.py:58-63, 65-128) for instances first_instance..+B of stream `key` in ONE kernel launch: the
+ * thread block that solves instance i draws it first (same counters and bits as (1)), into a per-block slab that stays in
+ * L2, so A never travels through HBM unless the caller asks for it.  Same outputs as (2).
+ * A_out/b_out/c_out (device; all three or none) receive the instances when the caller wants them.
+ * Odd n and shapes outside the row-per-thread kernel fall back to (1) into context scratch followed by (2), chunk by chunk.
  */
 int ddb_generate_solve_label_dev(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
                                  double density, double threshold,
                                  int32_t *status, double *x, double *obj, uint8_t *labels,
-                                 int32_t *n_active, int32_t *pivots, int32_t *ties,
+                                 int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations,
                                  double *A_out, double *b_out, double *c_out, void *stream);
+/* (3) with HOST output arrays (what the reference's loop hands its caller: labels, status, objective, x ...): nothing
+ * travels host -> device, results come back chunk by chunk while the next chunk is being solved. */
+int ddb_generate_solve_label_host(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
+                                  double density, double threshold,
+                                  int32_t *status, double *x, double *obj, uint8_t *labels,
+                                  int32_t *n_active, int32_t *pivots, int32_t *ties, int32_t *violations);
 
 /*
  * (4) CLASSIFIER FORWARD -- replaces Model.forward (src/ml/models/s2v.py:45-54; _forward_complete :124-187,

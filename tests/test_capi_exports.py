@@ -35,7 +35,7 @@ def test_library_exports_every_symbol(built):
 
 
 def test_library_loads_and_reports_version(built):
-    assert _lib.abi_version() == 1
+    assert _lib.abi_version() == 2
     lib = _lib.load()
     assert lib.ddb_last_error() is not None
 

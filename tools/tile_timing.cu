@@ -5,7 +5,7 @@
 #include <cstdlib>
 #include <vector>
 #include "../deep_dantzig_b200/csrc/generate.cu"
-#include "../deep_dantzig_b200/csrc/simplex_tile2d.cu"
+#include "../deep_dantzig_b200/csrc/experiments/simplex_tile2d.cu"
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e_)); return 1; } } while (0)
 
