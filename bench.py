@@ -26,6 +26,7 @@ if ROOT not in sys.path:
 M, N_VARS = 200, 100
 METRIC = 'LPs solved+labelled/sec at m=200 n=100'
 UNIT = 'LP/s'
+WORKLOAD = 'random dense LP m=200 n=100 fp64 (BASELINE.json configs[1] shape): generate -> solve -> label, generation excluded from the timed step'
 
 
 def _peaks():
@@ -63,7 +64,7 @@ def _cpu_worker(args):
     A, b, c = args
     out = []
     for i in range(A.shape[0]):
-        lp = oracle.LinProg(A[i], b[i], c[i], 'min', None)
+        lp = oracle.LinProg(A[i], b[i], c[i], 'min', None, polish=False)    # the timed CPU arm does the reference's work only
         lp.optimize()
         sc = lp.get_statuscode()
         if sc in (1, 2):
@@ -71,7 +72,23 @@ def _cpu_worker(args):
         else:
             act = set()
         labels = [(k, 1 if k in act else 0) for k in range(A.shape[1])]       # randomlp_dataset.py:101-102
-        out.append((sc, [l for _, l in labels]))
+        out.append((sc, [l for _, l in labels], lp.x))
+    return out
+
+
+def _polish_worker(args):
+    """Checker side (untimed): labels of the certified extended-precision vertex of HiGHS' active set."""
+    os.environ['OMP_NUM_THREADS'] = '1'
+    import numpy as np
+    from oracle import randomlp as oracle
+    A, b, c, xs = args
+    out = []
+    for i in range(A.shape[0]):
+        if xs[i] is None:
+            out.append((False, np.zeros(A.shape[1], np.uint8)))
+            continue
+        xp, ok = oracle.polish_vertex(A[i], b[i], c[i], xs[i])
+        out.append((ok, (np.abs(b[i] - A[i].dot(xp)) <= oracle.ACTIVE_THRESHOLD).astype(np.uint8)))
     return out
 
 
@@ -127,7 +144,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'random dense LP m=200 n=100 fp64 (BASELINE.json configs[1] shape), CPU sample of %d LPs/step' % per_step,
+        'config': {'workload': WORKLOAD, 'sample': 'CPU sample of %d numpy-legacy-stream LPs/step' % per_step,
                    'solver': 'HiGHS dual simplex via scipy (stand-in for the reference\'s Gurobi, which is proprietary and absent)'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -262,34 +279,117 @@ def run_ours(args):
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---- end-to-end through the host-buffer C-ABI entry point (pinned host inputs, H2D + D2H timed) -----------
+    # ---- end-to-end through the host-buffer C-ABI entry points (H2D + solve + D2H inside the timed region) -----------
+    #   e2e           : ddb_solve_label_host, caller's instances in PINNED host memory (DMA'd in place)
+    #   e2e_pageable  : the same call with plain numpy (pageable) arrays -- what INTEGRATION.md's ctypes stub passes;
+    #                   the library stages them through its pinned ring (N = 1 only: it doubles the host footprint)
+    #   e2e_generated : ddb_generate_solve_label_host -- the path the north star describes: Philox instances drawn inside
+    #                   the solver kernel, labels / status / objective / x / pivots back to host arrays; D2H only
     Be = min(args.e2e_batch, B)
+    e2e_steps = max(2, min(args.steps, args.e2e_steps))
     hA = torch.empty(Be, M, N_VARS, dtype=torch.float64, pin_memory=True)
     hb = torch.empty(Be, M, dtype=torch.float64, pin_memory=True)
     hc = torch.empty(Be, N_VARS, dtype=torch.float64, pin_memory=True)
     hA.copy_(A[:Be]); hb.copy_(b[:Be]); hc.copy_(c[:Be])
     torch.cuda.synchronize()
-    hout = solver.SolveResult(
-        status=torch.empty(Be, dtype=torch.int32).pin_memory().numpy(), x=torch.empty(Be, N_VARS, dtype=torch.float64).pin_memory().numpy(),
-        obj=torch.empty(Be, dtype=torch.float64).pin_memory().numpy(), labels=torch.empty(Be, M, dtype=torch.uint8).pin_memory().numpy(),
-        n_active=torch.empty(Be, dtype=torch.int32).pin_memory().numpy(), pivots=torch.empty(Be, 4, dtype=torch.int32).pin_memory().numpy(),
-        ties=torch.empty(Be, dtype=torch.int32).pin_memory().numpy(), violations=torch.empty(Be, dtype=torch.int32).pin_memory().numpy())
+    hout = solver._host_outputs(Be, M, N_VARS, pinned=True)
     nA, nb_, nc = hA.numpy(), hb.numpy(), hc.numpy()
-    solver.solve_label_host(nA, nb_, nc, device=local, out=hout)          # warm-up (allocates the staging slots)
-    if world > 1:
-        dist.barrier()
-    e2e_steps = max(2, min(args.steps, 3))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        solver.solve_label_host(nA, nb_, nc, device=local, out=hout)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * Be * e2e_steps / float(te.item())
+
+    def time_host_call(fn):
+        fn()                                                  # warm-up (allocates device slots / staging)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()                                              # returns when the results are in the host arrays
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return world * Be * e2e_steps / float(te.item())
+
+    e2e_value = time_host_call(lambda: solver.solve_label_host(nA, nb_, nc, device=local, out=hout))
     h2d = Be * (M * N_VARS + M + N_VARS) * 8
     d2h = Be * (4 + N_VARS * 8 + 8 + M + 4 + 16 + 4 + 4)
+    e2e_generated = {'value': time_host_call(lambda: solver.generate_solve_label_host(key, first, Be, M, N_VARS, device=local, out=hout)),
+                     'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': d2h, 'lps_per_step': Be, 'steps': e2e_steps,
+                     'api': 'ddb_generate_solve_label_host (instances drawn inside the solver kernel; pinned host outputs)'}
+    e2e_pageable = None
+    if world == 1 and not args.no_pageable:
+        pgA, pgb, pgc = np.array(nA), np.array(nb_), np.array(nc)       # plain numpy: pageable
+        pout = solver._host_outputs(Be, M, N_VARS, pinned=False)
+        e2e_pageable = {'value': time_host_call(lambda: solver.solve_label_host(pgA, pgb, pgc, device=local, out=pout)),
+                        'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h, 'lps_per_step': Be, 'steps': e2e_steps,
+                        'api': 'ddb_solve_label_host (pageable numpy inputs and outputs, staged through the library\'s pinned ring)'}
+        same = all((pout[k_] == hout[k_]).all() for k_ in ('status', 'labels', 'pivots'))
+        e2e_pageable['results_equal_pinned_call'] = bool(same)
+        del pgA, pgb, pgc
+
+    # ---- BASELINE.json configs[1] at its stated size: 1 000 000 LPs of (200,100), generated + solved + labelled by ONE call
+    # of the fused entry point (sharded over the ranks by global instance index; outputs stay on the device) ----------
+    config2_full = None
+    if not args.no_config2:
+        tot = 1000000
+        lo = tot * rank // world
+        cnt = tot * (rank + 1) // world - lo
+        big = solver._alloc_outputs(cnt, M, N_VARS, dev)
+        solver.generate_solve_label(key + 1, lo, min(cnt, 4096), M, N_VARS, device=local, out=None)      # warm-up of the fused kernel
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        solver.generate_solve_label(key + 1, lo, cnt, M, N_VARS, device=local, out=big)
+        c1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([c0.elapsed_time(c1) * 1e-3], dtype=torch.float64, device=dev)
+        counts = torch.stack([(big['status'] == 2).sum(), (big['status'] == 5).sum(), ((big['status'] != 2) & (big['status'] != 5)).sum(),
+                              big['labels'].sum(dtype=torch.int64), (big['ties'] * (big['status'] == 2)).sum()]).to(torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(counts)
+        config2_full = {'instances': tot, 'calls_per_rank': 1, 'seconds': float(tt.item()), 'lps_per_sec': tot / float(tt.item()),
+                        'optimal': int(counts[0].item()), 'unbounded': int(counts[1].item()), 'other_status': int(counts[2].item()),
+                        'labels_set': int(counts[3].item()), 'ties_reported': int(counts[4].item()),
+                        'api': 'ddb_generate_solve_label_dev (in-kernel Philox generation, counter = global instance index)'}
+        del big
+
+    # ---- BASELINE.json configs[2] (m/n x density sweep, cells dealt to the ranks) and configs[4] (data-parallel classifier
+    # training fed by on-GPU generation, NCCL gradient all-reduce) so that the driver observes them ----------------------
+    config3 = config5 = None
+    if not args.no_extras:
+        from deep_dantzig_b200 import phase_transitions
+        from deep_dantzig_b200.ml.models.s2v import Model as _Model
+        from deep_dantzig_b200.ml import train as _train
+        phase_transitions.sweep_ratio_density(per_cell=512, device=local)                 # warm-up (all shapes' kernels)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        cells = phase_transitions.sweep_ratio_density(per_cell=args.sweep_per_cell, device=local)
+        torch.cuda.synchronize()
+        ts = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        ninst = sum(v['instances'] for v in cells.values())
+        config3 = {'cells': len(cells), 'instances': ninst, 'seconds': float(ts.item()), 'lps_per_sec': ninst / float(ts.item()),
+                   'fraction_optimal': {'m/n=%g,density=%g' % k_: round(v['optimal'] / max(v['instances'], 1), 4) for k_, v in cells.items()},
+                   'mean_pivots': {'m/n=%g,density=%g' % k_: round(v['mean_pivots'], 1) for k_, v in cells.items()}}
+        torch.manual_seed(0)
+        tmodel = _Model('bipartite', 40, 3, on_cuda=True, verbose_init=False)
+        opt = torch.optim.SGD(tmodel.parameters(), lr=1e-6 / world, momentum=0.9)      # sum-reduced criterion (benchmark.py:75): step per instance constant
+        _train.train_on_device_stream(tmodel, opt, M, N_VARS, 4, 1024, key=key + 2, weight=(0.25, 0.75))      # warm-up
+        r5 = _train.train_on_device_stream(tmodel, opt, M, N_VARS, 40, 1024, key=key + 3, weight=(0.25, 0.75))
+        flat = torch.cat([q.detach().reshape(-1) for q in tmodel.parameters()])
+        in_sync = True
+        if world > 1:
+            lo_, hi_ = flat.clone(), flat.clone()
+            dist.all_reduce(lo_, op=dist.ReduceOp.MIN); dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+            in_sync = bool((lo_ == hi_).all().item())
+        config5 = {'steps': 40, 'lps_per_rank_per_step': 1024, 'lps_per_sec': r5['lps_per_sec'], 'seconds': r5['seconds'],
+                   'loss_first': float(r5['loss'][0]), 'loss_last': float(r5['loss'][-1]), 'replicas_in_sync': in_sync,
+                   'collective': 'one flat NCCL all-reduce of gradient + loss per step' if world > 1 else 'none (1 rank)'}
 
     # ---- second half of the hot path: batched classifier forward (and the training step's loss + gradient) over the
     # same resident instances, reference benchmark model (bipartite, p = 40, T = 3: src/benchmark.py:166-167) ---------
@@ -363,15 +463,12 @@ def run_ours(args):
     flop = 2.0 * (N_VARS + 1) * (piv[:, 0] * N_VARS + did_gemm * (M - N_VARS) * N_VARS
                                  + (piv[:, 1] + piv[:, 2]) * (M - N_VARS))
     onchip = {'fp64_flop_per_launch': float(flop.sum()), 'achieved_tflops': float(flop.sum()) / kern_s / 1e12,
-              'tableau_bytes_per_launch': float(flop.sum()) * 8.0, 'achieved_tableau_tbs': float(flop.sum()) * 8.0 / kern_s / 1e12,
               'mean_pivots': {'crash': float(piv[:, 0].mean()), 'phase1': float(piv[:, 1].mean()), 'phase2': float(piv[:, 2].mean())}}
     pk = _onchip_peaks()
     if pk:
         onchip['fp64_peak_tflops'] = pk.get('fp64_tflops'); onchip['smem_peak_tbs'] = pk.get('smem_tbs')
         if pk.get('fp64_tflops'):
             onchip['frac_fp64'] = onchip['achieved_tflops'] / pk['fp64_tflops']
-        if pk.get('smem_tbs'):
-            onchip['frac_smem'] = onchip['achieved_tableau_tbs'] / pk['smem_tbs']
 
     # ---- cpu_baseline + label match on a bounded sample of the same batch ------------------------------------
     cpu = None
@@ -395,17 +492,34 @@ def run_ours(args):
                          % (count, cores, dt)}
         glab = out['labels'][:count].cpu().numpy(); gst = st[:count]
         cst = np.array([r[0] for r in flat]); clab = np.array([r[1] for r in flat], dtype=np.uint8)
+        # checker (untimed): labels of the certified extended-precision vertex of HiGHS' active set -- HiGHS' raw x is only
+        # good to its own 1e-7 tolerance, which is the size of the reference's label threshold
+        pool = mp.get_context('fork').Pool(cores)
+        try:
+            parts = [p_ for p_ in np.array_split(np.arange(count), cores * 4) if len(p_)]
+            pol = pool.map(_polish_worker, [(sA[p_], sb[p_], sc_[p_], [flat[i][2] for i in p_]) for p_ in parts])
+        finally:
+            pool.close(); pool.join()
+        pol = [r for part in pol for r in part]
+        plab = np.array([r[1] for r in pol], dtype=np.uint8); pcert = np.array([r[0] for r in pol])
         same_status = ((gst == 2) == (cst == 2))
-        same_labels = (glab == clab).all(axis=1)
+        opt_ = cst == 2
+        same_raw = (glab == clab).all(axis=1)
+        same_pol = (glab == np.where(pcert[:, None], plab, clab)).all(axis=1)
         match = {'instances': int(count), 'status_match_pct': 100.0 * same_status.mean(),
-                 'label_match_pct': 100.0 * (same_status & same_labels).mean(),
-                 'ties_reported': int(out['ties'][:count].sum().item())}
+                 'label_match_pct': 100.0 * (same_status & same_pol).mean(),
+                 'label_match_pct_vs_raw_highs_x': 100.0 * (same_status & same_raw).mean(),
+                 'oracle_ties': int((opt_ & (plab != clab).any(axis=1) & pcert).sum()),
+                 'oracle_uncertified': int((opt_ & ~pcert).sum()),
+                 'ties_reported': int(out['ties'][:count].sum().item()),
+                 'note': 'oracle = HiGHS dual simplex, then the certified extended-precision vertex of its active set (oracle/randomlp.py: '
+                         'polish_vertex); oracle_ties = instances where HiGHS\' raw x would have been labelled differently'}
 
     line = {
         'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'random dense LP m=200 n=100 fp64 (BASELINE.json configs[1] shape), %d LPs/GPU/step, Philox instances resident in HBM' % B,
+        'config': {'workload': WORKLOAD, 'sample': '%d LPs/GPU/step, Philox instances resident in HBM' % B,
                    'lps_per_gpu_per_step': B, 'l2_policy': 'inputs (%.1f GB per step) exceed the 126 MB L2' % (B * alg_bytes_per_lp / 1e9),
                    'parallelism': 'instances sharded across %d GPU(s), no collective on the solve path; label/status gather to rank 0 per step' % world,
                    'fraction_optimal': float((st == 2).mean()), 'fraction_unbounded': float((st == 5).mean()),
@@ -415,6 +529,8 @@ def run_ours(args):
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                 'lps_per_step': Be, 'steps': e2e_steps, 'api': 'ddb_solve_label_host (pinned host buffers)',
                 'rank0_numa_node': numa_node},
+        'e2e_pageable': e2e_pageable, 'e2e_generated': e2e_generated, 'config2_full': config2_full,
+        'config3_sweep': config3, 'config5_dp_training': config5,
         'gpu_launches': int(launches), 'kernel_ms_per_step': statistics.mean(kern_ms), 'clocks': clocks,
     }
     emit(line)
@@ -452,6 +568,11 @@ def main():
     ap.add_argument('--e2e-batch', type=int, default=32768, help='LPs per end-to-end call (host buffers)')
     ap.add_argument('--cpu-sample', type=int, default=0)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
+    ap.add_argument('--e2e-steps', type=int, default=10, help='timed calls of every end-to-end figure')
+    ap.add_argument('--no-pageable', action='store_true', help='skip the pageable-input end-to-end figure')
+    ap.add_argument('--no-config2', action='store_true', help='skip the 1 000 000-LP run of BASELINE.json configs[1]')
+    ap.add_argument('--no-extras', action='store_true', help='skip the configs[2] sweep and configs[4] training records')
+    ap.add_argument('--sweep-per-cell', type=int, default=4096, help='instances per (m/n, density) cell of the sweep record')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours' and not args.no_cpu:
         pass   # the driver may ask for fewer; the timing rules ask for >= 3 and the default honours that

@@ -35,6 +35,7 @@ SIGNATURES = {
     'ddb_device_info': (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
     'ddb_solve_plan': (C.c_int, [_vp, C.c_int, C.c_int]),
     'ddb_set_solve_plan': (C.c_int, [_vp, C.c_int]),
+    'ddb_set_fused_mode': (C.c_int, [_vp, C.c_int]),
     'ddb_generate_dev': (C.c_int, [_vp, _u64, _i64, _i64, C.c_int, C.c_int, _f64, _vp, _vp, _vp, _vp, _vp]),
     'ddb_solve_label_dev': (C.c_int, [_vp, _i64, C.c_int, C.c_int, _vp, _vp, _vp, _f64, _vp,
                                       _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -115,6 +116,10 @@ class Context(object):
 
     def set_solve_plan(self, plan):
         check(self.lib.ddb_set_solve_plan(self.handle, int(plan)), 'ddb_set_solve_plan')
+
+    def set_fused_mode(self, mode):
+        """0 automatic, 1 in-kernel instance generation, 2 generator kernel + solver kernel."""
+        check(self.lib.ddb_set_fused_mode(self.handle, int(mode)), 'ddb_set_fused_mode')
 
     def close(self):
         if self.handle:

@@ -9,7 +9,7 @@
 #include <vector>
 
 #include "../../include/ddb200.h"
-#include "common.cuh"
+#include "philox.cuh"
 
 namespace ddb {
 size_t generic_smem_bytes(int m, int n, bool smem_tab);
@@ -132,6 +132,7 @@ struct ddb_ctx {
     DevBuf s2vflag;            // classifier: per-instance "has a zero coefficient" flags of the dense bipartite kernel
     Slot slots[kSlots];
     int forced_plan = -1;
+    int fused_mode = 0;        // 0 automatic (the measured-faster path), 1 in-kernel generation, 2 generator kernel + solver kernel
     int64_t launches = 0;
 };
 
@@ -275,6 +276,13 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
     return plan;
 }
 
+extern "C" int ddb_set_fused_mode(ddb_ctx* ctx, int mode) {
+    if (!ctx) return fail(DDB_EINVAL, "ddb_set_fused_mode: ctx is NULL");
+    if (mode < 0 || mode > 2) return fail(DDB_EINVAL, "ddb_set_fused_mode: mode %d", mode);
+    ctx->fused_mode = mode;
+    return DDB_OK;
+}
+
 extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
     if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
     if (plan < -1 || plan > 5) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
@@ -408,7 +416,7 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         const size_t fneed = generic_scratch_bytes(ctx, m, n, fplan, B);
         if (fneed > need) need = fneed;
         const size_t need_d = (which == 1) ? ddb::rowreg_d_scratch_bytes(m, n, grid) : 0;
-        const size_t need_slab = (gen && !A) ? (size_t)(grid > fgrid ? grid : fgrid) * per_lp : 0;
+        const size_t need_slab = (gen && !A) ? (size_t)(grid > fgrid ? grid : fgrid) * ddb::slab_doubles(m, n) * sizeof(double) : 0;
         if ((rc = scratch_acquire(ctx, st, need, need_d, need_slab))) return rc;
         a.gtab = (double*)ctx->scratch.p;
         a.dscr = (double*)ctx->dscr.p;
@@ -484,14 +492,15 @@ static int copy_threads() {
         int t = e ? atoi(e) : 0;
         if (t <= 0) {
             const unsigned hc = std::thread::hardware_concurrency();
-            t = hc >= 16 ? 8 : (hc >= 4 ? (int)hc / 2 : 1);
+            t = hc >= 4 ? (int)hc : 1;
+            if (t > 16) t = 16;
         }
         return t > 32 ? 32 : t;
     }();
     return v;
 }
 
-// memcpy split over a few threads: one core moves ~10 GB/s, PCIe 5 x16 wants ~55
+// memcpy split over the host cores (at most 16): one core moves ~5-10 GB/s, PCIe 5 x16 wants ~55
 static void parallel_memcpy(void* dst, const void* src, size_t bytes) {
     const int nt = copy_threads();
     if (nt <= 1 || bytes < (size_t)(8u << 20)) {
@@ -656,14 +665,21 @@ static int fused_launch(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int6
                         int32_t* pivots, int32_t* ties, int32_t* violations, double* A_out, double* b_out, double* c_out,
                         cudaStream_t st) {
     const bool keep = A_out && b_out && c_out;
-    // TRUE FUSION (even n, shapes of the row-per-thread kernel): ONE launch; every solver CTA draws its instance itself
-    // (Philox, counter = global instance index) into a per-CTA slab that lives in L2 -- A never travels through HBM and no
-    // generator kernel runs.  DDB_FUSED_INKERNEL=0 forces the two-kernel fallback below (A/B measurements).
-    static const bool inkernel = [] { const char* e = getenv("DDB_FUSED_INKERNEL"); return !(e && e[0] == '0'); }();
+    // IN-KERNEL GENERATION (even n, shapes of the row-per-thread kernel): ONE launch; every solver CTA draws its instance
+    // itself (Philox, counter = global instance index) into a per-CTA slab that lives in L2 -- A never travels through HBM
+    // and no generator kernel runs.  Measured on B200 at (200,100), 262 144 instances: 403 k LP/s, against 430 k LP/s for
+    // the generator kernel + solver kernel pipeline below (512 MB chunks): the solver kernel is latency-bound at ~11
+    // warp-cycles per issued instruction, so the generator's instructions cost more inside it (+14 %) than in a kernel of
+    // their own at full occupancy (+8.5 %), and the HBM round trip of A (2 x 163 KB per LP = 2 % of the HBM bandwidth) is
+    // cheap.  So automatic mode takes the two-kernel pipeline; ddb_set_fused_mode(ctx, 1) or DDB_FUSED_INKERNEL=1 selects the
+    // in-kernel generator (same bits, same results -- tests/test_gpu_solve.py checks both).
+    static const int env_mode = [] { const char* e = getenv("DDB_FUSED_INKERNEL"); return e ? (e[0] == '0' ? 2 : 1) : 0; }();
+    const int mode = ctx->fused_mode ? ctx->fused_mode : env_mode;
+    const bool inkernel = (mode == 1);
     const int plan = ddb_solve_plan(ctx, m, n);
     if (plan < 0) return plan;
     if (inkernel && plan == 0 && ctx->forced_plan < 0 && ddb::rowreg_gen_supported(m, n) &&
-        (!keep || (reinterpret_cast<uintptr_t>(A_out) & 15) == 0)) {
+        (!keep || ((reinterpret_cast<uintptr_t>(A_out) | reinterpret_cast<uintptr_t>(c_out)) & 15) == 0)) {
         GenSpec g{key, first_instance, density};
         return solve_launch(ctx, B, m, n, keep ? A_out : nullptr, keep ? b_out : nullptr, keep ? c_out : nullptr, threshold,
                             nullptr, status, x, obj, labels, n_active, pivots, ties, violations, &g, st);

@@ -141,7 +141,7 @@ __host__ __device__ inline RowLayout make_row_layout(int m, int n, int NC, int T
     L.ring = off;
     if (TS > 0) off += rr_align((size_t)kRingSlots * kRingRows * PD * 8);
     if (gen) {
-        const size_t need = rr_align(((size_t)kGenTileRows * n + 2 * (size_t)((n + 1) & ~1)) * 8);
+        const size_t need = rr_align(gen_smem_doubles(m, n) * 8);
         if (off < need) off = need;
     }
     L.bars = off;       off += rr_align((size_t)2 * kRingSlots * 8);
@@ -378,15 +378,12 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
         // ---- stage 0: crash order ---------------------------------------------------------------------------
         if constexpr (GEN) {
             // draw the instance here: into the caller's arrays when asked for, else into this CTA's slab (L2-resident)
-            const size_t per = (size_t)m * n + m + n;
-            double* Aw = a.A ? const_cast<double*>(a.A) + (size_t)lp * m * n : a.slab + (size_t)blockIdx.x * per;
-            double* bw = a.A ? const_cast<double*>(a.b) + (size_t)lp * m : a.slab + (size_t)blockIdx.x * per + (size_t)m * n;
-            double* cw = a.A ? const_cast<double*>(a.c) + (size_t)lp * n : a.slab + (size_t)blockIdx.x * per + (size_t)m * n + m;
-            double* tile = reinterpret_cast<double*>(smem_raw);
-            double* x0s = tile + (size_t)kGenTileRows * n;
-            double* cs = x0s + ((n + 1) & ~1);
-            generate_instance_cta((uint64_t)a.gen_key, (uint64_t)(a.gen_first + lp), m, n, a.gen_density, Aw, bw, cw, nullptr,
-                                  tile, x0s, cs, gbuf, gnn);
+            double* slab = a.slab + (size_t)blockIdx.x * slab_doubles(m, n);
+            double* Aw = a.A ? const_cast<double*>(a.A) + (size_t)lp * m * n : slab;
+            double* bw = a.A ? const_cast<double*>(a.b) + (size_t)lp * m : slab + slab_b_offset(m, n);
+            double* cw = a.A ? const_cast<double*>(a.c) + (size_t)lp * n : slab + slab_c_offset(m, n);
+            generate_instance_cta<NC * 1000 + TS * 10 + W>((uint64_t)a.gen_key, (uint64_t)(a.gen_first + lp), m, n, a.gen_density, Aw, bw, cw, nullptr,
+                                  reinterpret_cast<double*>(smem_raw), gbuf, gnn);
             Ag = Aw; bg = bw; cg = cw;
         } else {
             Ag = a.A + (size_t)lp * m * n;

@@ -341,10 +341,10 @@ __global__ void __launch_bounds__(NTMAX, 1) simplex_generic_kernel(SolveArgs a, 
         if (a.gen) {
             // fused generate -> solve -> label: an instance the row-per-thread kernel handed over exists nowhere unless the
             // caller asked for A -- draw it again (same counters, same bits) into this CTA's slab
-            const size_t per = (size_t)m * n + m + n;
-            double* Aw = a.A ? const_cast<double*>(Ag) : a.slab + (size_t)blockIdx.x * per;
-            double* bw = a.A ? const_cast<double*>(bg) : Aw + (size_t)m * n;
-            double* cw = a.A ? const_cast<double*>(cg) : Aw + (size_t)m * n + m;
+            double* slab = a.slab + (size_t)blockIdx.x * slab_doubles(m, n);
+            double* Aw = a.A ? const_cast<double*>(Ag) : slab;
+            double* bw = a.A ? const_cast<double*>(bg) : slab + slab_b_offset(m, n);
+            double* cw = a.A ? const_cast<double*>(cg) : slab + slab_c_offset(m, n);
             generate_instance_cta_notile((uint64_t)a.gen_key, (uint64_t)(a.gen_first + lp), m, n, a.gen_density, Aw, bw, cw, xbuf);
             Ag = Aw; bg = bw; cg = cw;
             fence_proxy_async_all();       // generic-proxy stores of the slab before the bulk-TMA staging below reads it

@@ -103,7 +103,7 @@ int ddb_solve_label_dev(ddb_ctx *ctx, int64_t B, int m, int n,
 
 /* Same contract, HOST buffers; H2D / D2H copies are done inside, in chunks of ~192 MB with three chunks in flight.
  * Page-locked caller memory (cudaHostAlloc / cudaHostRegister) is DMA'd in place.  PAGEABLE caller memory (a plain numpy
- * array, malloc) is first copied by a few host threads (DDB_COPY_THREADS, default 8) into the context's pinned staging
+ * array, malloc) is first copied by the host's cores (DDB_COPY_THREADS, default min(cores, 16)) into the context's pinned staging
  * ring and DMA'd from there, and results come back through pinned staging the same way -- so the copies of one chunk
  * overlap the solve of another for any caller, not only for one that pinned its buffers. */
 int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
@@ -114,12 +114,16 @@ int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
 
 /*
  * (3) FUSED GENERATE -> SOLVE -> LABEL -- the whole loop RandomLPDataset._generate_problems -> create_lp_problem
- * (src/data/randomlp_dataset.py:58-63, 65-128) for instances first_instance..+B of stream `key` in ONE kernel launch: the
- * thread block that solves instance i draws it first (same counters and bits as (1)), into a per-block slab that stays in
- * L2, so A never travels through HBM unless the caller asks for it.  Same outputs as (2).
- * A_out/b_out/c_out (device; all three or none) receive the instances when the caller wants them.
- * Odd n and shapes outside the row-per-thread kernel fall back to (1) into context scratch followed by (2), chunk by chunk.
+ * (src/data/randomlp_dataset.py:58-63, 65-128) for instances first_instance..+B of stream `key`; the caller never
+ * materialises A, b, c.  Same outputs as (2).  Two implementations, same bits and same results:
+ *   mode 2 (automatic choice, the measured-faster one): generator kernel (1) into context scratch, chunk by chunk, chunk
+ *          i + 1 generated on a side stream while chunk i is solved;
+ *   mode 1: ONE kernel launch -- the thread block that solves instance i draws it first into a per-block slab that stays
+ *          in L2, so A never travels through HBM (even n, shapes of the row-per-thread kernel).
+ * ddb_set_fused_mode(ctx, 0 | 1 | 2) selects (0 = automatic).  A_out/b_out/c_out (device; all three or none) receive the
+ * instances when the caller wants them.
  */
+int ddb_set_fused_mode(ddb_ctx *ctx, int mode);
 int ddb_generate_solve_label_dev(ddb_ctx *ctx, uint64_t key, int64_t first_instance, int64_t B, int m, int n,
                                  double density, double threshold,
                                  int32_t *status, double *x, double *obj, uint8_t *labels,

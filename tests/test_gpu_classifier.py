@@ -268,3 +268,58 @@ def test_dense_streaming_kernel_and_flagged_instances(cuda_device, m, n, p, T):
     with torch.no_grad():
         lpt = model.forward_batch_torch(A, b, c).cpu().numpy()
     assert _close(lp, lpt)
+
+
+@pytest.mark.parametrize('graph', ['bipartite', 'complete'])
+def test_training_trajectory_matches_the_reference_loop(cuda_device, golden_dir, graph):
+    """North-star bar "unchanged classifier accuracy": the mirror, trained through ``train_net`` on the GPU from the same
+    initial parameters on the same BASELINE.json configs[0] data in the same order with the reference's hyper-parameters
+    (src/run.py:58-72), lands on the trajectory of the UNMODIFIED reference model under the reference's own loop
+    (src/ml/train.py:49-71, criterion src/benchmark.py:70-77) -- tests/golden/train_trajectory_*.npz, made by
+    tests/golden/make_train_golden.py from /root/reference/src.  Per epoch: losses within 1e-3 relative, recall-1 threshold
+    within 1e-4, confusion counts identical up to the sample that sits exactly on the threshold."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml import train as tr
+    from oracle import randomlp as orl
+    g = np.load(os.path.join(golden_dir, 'train_trajectory_%s.npz' % graph))
+    m, n, p, T, epochs, batch, ntrain, ntest = [int(v) for v in g['dims']]
+    lr, momentum, wd = [float(v) for v in g['hyper']]
+    cfg1 = np.load(os.path.join(golden_dir, 'randomlp_config1.npz'))
+    assert list(cfg1['seeds'][:ntrain + ntest]) == list(g['seeds'])
+    labels = np.unpackbits(cfg1['labels_packed'], axis=1)[:ntrain + ntest, :m].astype(np.int64)
+    inst = [orl.generate_instance(m, n, int(s)) for s in g['seeds']]
+
+    def loader(lo, hi):
+        out = []
+        for q in range(lo, hi, batch):
+            e = min(q + batch, hi)
+            out.append({'A': torch.from_numpy(np.stack([inst[i][0] for i in range(q, e)])),
+                        'b': torch.from_numpy(np.stack([inst[i][1] for i in range(q, e)])),
+                        'c': torch.from_numpy(np.stack([inst[i][2] for i in range(q, e)])),
+                        'y': torch.from_numpy(labels[q:e])})
+        return out
+    model = Model(graph, p, T, on_cuda=True, verbose_init=False)
+    with torch.no_grad():
+        for k, v in model.named_parameters():
+            v.copy_(torch.from_numpy(g['init_' + k]).cuda())
+    crit = torch.nn.NLLLoss(weight=torch.from_numpy(g['weight']).cuda(), reduction='sum')
+    opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, weight_decay=wd)
+    hist = tr.train_net(model, crit, opt, loader(0, ntrain), loader(ntrain, ntrain + ntest), epochs, batch, cuda=True, verbose=False)
+    ref = g['history']            # [epoch][running, thr, train(loss,tp,fp,tn,fn), test(loss,tp,fp,tn,fn)]
+    thr = hist.get('thresholds')
+    for ep in range(epochs):
+        for split, off in (('train', 2), ('test', 7)):
+            mt = hist[split][ep]
+            want_loss, tp, fp, tn, fn = ref[ep][off:off + 5]
+            tot = tp + fp + tn + fn
+            assert abs(mt['total_loss'] - want_loss) <= 1e-3 * abs(want_loss), (graph, ep, split, mt['total_loss'], want_loss)
+            # accuracy / recall / pred_pos are ratios of the confusion counts: one sample may sit exactly on the threshold
+            assert abs(mt['accuracy'] * tot - (tp + tn)) <= 1.5, (graph, ep, split)
+            assert abs(mt['recall'] * (tp + fn) - tp) <= 1.5, (graph, ep, split)
+            assert abs(mt['pred_pos'] * tot - (tp + fp)) <= 1.5, (graph, ep, split)
+        if thr is not None:
+            assert abs(thr[ep] - ref[ep][1]) <= 1e-4, (graph, ep, thr[ep], ref[ep][1])
+    # and the parameters end where the reference's ended
+    for k, v in model.named_parameters():
+        want = g['final_' + k]
+        assert np.abs(v.detach().cpu().numpy() - want).max() <= 2e-3 * max(1.0, np.abs(want).max()), k

@@ -507,21 +507,28 @@ def test_fused_in_kernel_generator_is_bit_identical(cuda_device):
     """The fused call draws each instance inside the solver CTA.  Same (key, index) -> the same instance bits as the
     generator entry point, and -- same kernel arithmetic on the same bits -- the same results bit for bit as solving the
     materialised instances; chunk- and rank-independent (first_instance offsets)."""
-    from deep_dantzig_b200 import solver
-    for (m, n, B, dens) in [(200, 100, 700, 1.0), (50, 20, 3000, 1.0), (150, 100, 300, 0.5), (64, 32, 500, 1.0)]:
-        A, b, c = solver.generate(5150, 100, B, m, n, density=dens)
-        want = _to_np(solver.solve_label(A, b, c))
-        keep = solver.generate_solve_label(5150, 100, B, m, n, density=dens, keep_instances=True)
-        assert (keep['A'] == A).all() and (keep['b'] == b).all() and (keep['c'] == c).all()
-        lean = _to_np(solver.generate_solve_label(5150, 100, B, m, n, density=dens))
-        host = solver.generate_solve_label_host(5150, 100, B, m, n, density=dens)
-        tail = _to_np(solver.generate_solve_label(5150, 100 + B // 2, B - B // 2, m, n, density=dens))
-        for k in ('status', 'labels', 'pivots', 'n_active', 'ties', 'violations', 'x', 'obj'):
-            for name, got in (('keep', _to_np(keep)), ('lean', lean), ('host', host)):
-                eq = (got[k] == want[k]) | ((got[k] != got[k]) & (want[k] != want[k])) if k == 'obj' else (got[k] == want[k])
-                assert eq.all(), (m, n, k, name)
-            eq = (tail[k] == want[k][B // 2:]) | ((tail[k] != tail[k]) if k == 'obj' else False)
-            assert np.all(eq), (m, n, k, 'tail')
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    try:
+        for mode in (1, 2):           # 1: in-kernel generation (one launch), 2: generator kernel + solver kernel (automatic choice)
+            ctx.set_fused_mode(mode)
+            for (m, n, B, dens) in [(200, 100, 700, 1.0), (50, 20, 3000, 1.0), (150, 100, 300, 0.5), (64, 32, 500, 1.0),
+                                    (125, 100, 900, 0.1), (75, 20, 1000, 1.0)]:
+                A, b, c = solver.generate(5150, 100, B, m, n, density=dens)
+                want = _to_np(solver.solve_label(A, b, c))
+                keep = solver.generate_solve_label(5150, 100, B, m, n, density=dens, keep_instances=True)
+                assert (keep['A'] == A).all() and (keep['b'] == b).all() and (keep['c'] == c).all()
+                lean = _to_np(solver.generate_solve_label(5150, 100, B, m, n, density=dens))
+                host = solver.generate_solve_label_host(5150, 100, B, m, n, density=dens)
+                tail = _to_np(solver.generate_solve_label(5150, 100 + B // 2, B - B // 2, m, n, density=dens))
+                for k in ('status', 'labels', 'pivots', 'n_active', 'ties', 'violations', 'x', 'obj'):
+                    for name, got in (('keep', _to_np(keep)), ('lean', lean), ('host', host)):
+                        eq = (got[k] == want[k]) | ((got[k] != got[k]) & (want[k] != want[k])) if k == 'obj' else (got[k] == want[k])
+                        assert eq.all(), (mode, m, n, k, name)
+                    eq = (tail[k] == want[k][B // 2:]) | ((tail[k] != tail[k]) if k == 'obj' else False)
+                    assert np.all(eq), (mode, m, n, k, 'tail')
+    finally:
+        ctx.set_fused_mode(0)
     # odd n: the two-kernel fallback, same contract
     r = _to_np(solver.generate_solve_label(9, 0, 200, 33, 17))
     A, b, c = solver.generate(9, 0, 200, 33, 17)

@@ -31,7 +31,7 @@ int main(int argc, char** argv) {
     CK(cudaMalloc(&dbg, dbg_bytes)); CK(cudaMemset(dbg, 0, dbg_bytes));
     const size_t dbytes = ddb::rowreg_d_scratch_bytes(m, n, grid);
     CK(cudaMalloc(&dscr, dbytes ? dbytes : 16));
-    CK(cudaMalloc(&slab, (size_t)grid * ((size_t)m * n + m + n) * 8));
+    CK(cudaMalloc(&slab, (size_t)grid * ddb::slab_doubles(m, n) * 8));
     int launches = 0;
     CK(ddb::launch_generate(42, 0, B, m, n, 1.0, A, b, c, nullptr, sm, 0, &launches));
     ddb::SolveArgs a{};
