@@ -39,6 +39,9 @@ cudaError_t launch_simplex_rowreg(const SolveArgs& a, int sm_count, cudaStream_t
 bool rowreg_gen_supported(int m, int n);
 int rowreg_gen_grid(int m, int n, int sm_count);
 cudaError_t launch_simplex_rowreg_gen(const SolveArgs& a, int sm_count, cudaStream_t st);
+bool cluster_supported(int m, int n);
+size_t cluster_scratch_bytes(int m, int n, int sm_count, long long B);
+cudaError_t launch_simplex_cluster(const SolveArgs& a, int sm_count, cudaStream_t st);
 bool s2v_gram_tc_supported(int m, int n);
 size_t s2v_gram_out_floats(int m);
 cudaError_t launch_s2v_gram_tc(long long B, int m, int n, const double* A, const double* b, const double* c, float* out,
@@ -255,6 +258,8 @@ extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches :
 static int auto_plan(const ddb_ctx* ctx, int m, int n) {
     if (ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
     if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
+    static const bool no_cluster = [] { const char* e = getenv("DDB_NO_CLUSTER"); return e && e[0] == '1'; }();
+    if (!no_cluster && ddb::cluster_supported(m, n)) return 6;
     return 2;
 }
 
@@ -273,6 +278,8 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
         return fail(DDB_EUNSUPPORTED, "warp-tiled register kernel does not cover m=%d n=%d", m, n);
     if (plan == 5 && !ddb::rowpipe_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "software-pipelined row-per-thread kernel does not cover m=%d n=%d", m, n);
+    if (plan == 6 && !ddb::cluster_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "thread-block-cluster kernel does not cover m=%d n=%d", m, n);
     return plan;
 }
 
@@ -285,7 +292,7 @@ extern "C" int ddb_set_fused_mode(ddb_ctx* ctx, int mode) {
 
 extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
     if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
-    if (plan < -1 || plan > 5) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
+    if (plan < -1 || plan > 6) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
     ctx->forced_plan = plan;
     return DDB_OK;
 }
@@ -378,8 +385,9 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
                         double threshold, const uint8_t* row_mask, int32_t* status, double* x, double* obj, uint8_t* labels,
                         int32_t* n_active, int32_t* pivots, int32_t* ties, int32_t* violations, const GenSpec* gen,
                         cudaStream_t st) {
-    const int plan = ddb_solve_plan(ctx, m, n);
+    int plan = ddb_solve_plan(ctx, m, n);
     if (plan < 0) return plan;
+    if (plan == 6 && row_mask) plan = 2;       // reduced LPs (row masks) stay on the global-memory plan
 
     ddb::SolveArgs a;
     a.m = m; a.n = n; a.B = B;
@@ -434,6 +442,24 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         ctx->launches += 1;
         // fix-up pass: instances the tile could not hold / whose static crash basis was singular were flagged
         // status = -1; the generic kernel re-solves exactly those (it returns at once when none were flagged).
+        a.only_flagged = 1;
+        a.counter = ctx->counters + 3 * slot + 1;
+        rc = launch_generic(ctx, a, fplan, st);
+        if (rc) return rc;
+        return scratch_release(ctx, st);
+    }
+
+    if (plan == 6) {
+        // Thread-block-cluster kernel: the live tableau in the distributed shared memory of 1-8 CTAs, one LP per cluster.
+        // Instances it flags (singular static crash basis, ill-conditioned vertex) go to the generic kernel afterwards.
+        const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
+        size_t need = ddb::cluster_scratch_bytes(m, n, ctx->sm_count, B);
+        const size_t fneed = generic_scratch_bytes(ctx, m, n, fplan, B);
+        if (fneed > need) need = fneed;
+        if ((rc = scratch_acquire(ctx, st, need, 0, 0))) return rc;
+        a.gtab = (double*)ctx->scratch.p;
+        CUDA_TRY(ddb::launch_simplex_cluster(a, ctx->sm_count, st));
+        ctx->launches += 1;
         a.only_flagged = 1;
         a.counter = ctx->counters + 3 * slot + 1;
         rc = launch_generic(ctx, a, fplan, st);

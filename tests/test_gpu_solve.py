@@ -208,13 +208,51 @@ def test_parity_vs_oracle(cuda_device, m, n, N):
 
 
 def test_parity_large_global_tableau(cuda_device):
-    """BASELINE.json configs[3] shape (500,250): tableau does not fit in shared memory -> L2/HBM-streamed plan."""
+    """BASELINE.json configs[3] shape (500,250): the tableau does not fit one SM -> thread-block-cluster kernel (live tableau
+    in the distributed shared memory of four SMs), and the L2/HBM-streamed plan it replaces gives the same answers."""
     from deep_dantzig_b200 import solver, _lib
-    assert _lib.context(0).solve_plan(500, 250) == 2
+    ctx = _lib.context(0)
+    assert ctx.solve_plan(500, 250) == 6
     A, b, c = _numpy_batch(500, 250, [0, 1, 2, 3, 4, 5])
     r = _to_np(solver.solve_label(*_dev(A, b, c)))
     ref = oracle.solve_batch(A, b, c)
     _check_against_oracle(r, ref, A, b, c)
+    try:
+        ctx.set_solve_plan(2)
+        r2 = _to_np(solver.solve_label(*_dev(A, b, c)))
+    finally:
+        ctx.set_solve_plan(-1)
+    _check_against_oracle(r2, ref, A, b, c)
+    assert (r['status'] == r2['status']).all() and (r['labels'] == r2['labels']).all()
+
+
+@pytest.mark.parametrize('m,n,N', [(300, 150, 200), (400, 100, 150), (500, 250, 80), (260, 130, 200), (450, 200, 60), (600, 300, 24),
+                                   (301, 151, 100)])
+def test_cluster_kernel_agrees_with_the_streamed_plan(cuda_device, m, n, N):
+    """The cluster kernel (plan 6) and the global-memory plan (plan 2) implement the same algorithm on different memory:
+    same statuses, labels and pivot counts on Philox batches large enough that every cluster solves several instances;
+    x and objective within 1e-9."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    assert ctx.solve_plan(m, n) == 6
+    dA, db, dc = solver.generate(4711, 0, N, m, n)
+    try:
+        ctx.set_solve_plan(6)
+        r6 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(2)
+        r2 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    for k in ('status', 'labels', 'n_active'):
+        assert (r6[k] == r2[k]).all(), k
+    ok = r6['status'] == 2
+    assert ok.sum() > 0 or m < 2 * n
+    assert (r6['pivots'][:, 0] == r2['pivots'][:, 0]).all()
+    same_path = (r6['pivots'] == r2['pivots']).all(axis=1).mean()
+    print('(%d,%d): identical pivot counts on %.1f %% of %d instances' % (m, n, 100 * same_path, N))
+    if ok.any():
+        assert np.abs(r6['x'][ok] - r2['x'][ok]).max() <= 1e-9 * np.abs(r2['x'][ok]).max()
+        assert np.abs(r6['obj'][ok] - r2['obj'][ok]).max() <= 1e-9 * np.abs(r2['obj'][ok]).max()
 
 
 def test_plans_agree_bit_for_bit(cuda_device):
