@@ -385,9 +385,8 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
                         double threshold, const uint8_t* row_mask, int32_t* status, double* x, double* obj, uint8_t* labels,
                         int32_t* n_active, int32_t* pivots, int32_t* ties, int32_t* violations, const GenSpec* gen,
                         cudaStream_t st) {
-    int plan = ddb_solve_plan(ctx, m, n);
+    const int plan = ddb_solve_plan(ctx, m, n);
     if (plan < 0) return plan;
-    if (plan == 6 && row_mask) plan = 2;       // reduced LPs (row masks) stay on the global-memory plan
 
     ddb::SolveArgs a;
     a.m = m; a.n = n; a.B = B;

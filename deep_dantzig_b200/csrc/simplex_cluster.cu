@@ -236,6 +236,7 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kClNT, 1) simplex_c
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg_ = a.c + (size_t)lp * n;
+        const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;   // reduced LP: rows with mask 0 are left out
 
         // ---- stage 0: crash order (rows dealt to the warps of the whole cluster, scores written to every CTA) --------------
         for (int i = gwarp; i < m; i += gnw) {
@@ -248,7 +249,8 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kClNT, 1) simplex_c
             dot = warp_sum(dot);
             nn = warp_sum(nn);
             if (lane == 0) {
-                const double sc = (nn > 0.0) ? dot / sqrt(nn) : kInf * 0.5;
+                const bool excl = mask && mask[i] == 0;
+                const double sc = excl ? kInf : ((nn > 0.0) ? dot / sqrt(nn) : kInf * 0.5);
 #pragma unroll
                 for (int c = 0; c < CL; ++c) r_scores[c][i] = sc;
             }
@@ -270,8 +272,21 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kClNT, 1) simplex_c
         }
         __syncthreads();
         CL_T(0);
-        const int nN = m - n;
-        bool need_generic = (nN < 0);
+        int m_eff = m;
+        if (mask) {                                    // rows of the reduced LP (uniform over the cluster: same scores everywhere)
+            int cntm = 0;
+            for (int i = tid; i < m; i += kClNT) cntm += (scores[i] < kInf);
+            m_eff = __syncthreads_count(0);            // (barrier) ...
+            __shared__ int meff_sm;
+            if (tid == 0) meff_sm = 0;
+            __syncthreads();
+            cntm = __reduce_add_sync(FULL, cntm);
+            if (lane == 0) atomicAdd(&meff_sm, cntm);
+            __syncthreads();
+            m_eff = meff_sm;
+        }
+        const int nN = m_eff - n;
+        bool need_generic = (nN < 0) || (nN > CL * LR);
         int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
         int status = ST_OPTIMAL;
 
@@ -592,11 +607,12 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kClNT, 1) simplex_c
                     const double as = fabs(slack);
                     const int active = as <= a.thr;
                     const int nonbasic = (__ldcg(flagg + i) == 0);
+                    const bool excl = mask && mask[i] == 0;
                     lab[i] = (uint8_t)active;
                     nact += active;
-                    nties += ((as >= a.thr * 0.1 && as <= a.thr * 10.0) || (active != nonbasic)) ? 1 : 0;
+                    nties += ((as >= a.thr * 0.1 && as <= a.thr * 10.0) || (!excl && active != nonbasic)) ? 1 : 0;
                     nviol += (slack < -a.thr);
-                    nref += (nonbasic && as > a.thr * 0.01);
+                    nref += (!excl && nonbasic && as > a.thr * 0.01);
                 }
             }
             if (rank == 0) {

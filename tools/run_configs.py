@@ -47,5 +47,22 @@ if rank == 0:
     if hist:
         t['train_loss_first_last'] = [float(hist['loss'][:5].mean()), float(hist['loss'][-5:].mean())]
     print(json.dumps(t))
+    # what the reduced solve can give independently of the classifier's quality: an IDEAL mask -- the true active rows plus 20 %
+    # random rows -- through the same reduced solve + certificate
+    full = solver.solve_label(A2, b2, c2)
+    rng = torch.Generator(device=A2.device).manual_seed(5)
+    ideal = torch.maximum(full['labels'], (torch.rand(B, m, device=A2.device, generator=rng) < 0.2).to(torch.uint8)).contiguous()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    solver.solve_label(A2, b2, c2, row_mask=ideal); torch.cuda.synchronize()
+    ev[0].record(); full = solver.solve_label(A2, b2, c2); ev[1].record()
+    ev[2].record(); red = solver.solve_label(A2, b2, c2, row_mask=ideal); ev[3].record(); torch.cuda.synchronize()
+    okf = full['status'] == 2
+    cert = (red['status'] == 2) & (red['violations'] == 0)
+    print(json.dumps({'config': 'BASELINE.json configs[3], ideal mask (true active rows + 20 % random rows) at (500,250)', 'instances': B,
+                      'rows_kept_fraction': float(ideal.float().mean()), 'full_solve_ms': ev[0].elapsed_time(ev[1]), 'reduced_solve_ms': ev[2].elapsed_time(ev[3]),
+                      'speedup': ev[0].elapsed_time(ev[1]) / ev[2].elapsed_time(ev[3]), 'full_lps': B / ev[0].elapsed_time(ev[1]) * 1e3,
+                      'reduced_lps': B / ev[2].elapsed_time(ev[3]) * 1e3, 'certified_of_optimal': int((cert & okf).sum()), 'optimal': int(okf.sum()),
+                      'labels_equal_on_certified': bool((red['labels'][cert & okf] == full['labels'][cert & okf]).all()),
+                      'mean_pivots_full': float(full['pivots'][:, 3].float().mean()), 'mean_pivots_reduced': float(red['pivots'][:, 3].float().mean())}))
 if world > 1:
     dist.destroy_process_group()
