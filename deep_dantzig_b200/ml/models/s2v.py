@@ -142,23 +142,28 @@ class Model(nn.Module):
         reading it synchronises with the device."""
         return int(self._last_grad_flag.item()) == 0
 
-    def forward_batch_torch(self, A, b, c):
-        """Differentiable batched restatement (same arithmetic, relu-sum identity, quirks B9/B10)."""
+    def forward_batch_torch(self, A, b, c, feats=None):
+        """Differentiable batched restatement (same arithmetic, relu-sum identity, quirks B9/B10).  ``feats`` carries the
+        node flags of items that are not plain random LPs (MPS / PLNN items): bipartite ->
+        (is_inequality [B,m], is_bound [B,m]); complete -> node_features [B,m] (1 for an inequality row, 0 for an equality).
+        Without it every row is a non-bound inequality, which is what the CUDA kernels assume."""
         if self.graph == 'complete':
-            scores = self._scores_complete(A, b, c)
+            scores = self._scores_complete(A, b, c, feats)
         else:
-            scores = self._scores_bipartite(A, b, c)
+            scores = self._scores_bipartite(A, b, c, feats)
         self.probs = F.softmax(scores, dim=2)
         return F.log_softmax(scores, dim=2)
 
-    def _scores_bipartite(self, A, b, c):
+    def _scores_bipartite(self, A, b, c, feats=None):
         B, m, n = A.shape
         p = self.p
         A32, rhs, cv = A.float(), b.float(), c.float()
         Ab = F.normalize(torch.cat((A32, -rhs.unsqueeze(2)), 2), p=2, dim=2)
         An = Ab[:, :, :n]
         adj = (A32 != 0).float()
-        cfe = torch.stack((torch.ones_like(rhs), -Ab[:, :, n], torch.zeros_like(rhs), torch.bmm(An, cv.unsqueeze(2)).squeeze(2)), 2)  # [B,m,4]
+        is_ineq = torch.ones_like(rhs) if feats is None else feats[0].to(rhs)
+        is_bound = torch.zeros_like(rhs) if feats is None else feats[1].to(rhs)
+        cfe = torch.stack((is_ineq, -Ab[:, :, n], is_bound, torch.bmm(An, cv.unsqueeze(2)).squeeze(2)), 2)  # [B,m,4]
         Sp, Sn = F.relu(An).sum(2), F.relu(-An).sum(2)                     # [B,m]
         Cp, Cn = F.relu(An).sum(1), F.relu(-An).sum(1)                     # [B,n]
         t4c, t4v = self.t4c[0, :, 0], self.t4v[0, :, 0]
@@ -182,9 +187,10 @@ class Model(nn.Module):
         emb = torch.cat((emb, cfe.transpose(1, 2)), 1)
         return (self.t8 @ emb).transpose(1, 2)                                                                  # [B,m,2]
 
-    def _scores_complete(self, A, b, c):
+    def _scores_complete(self, A, b, c, feats=None):
         B, m, n = A.shape
         p = self.p
+        nfeat = None if feats is None else feats.to(A.device).float()         # [B,m] node features (s2v.py:100: u1 = t0 + t1 feat)
         Ab = F.normalize(torch.cat((A.double(), b.double().unsqueeze(2)), 2), p=2, dim=2).float()
         c0 = torch.cat((c.float(), torch.zeros(B, 1, device=A.device)), 1).unsqueeze(1)
         G = torch.cat((Ab, c0), 1)                                          # [B,m+1,n+1]
@@ -199,7 +205,8 @@ class Model(nn.Module):
         scal = relu_rc @ self.t4rc                                          # [B]   (B10)
         relu_cr = F.relu(self.t4cr).unsqueeze(0) * sp.unsqueeze(1) + F.relu(-self.t4cr).unsqueeze(0) * sn.unsqueeze(1)
         u3c = relu_cr @ self.t3cr.t()                                       # [B,p]
-        base_r = (self.t0 + self.t1).unsqueeze(0) + w3p.view(1, p, 1) * Wp.unsqueeze(1) + w3n.view(1, p, 1) * Wn.unsqueeze(1) \
+        u1 = (self.t0 + self.t1).unsqueeze(0) if nfeat is None else self.t0.unsqueeze(0) + self.t1.unsqueeze(0) * nfeat.unsqueeze(1)
+        base_r = u1 + w3p.view(1, p, 1) * Wp.unsqueeze(1) + w3n.view(1, p, 1) * Wn.unsqueeze(1) \
             + scal.view(B, 1, 1)
         mu = torch.zeros(B, p, m + 1, device=A.device)
         for _ in range(self.T):
@@ -214,17 +221,31 @@ class Model(nn.Module):
     # ------------------------------------------------------------------------------------------------------------
     # reference-format single item
     # ------------------------------------------------------------------------------------------------------------
+    def _item_feats(self, item):
+        """Node flags of an item when they are not the random-LP ones (then the CUDA kernels do not apply), else None."""
+        if self.graph == 'complete':
+            nf = item.get('node_features')
+            if nf is None:
+                return None
+            nf = torch.as_tensor(np.asarray(nf)).reshape(-1).float()
+            m = nf.numel() - 1                                   # trailing entry = the cost node
+            return None if bool((nf[:m] == 1).all()) else nf[:m].reshape(1, m)
+        cf = item['c_feats']
+        cf = cf.reshape(-1, cf.shape[-1])
+        if bool((cf[:, 0] == 1).all()) and bool((cf[:, 2] == 0).all()):
+            return None
+        return (cf[:, 0].reshape(1, -1).float(), cf[:, 2].reshape(1, -1).float())
+
     def _item_to_abc(self, item):
         if self.graph == 'complete':
-            A, b, c = item['A'], item['b'], item['c']
+            lp = item['lp'] if 'lp' in item else item
+            A, b, c = [torch.as_tensor(np.asarray(lp[k])) if not torch.is_tensor(lp[k]) else lp[k] for k in ('A', 'b', 'c')]
             A = A.reshape(1, A.shape[-2], A.shape[-1])
             return A.double(), b.reshape(1, -1).double(), c.reshape(1, -1).double()
         dims = item['dims']
         m, n = int(dims['m']), int(dims['n'])
         cf = item['c_feats']
         cf = cf.reshape(-1, cf.shape[-1])
-        if not (bool((cf[:, 0] == 1).all()) and bool((cf[:, 2] == 0).all())):
-            raise NotImplementedError('equality rows / bound rows belong to the PLNN path (SURVEY.md 8(f) rank 4)')
         A = torch.zeros(m, n, dtype=torch.float64)
         idx = torch.as_tensor([[int(q) for q in pr] for pr in item['e_feats']['i']], dtype=torch.long).reshape(-1, 2)
         A[idx[:, 0], idx[:, 1]] = torch.as_tensor([float(q) for q in item['e_feats']['coeffs']], dtype=torch.float64)
@@ -237,7 +258,14 @@ class Model(nn.Module):
             raise ValueError('Graph not recognised')
         A, b, c = self._item_to_abc(item)
         dev = self.t0.device
-        logp = self.forward_batch(A.to(dev), b.to(dev), c.to(dev))
+        feats = self._item_feats(item)
+        if feats is None:
+            logp = self.forward_batch(A.to(dev), b.to(dev), c.to(dev))
+        else:
+            # MPS / PLNN items (equality rows, bound rows): the batched torch restatement with the item's node flags --
+            # library kernels; the hand-written CUDA kernels cover the random-LP flags only
+            feats = feats.to(dev) if torch.is_tensor(feats) else tuple(f.to(dev) for f in feats)
+            logp = self.forward_batch_torch(A.to(dev), b.to(dev), c.to(dev), feats)
         in_loss = [int(q) for q in item['in_loss']]
         self.probs = self.probs[0, in_loss]
         return logp[0, in_loss]

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(128, 2) k_rank1(double* out, long long* cyc, i
         }
         f = f * 0.999;
     }
+    __syncthreads();        // time the LAST warp: with a greedy-then-oldest scheduler warp 0 alone finishes early (the first
+                            // version of this benchmark read 1.58 clk per warp-DFMA per SMSP that way, above the hardware rate)
     const long long t1 = clock64();
     double s = 0;
     for (int c = 0; c < NC; ++c) s += T[c];
