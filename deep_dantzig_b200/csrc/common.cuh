@@ -118,6 +118,25 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                  : "memory");
 }
 
+// same with an L2 cache policy (createpolicy): per-CTA scratch that is rewritten by every LP should stay in L2
+__device__ __forceinline__ void tma_load_1d_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void st_global_v2_hint(double* p, double x, double y, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(x), "d"(y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_global_hint(double* p, double x, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(x), "l"(pol) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // warp argmin helpers with Bland (lowest variable index) tie-breaking
 // ---------------------------------------------------------------------------------------------------------

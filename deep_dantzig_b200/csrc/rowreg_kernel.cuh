@@ -539,6 +539,9 @@ __global__ void __launch_bounds__(W * 32, MINB) simplex_rowreg_kernel(SolveArgs 
             if (crow) {
                 const int k = pivcol[tid];
                 if constexpr (HYB) {
+                    // (an L2 evict_last policy on these stores and on the bulk copies that read them back was measured: DRAM traffic
+                    // per LP 392 -> 384 KB, throughput -1 % -- the working set of 444 resident LPs, A 71 MB + D 36 MB + parked rows
+                    // 25 MB, exceeds the 126 MB L2 either way, and DRAM runs at 2 % of its bandwidth -- so plain stores it is)
                     double* drow = Dg + (size_t)k * PD;
                     double2* d2 = reinterpret_cast<double2*>(drow);
                     const double2* o2 = reinterpret_cast<const double2*>(Ts_own);
