@@ -306,7 +306,8 @@ def test_training_trajectory_matches_the_reference_loop(cuda_device, golden_dir,
     opt = torch.optim.SGD(model.parameters(), lr=lr, momentum=momentum, weight_decay=wd)
     hist = tr.train_net(model, crit, opt, loader(0, ntrain), loader(ntrain, ntrain + ntest), epochs, batch, cuda=True, verbose=False)
     ref = g['history']            # [epoch][running, thr, train(loss,tp,fp,tn,fn), test(loss,tp,fp,tn,fn)]
-    thr = hist.get('thresholds')
+    assert set(hist) == {'train', 'test'}
+    thr = tr.train_net.last_thresholds
     for ep in range(epochs):
         for split, off in (('train', 2), ('test', 7)):
             mt = hist[split][ep]
