@@ -69,6 +69,19 @@ cudaError_t launch_s2v_metrics(long long N, const float* logp, const float* prob
                                float w0, float w1, double* out, unsigned int* minbits, int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_count, long long smem_optin, cudaStream_t st,
                                       const char** why);
+struct S2vCGradArgs {
+    long long B;
+    int m, p, T;
+    const float* gram;
+    int gram_pitch;
+    const float* params;
+    const uint8_t* labels;
+    float w0, w1;
+    float* grad;
+    double* loss;
+};
+size_t s2v_complete_grad_smem_bytes(int m, int p, int T);
+cudaError_t launch_s2v_complete_grad(const S2vCGradArgs& a, int sm_count, long long smem_optin, cudaStream_t st, const char** why);
 }  // namespace ddb
 
 static thread_local char g_err[512] = "";
@@ -931,8 +944,7 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
                                      float w0, float w1, float* grad, double* loss, int32_t* not_dense, void* stream) {
     if (!ctx || !A || !b || !c || !params || !labels || !grad || !loss || !not_dense)
         return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: NULL argument");
-    if (graph != 1)
-        return fail(DDB_EUNSUPPORTED, "ddb_s2v_loss_grad_dev: only the bipartite variant (graph 1) has a device backward");
+    if (graph != 0 && graph != 1) return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: Graph not recognised (%d)", graph);
     if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
         return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: B=%lld m=%d n=%d p=%d T=%d", (long long)B, m, n, p, T);
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -943,6 +955,30 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
     CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
     CUDA_TRY(cudaMemsetAsync(not_dense, 0, sizeof(int32_t), st));
     if (B == 0) return DDB_OK;
+    if (graph == 0) {
+        // complete variant: relu row sums of W = G G^T from the tcgen05 Gram kernel (W depends on the data only), then
+        // forward + hand-written backward on them (csrc/s2v_complete_backward.cu)
+        if (!ddb::s2v_gram_tc_supported(m, n) || (long long)ddb::s2v_complete_grad_smem_bytes(m, p, T) > ctx->smem_optin || p > 64)
+            return fail(DDB_EUNSUPPORTED, "classifier backward (complete): embeddings do not fit in shared memory (m=%d n=%d p=%d T=%d)", m, n, p, T);
+        const size_t need = (size_t)B * ddb::s2v_gram_out_floats(m) * sizeof(float);
+        if (need > ctx->gram.cap) CUDA_TRY(cudaStreamSynchronize(st));
+        int rc = ensure(ctx->gram, need);
+        if (rc) return rc;
+        CUDA_TRY(ddb::launch_s2v_gram_tc(B, m, n, A, b, c, (float*)ctx->gram.p, ctx->sm_count, st));
+        ctx->launches += 1;
+        ddb::S2vCGradArgs g;
+        g.B = B; g.m = m; g.p = p; g.T = T;
+        g.gram = (const float*)ctx->gram.p; g.gram_pitch = (int)(ddb::s2v_gram_out_floats(m) / 3);
+        g.params = params; g.labels = labels; g.w0 = w0; g.w1 = w1; g.grad = grad; g.loss = loss;
+        const char* why = "";
+        cudaError_t e = ddb::launch_s2v_complete_grad(g, ctx->sm_count, ctx->smem_optin, st, &why);
+        if (e != cudaSuccess) {
+            if (why[0]) return fail(DDB_EUNSUPPORTED, "%s (m=%d n=%d p=%d T=%d)", why, m, n, p, T);
+            return fail(DDB_ECUDA, "s2v backward launch: %s", cudaGetErrorString(e));
+        }
+        ctx->launches += 1;
+        return DDB_OK;
+    }
     ddb::S2vGradArgs a;
     a.B = B; a.m = m; a.n = n; a.p = p; a.T = T;
     a.A = A; a.b = b; a.c = c; a.params = params; a.labels = labels; a.w0 = w0; a.w1 = w1;

@@ -102,9 +102,11 @@ class Model(nn.Module):
         return logp
 
     def device_backward_supported(self, A):
-        """The hand-written backward (csrc/s2v_backward.cu) covers the reference's default model -- bipartite graph, dense
-        instances, p <= 64; everything else trains through ``forward_batch_torch`` + autograd."""
-        return self.graph == 'bipartite' and self.p <= 64 and A.is_cuda and not self.force_torch
+        """The hand-written backward covers the bipartite graph on dense instances (csrc/s2v_backward.cu, the reference's
+        default model) and the complete graph (csrc/s2v_complete_backward.cu, m + 1 <= 256), both with p <= 64; what the
+        kernels do not fit (``DdbError`` "do not fit") and sparse bipartite instances train through
+        ``forward_batch_torch`` + autograd."""
+        return self.graph in GRAPH_CODE and self.p <= 64 and A.is_cuda and not self.force_torch
 
     def loss_and_grad_batch(self, A, b, c, labels, weight):
         """One training step's loss and gradient on the device: ``ddb_s2v_loss_grad_dev``.  Replaces the reference's

@@ -69,7 +69,7 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
 
 def _device_backward_ok(model, criterion, A):
     """The device backward implements the reference's criterion (weighted NLL, summed: benchmark.py:70-75) for the
-    bipartite model on dense instances; anything else goes through autograd."""
+    bipartite model on dense instances and for the complete model; anything else goes through autograd."""
     return (hasattr(model, 'device_backward_supported') and not getattr(model, '_no_device_backward', False)
             and model.device_backward_supported(A)
             and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum'
