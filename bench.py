@@ -417,13 +417,44 @@ def run_ours(args):
         torch.cuda.synchronize()
         f_s = cev[0].elapsed_time(cev[1]) / 5 * 1e-3
         g_s = cev[2].elapsed_time(cev[3]) / 3 * 1e-3
+
+        def _time_grad(mdl, tA, tb, tc, ty, reps=3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            mdl.zero_grad(); mdl.loss_and_grad_batch(tA, tb, tc, ty, [0.25, 0.75])
+            e0.record()
+            for _ in range(reps):
+                mdl.zero_grad(); mdl.loss_and_grad_batch(tA, tb, tc, ty, [0.25, 0.75])
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps * 1e-3
+        # the other graph variant of the reference model (s2v.py:124-187) and the general-adjacency path (zero coefficients)
+        cmodel = Model('complete', 40, 3, on_cuda=True, verbose_init=False)
+        cg_s = _time_grad(cmodel, gA, gb, gc, gy)
+        with torch.no_grad():
+            cmodel.forward_batch(gA, gb, gc)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                cmodel.forward_batch(gA, gb, gc)
+            e1.record()
+            torch.cuda.synchronize()
+            cf_s = e0.elapsed_time(e1) / 3 * 1e-3
+        Bs = min(B, 1184)
+        sA, sb_, sc_ = solver.generate(key + 7, 0, Bs, M, N_VARS, density=0.5, device=local)
+        sg_s = _time_grad(model, sA, sb_, sc_, out['labels'][:Bs])
+        del sA, sb_, sc_
         cls_bytes = 8 * (M * N_VARS + M + N_VARS) + 16 * M          # fp64 instance in, log-probs + probs out
         hbm_peak_c, _ = _peaks()
         classifier = {'model': 'bipartite s2v, p=40, T=3 (reference benchmark.py:166-167)', 'instances_per_launch': B,
                       'forward_instances_per_s': B / f_s, 'forward_ms': f_s * 1e3,
                       'roofline': {'bound': 'hbm', 'achieved': cls_bytes * B / f_s / 1e9, 'peak': hbm_peak_c, 'unit': 'GB/s',
                                    'frac': cls_bytes * B / f_s / 1e9 / hbm_peak_c, 'algorithmic_bytes_per_instance': cls_bytes},
-                      'loss_grad_instances_per_s': Bg / g_s, 'loss_grad_ms': g_s * 1e3, 'loss_grad_instances_per_launch': Bg}
+                      'loss_grad_instances_per_s': Bg / g_s, 'loss_grad_ms': g_s * 1e3, 'loss_grad_instances_per_launch': Bg,
+                      'complete_graph': {'forward_instances_per_s': Bg / cf_s, 'loss_grad_instances_per_s': Bg / cg_s,
+                                         'instances_per_launch': Bg,
+                                         'kernels': 'tcgen05 Gram row sums + rounds/head (forward), + hand-written backward (loss_grad)'},
+                      'general_adjacency': {'loss_grad_instances_per_s': Bs / sg_s, 'instances_per_launch': Bs, 'density': 0.5,
+                                            'kernels': 'streaming kernel flags the instances, general-adjacency kernel adds them'}}
         if not args.no_cpu and world == 1:
             # the reference runs its model one instance at a time on the host (ml/utils.py:3-25): the oracle port, 1 core
             from oracle import classifier as oc

@@ -64,7 +64,27 @@ struct S2vGradArgs {
     float* grad;
     double* loss;
     int* error_flag;
+    int* inst_flag;
 };
+struct S2vGGradArgs {
+    long long B;
+    int m, n, p, T;
+    const double* A;
+    const double* b;
+    const double* c;
+    const float* params;
+    const uint8_t* labels;
+    float w0, w1;
+    float* grad;
+    double* loss;
+    const int* inst_flag;
+    const int* flag_count;
+    float* scratch;
+};
+size_t s2v_general_grad_smem_bytes(int m, int n, int p);
+size_t s2v_general_grad_scratch_floats(int m, int n, int p, int T);
+int s2v_general_grad_grid(long long B, int sm_count);
+cudaError_t launch_s2v_bipartite_general_grad(const S2vGGradArgs& a, int grid, long long smem_optin, cudaStream_t st, const char** why);
 cudaError_t launch_s2v_metrics(long long N, const float* logp, const float* probs, const uint8_t* labels, float thresh,
                                float w0, float w1, double* out, unsigned int* minbits, int sm_count, cudaStream_t st);
 cudaError_t launch_s2v_bipartite_grad(const S2vGradArgs& a, int npar, int sm_count, long long smem_optin, cudaStream_t st,
@@ -149,6 +169,7 @@ struct ddb_ctx {
     cudaEvent_t chunk_ev[2] = {nullptr, nullptr};
     DevBuf gram;               // classifier: per-instance Gram row sums from the tensor-core kernel
     DevBuf s2vflag;            // classifier: per-instance "has a zero coefficient" flags of the dense bipartite kernel
+    DevBuf s2vgscr;            // classifier: per-CTA scratch of the general-adjacency loss + gradient kernel
     Slot slots[kSlots];
     int forced_plan = -1;
     int fused_mode = 0;        // 0 automatic (the measured-faster path), 1 in-kernel generation, 2 generator kernel + solver kernel
@@ -245,6 +266,7 @@ extern "C" int ddb_destroy(ddb_ctx* ctx) {
     release(ctx->genb);
     release(ctx->genc);
     release(ctx->gram);
+    release(ctx->s2vgscr);
     release(ctx->s2vflag);
     if (ctx->scratch_free) cudaEventDestroy(ctx->scratch_free);
     if (ctx->gen_free) cudaEventDestroy(ctx->gen_free);
@@ -983,8 +1005,39 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
     a.B = B; a.m = m; a.n = n; a.p = p; a.T = T;
     a.A = A; a.b = b; a.c = c; a.params = params; a.labels = labels; a.w0 = w0; a.w1 = w1;
     a.grad = grad; a.loss = loss; a.error_flag = not_dense;
+    // dense instances (the reference's distribution) go through the streaming kernel, which flags every instance with a zero
+    // coefficient; the general-adjacency kernel then adds exactly those (3 us when there are none)
+    const int ggrid = ddb::s2v_general_grad_grid(B, ctx->sm_count);
+    const size_t need_flag = (size_t)(B + 1) * sizeof(int);
+    const size_t need_scr = (size_t)ggrid * ddb::s2v_general_grad_scratch_floats(m, n, p, T) * sizeof(float);
+    if (need_flag > ctx->s2vflag.cap || need_scr > ctx->s2vgscr.cap) CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = ensure(ctx->s2vflag, need_flag);
+    if (rc) return rc;
+    if ((rc = ensure(ctx->s2vgscr, need_scr))) return rc;
+    a.inst_flag = (int*)ctx->s2vflag.p;
+    CUDA_TRY(cudaMemsetAsync(a.inst_flag, 0, need_flag, st));
     const char* why = "";
-    cudaError_t e = ddb::launch_s2v_bipartite_grad(a, npar, ctx->sm_count, ctx->smem_optin, st, &why);
+    static const bool no_dense_grad = [] { const char* e = getenv("DDB_S2V_NO_DENSE"); return e && e[0] == '1'; }();
+    bool all_general = no_dense_grad;
+    if (!all_general) {
+        cudaError_t e = ddb::launch_s2v_bipartite_grad(a, npar, ctx->sm_count, ctx->smem_optin, st, &why);
+        if (e == cudaErrorInvalidValue && why[0]) {
+            all_general = true;                  // the dense kernel does not fit this shape: everything through the general kernel
+        } else if (e != cudaSuccess) {
+            return fail(DDB_ECUDA, "s2v backward launch: %s", cudaGetErrorString(e));
+        } else {
+            ctx->launches += 1;
+        }
+    }
+    if (all_general) CUDA_TRY(cudaMemsetAsync(not_dense, 1, 1, st));      // little-endian int32 1: every instance takes the general kernel
+    ddb::S2vGGradArgs g;
+    g.B = B; g.m = m; g.n = n; g.p = p; g.T = T;
+    g.A = A; g.b = b; g.c = c; g.params = params; g.labels = labels; g.w0 = w0; g.w1 = w1;
+    g.grad = grad; g.loss = loss;
+    g.inst_flag = all_general ? nullptr : a.inst_flag;
+    g.flag_count = all_general ? nullptr : a.inst_flag + B;
+    g.scratch = (float*)ctx->s2vgscr.p;
+    cudaError_t e = ddb::launch_s2v_bipartite_general_grad(g, ggrid, ctx->smem_optin, st, &why);
     if (e != cudaSuccess) {
         if (why[0]) return fail(DDB_EUNSUPPORTED, "%s (m=%d n=%d p=%d T=%d)", why, m, n, p, T);
         return fail(DDB_ECUDA, "s2v backward launch: %s", cudaGetErrorString(e));

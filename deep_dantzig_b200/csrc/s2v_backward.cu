@@ -31,6 +31,8 @@ struct S2vGradArgs {
     float* grad;               // [param_count], accumulated with atomics (zeroed by the caller)
     double* loss;              // scalar, accumulated with atomics (zeroed by the caller)
     int* error_flag;           // set to 1 when an instance is not dense (general adjacency is not handled here)
+    int* inst_flag;            // [B + 1]: inst_flag[lp] = 1 for every such instance, inst_flag[B] counts them -- the general
+                               // kernel (s2v_bipartite_general_backward.cu) then processes exactly those
 };
 
 namespace {
@@ -289,7 +291,11 @@ __global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1) s2v_bipartite_grad_ke
             for (int e = tid; e < p * NP; e += nt) mu[e] = 0.f;
         __syncthreads();
         if (*iflag) {                     // sparse instance: not handled by this kernel (uniform decision)
-            if (tid == 0) *a.error_flag = 1;
+            if (tid == 0) {
+                *a.error_flag = 1;
+                a.inst_flag[lp] = 1;
+                atomicAdd(a.inst_flag + a.B, 1);
+            }
             __syncthreads();
             continue;
         }

@@ -80,7 +80,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
 struct GramLayout {
     int RG;            // 8-row groups per plane
     int PLB;           // plane pitch in bytes
-    size_t hi, lo, stage, inv, rowacc, bar, slot, total;   // hi / lo of stage 0; stage = byte offset between the two stages
+    size_t hi, lo, stage, inv, invs, diag, rowacc, bar, slot, total;   // hi / lo of stage 0; stage = byte offset between the two stages
 };
 __host__ __device__ inline GramLayout gram_layout(int m) {
     GramLayout L;
@@ -95,18 +95,50 @@ __host__ __device__ inline GramLayout gram_layout(int m) {
     L.stage = off;
     off *= 2;                                  // second stage: produce chunk k+1 while the tensor core reads chunk k
     off = (off + 15) / 16 * 16;
-    L.inv = off;  off += (size_t)(M1 + 16) * 4;
-    off = (off + 15) / 16 * 16;
+    L.inv = off;  off += (size_t)288 * 4;      // 1 / |[a_i, b_i]| per row, 1 for the cost node, 0 beyond
+    L.invs = off; off += (size_t)288 * 4;      // the same with 0 from the cost node on: weights of the relu row sums
+    L.diag = off; off += (size_t)256 * 4;
     L.rowacc = off; off += (size_t)4 * 3 * 256 * 4;      // epilogue: per-row partial sums of the four column groups
     off = (off + 15) / 16 * 16;
-    L.bar = off;  off += 32;
+    L.bar = off;  off += 64;
     L.slot = off; off += 16;
     L.total = off;
     return L;
 }
 
-constexpr int GT = 512;                    // threads per CTA: 16 warps stream A, warps 0-3 own the accumulator rows
+constexpr int GPW = 16;                    // producer / epilogue warps
+constexpr int GPT = GPW * 32;              // ... threads
+constexpr int GT = GPT + 32;               // + one MMA-issue warp
 
+__device__ __forceinline__ void producers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(GPT) : "memory"); }
+
+// two 16-column loads of my TMEM lane in flight, one wait
+__device__ __forceinline__ void tmem_ld16x2(uint32_t t0, uint32_t t1, bool second, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(t0));
+    if (second) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+            : "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(t1));
+    } else {
+#pragma unroll
+        for (int i = 16; i < 32; ++i) r[i] = 0u;
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// WARP-SPECIALISED: warps 0 .. 15 stream A (fp64 -> tf32 hi / lo in the canonical UMMA layout, two stages) and run the
+// epilogue; warp 16 only issues the MMAs.  full[stage] (16 producer-warp arrivals) / empty[stage] (tcgen05.commit) hand
+// the stages back and forth, tfree (16 arrivals) tells the MMA warp that the accumulators of the previous instance
+// have been read.  The producers never wait for the issue of an MMA and the issuing thread never converts a number.
 template <int TMEM_COLS>
 __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -117,8 +149,12 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
     unsigned char* hi = smem_raw + L.hi;
     unsigned char* lo = smem_raw + L.lo;
     float* rowacc = reinterpret_cast<float*>(smem_raw + L.rowacc);   // [4 column groups][3: Wp, Wn, wc][256 rows]
-    float* inv = reinterpret_cast<float*>(smem_raw + L.inv);       // 1 / |[a_i, b_i]| per row (1 for the cost node)
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + L.bar);
+    float* inv = reinterpret_cast<float*>(smem_raw + L.inv);
+    float* invs = reinterpret_cast<float*>(smem_raw + L.invs);
+    float* diag = reinterpret_cast<float*>(smem_raw + L.diag);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + L.bar);   // [2]
+    uint64_t* empty = full + 2;                                       // [2]
+    uint64_t* tfree = full + 4;
     uint32_t* slot = reinterpret_cast<uint32_t*>(smem_raw + L.slot);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int rows_pl = L.RG * 8;
@@ -129,177 +165,218 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (tid == 0) {
-        mbar_init(bar, 1);
-        mbar_init(bar + 1, 1);
+        mbar_init(full, GPW);
+        mbar_init(full + 1, GPW);
+        mbar_init(empty, 1);
+        mbar_init(empty + 1, 1);
+        mbar_init(tfree, GPW);
         fence_mbar_init();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *slot;
-    uint32_t par0 = 0, par1 = 0;          // phase parity of the two stage barriers
-    bool pend0 = false, pend1 = false;    // stage has MMAs in flight that have not been waited for
 
-    // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = NN
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t hi_s = smem_u32(hi), lo_s = smem_u32(lo);
-
-    // software-pipelined producer: the global loads of chunk k + 1 are issued before chunk k is converted, stored and
-    // multiplied (RPW rows per warp and chunk, one column per lane)
-    constexpr int RPW = 256 / (GT / 32);
-    double vnext[RPW];
-    auto load_chunk = [&](long long lpq, int kc) {
-        const double* Ag = a.A + (size_t)lpq * m * n;
-        const double* bg = a.b + (size_t)lpq * m;
-        const double* cg = a.c + (size_t)lpq * n;
-        const int kabs = kc * KC + lane;
-#pragma unroll
-        for (int q = 0; q < RPW; ++q) {
-            const int r = warp + q * (GT / 32);
-            double v = 0.0;
-            if (r < m) {
-                if (kabs < n) v = __ldg(Ag + (size_t)r * n + kabs);
-                else if (kabs == n) v = __ldg(bg + r);
-            } else if (r == m) {
-                if (kabs < n) v = __ldg(cg + kabs);
-            }
-            vnext[q] = v;
-        }
-    };
-    if ((long long)blockIdx.x < a.B) load_chunk(blockIdx.x, 0);
-
-    for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
-
-        // The product runs on the UNNORMALISED rows G' = [[A | b] ; [c, 0]]: W'_ii is the squared row norm, so the
-        // normalisation of the reference (s2v.py:145) becomes a row / column scaling of the accumulators in the
-        // epilogue and A is read exactly once.
-        for (int kc = 0; kc < nkc; ++kc) {
-            const int stg = kc & 1;
-            // this chunk's values were loaded one chunk ago (vnext); start the loads of the NEXT chunk (the next
-            // instance's first one after the last) now, so that they fly during the convert / store / MMA issue below
-            double vcur[RPW];
-#pragma unroll
-            for (int q = 0; q < RPW; ++q) vcur[q] = vnext[q];
-            {
-                const bool wrap = (kc + 1 == nkc);
-                const long long lpn = wrap ? lp + gridDim.x : lp;
-                if (lpn < a.B) load_chunk(lpn, wrap ? 0 : kc + 1);
-            }
-            // the MMAs that read this stage two chunks ago must have finished before it is overwritten
-            if (stg == 0 && pend0) { mbar_wait(bar, par0); par0 ^= 1; pend0 = false; }
-            if (stg == 1 && pend1) { mbar_wait(bar + 1, par1); par1 ^= 1; pend1 = false; }
-            unsigned char* hs = hi + (size_t)stg * L.stage;
-            unsigned char* ls = lo + (size_t)stg * L.stage;
-            // ---- produce the chunk: rows of G' -> (hi, lo) tf32 in the canonical UMMA layout -------------------------------
-            const uint32_t coff = (uint32_t)(lane >> 2) * L.PLB + (lane & 3) * 4;
-#pragma unroll
-            for (int q = 0; q < RPW; ++q) {
-                const int r = warp + q * (GT / 32);
-                if (r < rows_pl) {
-                    const float g = (float)vcur[q];
-                    const uint32_t h = to_tf32(g);
-                    const uint32_t l = to_tf32(g - __uint_as_float(h));
-                    const uint32_t off = coff + (uint32_t)(r >> 3) * 128 + (r & 7) * 16;
-                    *reinterpret_cast<uint32_t*>(hs + off) = h;
-                    *reinterpret_cast<uint32_t*>(ls + off) = l;
-                }
-            }
-            fence_proxy_async();
-            __syncthreads();
-            if (tid == 0) {
+    if (warp == GPW) {
+        // ================= MMA warp: lane 0 issues, the warp stays converged on the waits =================
+        // instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = NN
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint64_t dbase = ((uint64_t)((uint32_t)L.PLB >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+        const uint32_t hi_s = smem_u32(hi), lo_s = smem_u32(lo);
+        long long g = 0;
+        int inst = 0;
+        for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x, ++inst) {
+            if (inst >= 1) mbar_wait(tfree, (uint32_t)((inst - 1) & 1));     // the previous accumulators have been read
+            for (int kc = 0; kc < nkc; ++kc, ++g) {
+                const int stg = (int)(g & 1);
+                mbar_wait(full + stg, (uint32_t)((g >> 1) & 1));
                 tc_fence_after();
-                const uint32_t hb = hi_s + (uint32_t)(stg * L.stage), lb = lo_s + (uint32_t)(stg * L.stage);
+                if (lane == 0) {
+                    const uint32_t hb = hi_s + (uint32_t)(stg * L.stage), lb = lo_s + (uint32_t)(stg * L.stage);
 #pragma unroll 1
-                for (int mt = 0; mt < MT; ++mt) {
-                    const uint32_t d = tmem_base + (uint32_t)(mt * NN);
-#pragma unroll 1
-                    for (int s = 0; s < KC / 8; ++s) {
-                        const uint32_t ko = (uint32_t)(2 * s) * L.PLB;
-                        const uint64_t a_hi = smem_desc(hb + ko + mt * 2048, L.PLB, 128);
-                        const uint64_t a_lo = smem_desc(lb + ko + mt * 2048, L.PLB, 128);
-                        const uint64_t b_hi = smem_desc(hb + ko, L.PLB, 128);
-                        const uint64_t b_lo = smem_desc(lb + ko, L.PLB, 128);
-                        umma_tf32(d, a_hi, b_hi, idesc, (kc | s) != 0);
-                        umma_tf32(d, a_hi, b_lo, idesc, 1);
-                        umma_tf32(d, a_lo, b_hi, idesc, 1);
-                    }
-                }
-                umma_commit(bar + stg);
-            }
-            if (stg == 0) pend0 = true; else pend1 = true;
-        }
-        // all MMAs of this instance have to be complete before the accumulators are read
-        if (pend0) { mbar_wait(bar, par0); par0 ^= 1; pend0 = false; }
-        if (pend1) { mbar_wait(bar + 1, par1); par1 ^= 1; pend1 = false; }
-        tc_fence_after();
-
-        // ---- epilogue (warps 0-3: thread t owns accumulator row t of each tile) ------------------------------------------
-        // pass 1: the diagonal gives the row norms
-        if (warp < 4) {
-            for (int mt = 0; mt < MT; ++mt) {
-                const int i = mt * 128 + tid;
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NN);
-                // the diagonal entries of my warp's 32 rows sit in two 16-column chunks (warp-uniform addresses:
-                // tcgen05.ld is a warp-collective)
-                const int cb = mt * 128 + warp * 32;
-                float dg = 0.f;
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const uint32_t d = tmem_base + (uint32_t)(mt * NN);
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (cb + 16 * h < NN) {
-                        float v[16];
-                        tmem_ld16(taddr + cb + 16 * h, v);
-#pragma unroll
-                        for (int q = 0; q < 16; ++q)
-                            if (lane == 16 * h + q) dg = v[q];
-                    }
-                }
-                if (i < M1) inv[i] = (i < m) ? 1.0f / fmaxf(sqrtf(dg), 1e-12f) : 1.0f;
-            }
-        }
-        __syncthreads();
-        // pass 2: W_ij = W'_ij inv_i inv_j, relu row sums.  All 16 warps: warp w reads the TMEM lanes of its quadrant
-        // (w % 4, the hardware's lane restriction) and every fourth 16-column chunk (w / 4); the four partial sums of a
-        // row meet in shared memory.
-        {
-            const int wq = warp & 3, wg = warp >> 2;
-            for (int mt = 0; mt < MT; ++mt) {
-                const int i = mt * 128 + wq * 32 + lane;
-                const float ii = (i < M1) ? inv[i] : 0.f;
-                float sp = 0.f, sn = 0.f, wl = 0.f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * NN);
-                for (int c0 = 16 * wg; c0 < NN; c0 += 64) {
-                    float v[16];
-                    tmem_ld16(taddr + c0, v);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const int j = c0 + q;
-                        if (j != i && j <= m) {
-                            const float w = v[q] * ii * inv[j];
-                            if (j < m) { sp += fmaxf(w, 0.f); sn += fmaxf(-w, 0.f); }
-                            else wl = w;
+                        for (int s = 0; s < KC / 8; ++s) {
+                            const uint32_t ko = (uint32_t)(2 * s) * L.PLB;
+                            const uint64_t a_hi = dbase | (uint64_t)(((hb + ko + mt * 2048) & 0x3FFFF) >> 4);
+                            const uint64_t a_lo = dbase | (uint64_t)(((lb + ko + mt * 2048) & 0x3FFFF) >> 4);
+                            const uint64_t b_hi = dbase | (uint64_t)(((hb + ko) & 0x3FFFF) >> 4);
+                            const uint64_t b_lo = dbase | (uint64_t)(((lb + ko) & 0x3FFFF) >> 4);
+                            umma_tf32(d, a_hi, b_hi, idesc, (kc | s) != 0);
+                            umma_tf32(d, a_hi, b_lo, idesc, 1);
+                            umma_tf32(d, a_lo, b_hi, idesc, 1);
                         }
                     }
+                    umma_commit(empty + stg);      // arrives when every MMA issued so far has finished reading / writing
                 }
-                float* ra = rowacc + (size_t)wg * 3 * 256 + (mt * 128 + wq * 32 + lane);
-                ra[0] = sp;
-                ra[256] = sn;
-                ra[512] = wl;
+                __syncwarp();
             }
         }
-        tc_fence_before();
-        __syncthreads();
-        for (int i = tid; i < M1; i += GT) {
-            float* o = a.out + (size_t)lp * 3 * a.MP;
-            // fixed summation order over the four column groups: the result does not depend on warp timing
-            o[i] = (rowacc[i] + rowacc[768 + i]) + (rowacc[1536 + i] + rowacc[2304 + i]);
-            o[a.MP + i] = (rowacc[256 + i] + rowacc[1024 + i]) + (rowacc[1792 + i] + rowacc[2560 + i]);
-            o[2 * a.MP + i] = (rowacc[512 + i] + rowacc[1280 + i]) + (rowacc[2048 + i] + rowacc[2816 + i]);
+    } else {
+        // ================= producer / epilogue warps =================
+        // software-pipelined producer: the global loads of chunk k + 1 are issued before chunk k is converted and stored
+        // (RPW rows per warp and chunk, one column per lane)
+        constexpr int RPW = 256 / GPW;
+        double vnext[RPW];
+        auto load_chunk = [&](long long lpq, int kc) {
+            const double* Ag = a.A + (size_t)lpq * m * n;
+            const double* bg = a.b + (size_t)lpq * m;
+            const double* cg = a.c + (size_t)lpq * n;
+            const int kabs = kc * KC + lane;
+#pragma unroll
+            for (int q = 0; q < RPW; ++q) {
+                const int r = warp + q * GPW;
+                double v = 0.0;
+                if (r < m) {
+                    if (kabs < n) v = __ldg(Ag + (size_t)r * n + kabs);
+                    else if (kabs == n) v = __ldg(bg + r);
+                } else if (r == m) {
+                    if (kabs < n) v = __ldg(cg + kabs);
+                }
+                vnext[q] = v;
+            }
+        };
+        if ((long long)blockIdx.x < a.B) load_chunk(blockIdx.x, 0);
+        long long g = 0;
+
+        for (long long lp = blockIdx.x; lp < a.B; lp += gridDim.x) {
+            // The product runs on the UNNORMALISED rows G' = [[A | b] ; [c, 0]]: W'_ii is the squared row norm, so the
+            // normalisation of the reference (s2v.py:145) becomes a row / column scaling of the accumulators in the
+            // epilogue and A is read exactly once.
+            for (int kc = 0; kc < nkc; ++kc, ++g) {
+                const int stg = (int)(g & 1);
+                double vcur[RPW];
+#pragma unroll
+                for (int q = 0; q < RPW; ++q) vcur[q] = vnext[q];
+                {
+                    const bool wrap = (kc + 1 == nkc);
+                    const long long lpn = wrap ? lp + gridDim.x : lp;
+                    if (lpn < a.B) load_chunk(lpn, wrap ? 0 : kc + 1);
+                }
+                // the MMAs that read this stage two chunks ago must have finished before it is overwritten
+                if (g >= 2) mbar_wait(empty + stg, (uint32_t)(((g >> 1) - 1) & 1));
+                unsigned char* hs = hi + (size_t)stg * L.stage;
+                unsigned char* ls = lo + (size_t)stg * L.stage;
+                const uint32_t coff = (uint32_t)(lane >> 2) * L.PLB + (lane & 3) * 4 + (uint32_t)(warp >> 3) * 128 + (warp & 7) * 16;
+#pragma unroll
+                for (int q = 0; q < RPW; ++q) {
+                    const int r = warp + q * GPW;
+                    if (r < rows_pl) {
+                        const float gq = (float)vcur[q];
+                        const uint32_t h = to_tf32(gq);
+                        const uint32_t l = to_tf32(gq - __uint_as_float(h));
+                        const uint32_t off = coff + (uint32_t)q * (GPW / 8) * 128;      // (r >> 3) * 128 + (r & 7) * 16
+                        *reinterpret_cast<uint32_t*>(hs + off) = h;
+                        *reinterpret_cast<uint32_t*>(ls + off) = l;
+                    }
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full + stg);
+            }
+            // all MMAs of this instance are complete when the last chunk's commit has arrived
+            {
+                const long long gl = g - 1;
+                mbar_wait(empty + (int)(gl & 1), (uint32_t)((gl >> 1) & 1));
+            }
+            tc_fence_after();
+
+            // ---- epilogue ------------------------------------------------------------------------------------------------
+            // pass 1 (warps 0-3: thread t owns accumulator row t of each tile): the diagonal gives the row norms
+            if (warp < 4) {
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int i = mt * 128 + tid;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * NN);
+                    const int cb = mt * 128 + warp * 32;       // my warp's 32 diagonal entries sit in two 16-column chunks
+                    float dg = 0.f;
+                    if (cb < NN) {
+                        float v[32];
+                        tmem_ld16x2(taddr + cb, taddr + cb + 16, cb + 16 < NN, v);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (lane == q) dg = v[q];
+                    }
+                    if (i < 256) {
+                        const float iv = (i < m) ? 1.0f / fmaxf(sqrtf(dg), 1e-12f) : (i == m ? 1.0f : 0.f);
+                        inv[i] = iv;
+                        invs[i] = (i < m) ? iv : 0.f;
+                        diag[i] = dg;
+                    }
+                }
+            }
+            for (int i = 256 + tid; i < 288; i += GPT) { inv[i] = 0.f; invs[i] = 0.f; }
+            producers_sync();
+            // pass 2: W_ij = W'_ij inv_i inv_j; relu row sums  Wp_i = inv_i sum_j inv_j relu(W'_ij),  Wn_i = Wp_i - inv_i sum_j inv_j W'_ij
+            // (inv > 0).  Warp w reads the TMEM lanes of its quadrant (w % 4, the hardware's lane restriction) and every fourth
+            // 16-column chunk (w / 4), two chunks in flight; chunks that hold my rows' diagonal or the cost column take the
+            // guarded path; the four partial sums of a row meet in shared memory.
+            {
+                const int wq = warp & 3, wg = warp >> 2;
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int i0 = mt * 128 + wq * 32, i = i0 + lane;
+                    const float ii = inv[i];
+                    float sp = 0.f, sa = 0.f, wl = 0.f;
+                    const uint32_t taddr = tmem_base + ((uint32_t)(wq * 32) << 16) + (uint32_t)(mt * NN);
+                    for (int c0 = 16 * wg; c0 < NN; c0 += 128) {
+                        float v[32];
+                        const bool second = c0 + 64 < NN;
+                        tmem_ld16x2(taddr + c0, taddr + c0 + 64, second, v);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int cc = c0 + 64 * h;
+                            if (h == 1 && !second) break;
+                            const bool special = (cc < i0 + 32 && cc + 16 > i0) || (cc <= m && cc + 16 > m);   // warp-uniform
+                            if (!special) {
+#pragma unroll
+                                for (int q4 = 0; q4 < 4; ++q4) {
+                                    const float4 w4 = *reinterpret_cast<const float4*>(invs + cc + 4 * q4);
+                                    const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                                    for (int u = 0; u < 4; ++u) {
+                                        const float x = v[16 * h + 4 * q4 + u];
+                                        sp = fmaf(ws[u], fmaxf(x, 0.f), sp);
+                                        sa = fmaf(ws[u], x, sa);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int q = 0; q < 16; ++q) {
+                                    const int j = cc + q;
+                                    const float x = v[16 * h + q];
+                                    if (j != i && j < m) {
+                                        const float wj = invs[j];
+                                        sp = fmaf(wj, fmaxf(x, 0.f), sp);
+                                        sa = fmaf(wj, x, sa);
+                                    }
+                                    if (j == m && j != i) wl = x * ii;
+                                }
+                            }
+                        }
+                    }
+                    float* ra = rowacc + (size_t)wg * 3 * 256 + i;
+                    ra[0] = sp * ii;
+                    ra[256] = (sp - sa) * ii;
+                    ra[512] = wl;
+                }
+            }
+            // the accumulators have been read: the MMA warp may start the next instance
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tfree);
+            producers_sync();
+            for (int i = tid; i < M1; i += GPT) {
+                float* o = a.out + (size_t)lp * 3 * a.MP;
+                // fixed summation order over the four column groups: the result does not depend on warp timing
+                o[i] = (rowacc[i] + rowacc[768 + i]) + (rowacc[1536 + i] + rowacc[2304 + i]);
+                o[a.MP + i] = (rowacc[256 + i] + rowacc[1024 + i]) + (rowacc[1792 + i] + rowacc[2560 + i]);
+                o[2 * a.MP + i] = (rowacc[512 + i] + rowacc[1280 + i]) + (rowacc[2048 + i] + rowacc[2816 + i]);
+            }
+            producers_sync();
         }
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
     }
 
+    tc_fence_before();
     __syncthreads();
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");

@@ -102,10 +102,10 @@ class Model(nn.Module):
         return logp
 
     def device_backward_supported(self, A):
-        """The hand-written backward covers the bipartite graph on dense instances (csrc/s2v_backward.cu, the reference's
-        default model) and the complete graph (csrc/s2v_complete_backward.cu, m + 1 <= 256), both with p <= 64; what the
-        kernels do not fit (``DdbError`` "do not fit") and sparse bipartite instances train through
-        ``forward_batch_torch`` + autograd."""
+        """The hand-written backward covers the bipartite graph -- dense instances (csrc/s2v_backward.cu, the reference's
+        default model) and instances with zero coefficients (csrc/s2v_bipartite_general_backward.cu) -- and the complete
+        graph (csrc/s2v_complete_backward.cu, m + 1 <= 256), all with p <= 64; only what the kernels do not fit
+        (``DdbError`` "do not fit") trains through ``forward_batch_torch`` + autograd."""
         return self.graph in GRAPH_CODE and self.p <= 64 and A.is_cuda and not self.force_torch
 
     def loss_and_grad_batch(self, A, b, c, labels, weight):
@@ -140,8 +140,9 @@ class Model(nn.Module):
         return loss
 
     def last_batch_was_dense(self):
-        """False if the last ``loss_and_grad_batch`` met an instance with a zero coefficient (its result is then invalid);
-        reading it synchronises with the device."""
+        """False if the last ``loss_and_grad_batch`` met an instance with a zero coefficient -- informational: such
+        instances went through the general-adjacency kernel, the result is complete either way; reading it synchronises
+        with the device."""
         return int(self._last_grad_flag.item()) == 0
 
     def forward_batch_torch(self, A, b, c, feats=None):

@@ -38,14 +38,10 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
             optimizer.zero_grad()
             loss = None
             if _device_backward_ok(model, criterion, A):
-                # hand-written loss + gradient kernel (csrc/s2v_backward.cu): one launch per batch
+                # hand-written loss + gradient kernels (csrc/s2v_backward.cu and its general-adjacency / complete-graph
+                # siblings): dense instances in one streaming launch, instances with zero coefficients in a second one
                 try:
                     loss = model.loss_and_grad_batch(A, b, c, y, [float(criterion.weight[0]), float(criterion.weight[1])])
-                    if not model.last_batch_was_dense():
-                        # the kernel itself reports an instance with a zero coefficient (no separate pass over A): its
-                        # result is invalid, this batch goes through autograd
-                        optimizer.zero_grad()
-                        loss = None
                 except _lib.DdbError as exc:
                     if 'do not fit' not in str(exc):
                         raise
@@ -208,9 +204,6 @@ def train_on_device_stream(model, optimizer, m, n, steps, batch_per_rank, key=0,
     dev = _model_device(model)
     if dev.type != 'cuda':
         raise _lib.DdbError('train_on_device_stream runs on the GPU only; there is no CPU fallback')
-    if density < 1.0:
-        raise _lib.DdbError('train_on_device_stream: the loss + gradient kernel covers dense instances only (an instance with a '
-                            'zero coefficient contributes nothing); density=%g would train on partial gradients' % density)
     rank, W = parallel.world()
     B = int(batch_per_rank)
     thr = _lib.DEFAULT_THRESHOLD if threshold is None else threshold
@@ -235,7 +228,6 @@ def train_on_device_stream(model, optimizer, m, n, steps, batch_per_rank, key=0,
             ready[step % 2].record(side)
 
     losses = torch.zeros(steps, dtype=torch.float64, device=dev)
-    not_dense = torch.zeros(1, dtype=torch.int32, device=dev)         # accumulated on the device, read once at the end
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if W > 1:
         torch.distributed.barrier()
@@ -249,7 +241,6 @@ def train_on_device_stream(model, optimizer, m, n, steps, batch_per_rank, key=0,
             produce(step + 1)
         optimizer.zero_grad()
         loss = model.loss_and_grad_batch(bf['A'], bf['b'], bf['c'], bf['labels'], weight)
-        not_dense += model._last_grad_flag
         consumed[step % 2].record(main)
         if W > 1:
             flat = torch.cat([q.grad.reshape(-1) for q in model.parameters()] + [loss.reshape(1).float()])
@@ -269,8 +260,5 @@ def train_on_device_stream(model, optimizer, m, n, steps, batch_per_rank, key=0,
     if W > 1:
         torch.distributed.all_reduce(secs, op=torch.distributed.ReduceOp.MAX)
     secs = float(secs.item())
-    if int(not_dense.item()) != 0:
-        raise _lib.DdbError('train_on_device_stream: a generated instance had a zero coefficient; the loss + gradient kernel '
-                            'skipped it, so the run trained on partial gradients')
     total = steps * W * B
     return {'loss': losses.cpu().numpy(), 'lps': total, 'seconds': secs, 'lps_per_sec': total / secs}

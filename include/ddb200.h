@@ -159,8 +159,8 @@ int ddb_s2v_forward_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p,
  * labels[B,m] u8 (0/1) are the active-constraint labels of (2).  Outputs (device, overwritten):
  *   grad[ddb_s2v_param_count(graph, p)] = d loss / d params in the flat order of (4), summed over the batch;
  *   loss = summed weighted negative log-likelihood (fp64 accumulation of fp32 terms);
- *   not_dense = 1 if an instance has a zero in A and graph == 1 (the bipartite kernel covers the reference's dense random
- *   LPs; such an instance contributes nothing and the caller must treat the call as failed).  Always 0 for graph 0.
+ *   not_dense = 1 if an instance has a zero in A and graph == 1 (informational: the streaming kernel covers the reference's
+ *   dense random LPs and flags such instances, a general-adjacency kernel then adds exactly those).  Always 0 for graph 0.
  * graph 1 ('bipartite', the reference's default, benchmark.py:166): p <= 64.
  * graph 0 ('complete'): tcgen05 Gram kernel (relu row sums of W = G G^T) + a forward/backward kernel on them; needs
  *   m + 1 <= 256, p <= 64 and T p m floats of embeddings in shared memory, else DDB_EUNSUPPORTED ("do not fit").

@@ -172,13 +172,33 @@ def test_backward_kernel_vs_autograd_large_batch(cuda_device, graph, m, n, p, T,
     assert float((g_dev - g_ref).abs().max()) <= 5e-4 * float(g_ref.abs().max()) + 1e-5
 
 
-def test_backward_kernel_flags_sparse_instances(cuda_device):
+@pytest.mark.parametrize('m,n,p,T,B,density', [(40, 20, 8, 2, 64, 0.5), (200, 100, 40, 3, 160, 0.1), (60, 30, 12, 3, 300, 0.3),
+                                               (37, 19, 13, 1, 50, 0.5), (50, 20, 64, 4, 40, 0.5), (23, 9, 5, 0, 20, 0.5)])
+def test_backward_general_adjacency_vs_autograd(cuda_device, m, n, p, T, B, density):
+    """Instances with zero coefficients (general adjacency; at density 0.1 also empty rows and columns) mixed with dense
+    ones: the streaming kernel flags them, the general-adjacency kernel adds them; loss and gradient equal autograd through
+    the batched torch restatement."""
     from deep_dantzig_b200.ml.models.s2v import Model
     from deep_dantzig_b200 import solver
-    model = Model('bipartite', 8, 2, on_cuda=True, verbose_init=False)
-    A, b, c = solver.generate(6, 0, 8, 40, 20, density=0.5)
-    model.loss_and_grad_batch(A, b, c, torch.zeros(8, 40, dtype=torch.uint8, device='cuda'), [0.5, 0.5])
+    torch.manual_seed(5)
+    model = Model('bipartite', p, T, on_cuda=True, verbose_init=False)
+    A, b, c = solver.generate(6, 0, B, m, n, density=density)
+    Ad, bd, cd = solver.generate(7, 0, B // 2, m, n)                       # dense instances in the same batch
+    A, b, c = torch.cat((A, Ad)), torch.cat((b, bd)), torch.cat((c, cd))
+    y = solver.solve_label(A, b, c)['labels']
+    y[::3] = (torch.rand_like(y[::3].float()) < 0.3).to(y.dtype)           # labels on sparse / unbounded instances too
+    w = [0.3, 0.7]
+    model.zero_grad()
+    l_dev = model.loss_and_grad_batch(A, b, c, y, w)
     assert not model.last_batch_was_dense()
+    g_dev = torch.cat([q.grad.reshape(-1) for q in model.parameters()]).clone()
+    model.zero_grad()
+    crit = torch.nn.NLLLoss(weight=torch.tensor(w, device='cuda'), reduction='sum')
+    l_ref = crit(model.forward_batch_torch(A, b, c).reshape(-1, 2), y.long().reshape(-1))
+    l_ref.backward()
+    g_ref = torch.cat([(q.grad if q.grad is not None else torch.zeros_like(q)).reshape(-1) for q in model.parameters()])
+    assert abs(float(l_dev) - float(l_ref.detach())) <= 2e-4 * abs(float(l_ref.detach()))
+    assert float((g_dev - g_ref).abs().max()) <= 5e-4 * float(g_ref.abs().max()) + 1e-5
 
 
 def test_device_metrics_match_sklearn_and_torch(cuda_device):
