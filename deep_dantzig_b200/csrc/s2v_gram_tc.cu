@@ -219,20 +219,24 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
         // (RPW rows per warp and chunk, one column per lane)
         constexpr int RPW = 256 / GPW;
         double vnext[RPW];
+        // my rows are r = warp + q GPW: the first qlim of them are rows of [A | b], slot qc (if any) is the cost row [c, 0]
+        const int qlim = (m > warp) ? (m - warp + GPW - 1) / GPW : 0;
+        const int qc = (m >= warp && ((m - warp) % GPW) == 0) ? (m - warp) / GPW : -1;
         auto load_chunk = [&](long long lpq, int kc) {
-            const double* Ag = a.A + (size_t)lpq * m * n;
-            const double* bg = a.b + (size_t)lpq * m;
-            const double* cg = a.c + (size_t)lpq * n;
+            // a lane owns ONE column of the chunk: a column of A (stride n), the column b (stride 1) or padding
             const int kabs = kc * KC + lane;
+            const bool colA = kabs < n, colB = kabs == n;
+            const size_t stride = colA ? (size_t)n : 1;
+            const double* p = (colA ? a.A + (size_t)lpq * m * n + kabs : a.b + (size_t)lpq * m) + (size_t)warp * stride;
+            const double* pc = a.c + (size_t)lpq * n + (colA ? kabs : 0);
+            const bool any = colA || colB;
 #pragma unroll
             for (int q = 0; q < RPW; ++q) {
-                const int r = warp + q * GPW;
                 double v = 0.0;
-                if (r < m) {
-                    if (kabs < n) v = __ldg(Ag + (size_t)r * n + kabs);
-                    else if (kabs == n) v = __ldg(bg + r);
-                } else if (r == m) {
-                    if (kabs < n) v = __ldg(cg + kabs);
+                if (q < qlim) {
+                    if (any) v = __ldg(p + (size_t)q * GPW * stride);
+                } else if (q == qc) {
+                    if (colA) v = __ldg(pc);
                 }
                 vnext[q] = v;
             }
@@ -256,19 +260,22 @@ __global__ void __launch_bounds__(GT, 1) s2v_gram_tc_kernel(S2vGramArgs a) {
                 }
                 // the MMAs that read this stage two chunks ago must have finished before it is overwritten
                 if (g >= 2) mbar_wait(empty + stg, (uint32_t)(((g >> 1) - 1) & 1));
-                unsigned char* hs = hi + (size_t)stg * L.stage;
-                unsigned char* ls = lo + (size_t)stg * L.stage;
+                // element (row r, column lane) of the chunk: plane lane / 4, 8-row group r / 8, row r % 8, word lane % 4; with
+                // r = warp + q GPW the address is a per-thread base + q * (GPW / 8) * 128 (an immediate).  hi = tf32(g) rounded,
+                // lo = g - hi as it is: kind::tf32 reads the upper 19 bits of an fp32 container, which drops 2^-22 |g| at most --
+                // the size of the Glo Glo^T term the 3xTF32 product leaves out anyway
                 const uint32_t coff = (uint32_t)(lane >> 2) * L.PLB + (lane & 3) * 4 + (uint32_t)(warp >> 3) * 128 + (warp & 7) * 16;
+                const uint32_t hsa = smem_u32(hi) + (uint32_t)(stg * L.stage) + coff;
+                const uint32_t lsa = smem_u32(lo) + (uint32_t)(stg * L.stage) + coff;
+                const int qrows = (rows_pl - warp + GPW - 1) / GPW;          // slots whose row lies inside the planes
 #pragma unroll
                 for (int q = 0; q < RPW; ++q) {
-                    const int r = warp + q * GPW;
-                    if (r < rows_pl) {
+                    if (q < qrows) {
                         const float gq = (float)vcur[q];
                         const uint32_t h = to_tf32(gq);
-                        const uint32_t l = to_tf32(gq - __uint_as_float(h));
-                        const uint32_t off = coff + (uint32_t)q * (GPW / 8) * 128;      // (r >> 3) * 128 + (r & 7) * 16
-                        *reinterpret_cast<uint32_t*>(hs + off) = h;
-                        *reinterpret_cast<uint32_t*>(ls + off) = l;
+                        const float l = gq - __uint_as_float(h);
+                        asm volatile("st.shared.b32 [%0], %1;" ::"r"(hsa + (uint32_t)q * (GPW / 8) * 128), "r"(h) : "memory");
+                        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lsa + (uint32_t)q * (GPW / 8) * 128), "f"(l) : "memory");
                     }
                 }
                 fence_proxy_async();
