@@ -90,7 +90,7 @@ __host__ __device__ inline size_t ggrad_scratch_floats(int m, int n, int p, int 
 
 // S = slots of the element-wise p x p register accumulators: ceil(p * p / kGT)
 template <int S>
-__global__ void __launch_bounds__(kGT, 1) s2v_bipartite_general_grad_kernel(S2vGGradArgs a) {
+__global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vGGradArgs a) {
     extern __shared__ __align__(16) float sm[];
     const int m = a.m, n = a.n, p = a.p, T = a.T, PP = gpad4(p), NP = m + n;
     const int NW32 = (n + 31) / 32, MW32 = (m + 31) / 32;
@@ -591,7 +591,8 @@ __global__ void __launch_bounds__(kGT, 1) s2v_bipartite_general_grad_kernel(S2vG
 
 size_t s2v_general_grad_smem_bytes(int m, int n, int p) { return ggrad_layout(m, n, p).total * 4; }
 size_t s2v_general_grad_scratch_floats(int m, int n, int p, int T) { return ggrad_scratch_floats(m, n, p, T); }
-int s2v_general_grad_grid(long long B, int sm_count) { return (int)((B < sm_count) ? B : sm_count); }
+// two CTAs per SM (latency-bound: the embeddings of every round live in an L2-resident scratch)
+int s2v_general_grad_grid(long long B, int sm_count) { return (int)((B < 2 * sm_count) ? B : 2 * sm_count); }
 
 cudaError_t launch_s2v_bipartite_general_grad(const S2vGGradArgs& a, int grid, long long smem_optin, cudaStream_t st, const char** why) {
     *why = "";

@@ -5,7 +5,8 @@ rule (first ROC threshold with TPR == 1.0 on the train set, :138-140).
 What changes: a DataLoader batch is ONE batched forward/backward (``Model.forward_batch``) instead of a Python loop of
 single-instance calls; the summed loss gives the same gradient as the reference's accumulation (:60-66).  Under
 torch.distributed every rank trains on its shard of the batch and gradients are summed with one flat all-reduce.
-Batches are dicts as produced by ``ml.utils.collate_randomlp``."""
+Batches are dicts as produced by ``ml.utils.collate_randomlp``; a batch that is a LIST of reference-format items (``DatasetPLNN`` with
+``collate_items``: MPS / PLNN LPs of different shapes) takes the reference's own per-item loop."""
 import ctypes as C
 import time
 
@@ -18,6 +19,25 @@ from .. import _lib, parallel
 
 def _to_device(batch, dev):
     return batch['A'].to(dev), batch['b'].to(dev), batch['c'].to(dev), batch['y'].to(dev)
+
+
+def collate_items(items):
+    """DataLoader ``collate_fn`` for reference-format items of different shapes (``DatasetPLNN``): the batch is the list."""
+    return list(items)
+
+
+def _is_item_batch(data):
+    """A batch of reference-format items (MPS / PLNN LPs: one shape per item, equality / bound flags) rather than the
+    collated random-LP tensors of ``ml.utils.collate_randomlp``."""
+    return isinstance(data, (list, tuple))
+
+
+def _item_xy(item, graph, dev):
+    """(x, y) of one reference-format item as ``batched`` yields them (src/ml/utils.py:3-25): y = labels of the in_loss rows."""
+    in_loss = [int(q) for q in item['in_loss']]
+    lab = item['node_labels'] if graph == 'complete' else item['c_labels']
+    lab = torch.as_tensor(np.asarray(lab)).reshape(-1)
+    return item, lab[in_loss].long().to(dev)
 
 
 def _model_device(model):
@@ -34,6 +54,17 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
         epoch_start = time.time()
         running_loss = 0.0
         for data in trainloader:
+            if _is_item_batch(data):
+                # the reference's own loop (train.py:57-66): one forward / backward per item, gradients accumulate
+                optimizer.zero_grad()
+                for item in data:
+                    x, y = _item_xy(item, model.graph, dev)
+                    loss = criterion(model(x), y)
+                    loss.backward()
+                parallel.allreduce_gradients(model)
+                optimizer.step()
+                running_loss += float(loss.detach())                  # the last item's loss, as train.py:68-69 records it
+                continue
             A, b, c, y = _to_device(data, dev)
             optimizer.zero_grad()
             loss = None
@@ -79,6 +110,13 @@ def _probs_and_labels(loader, model):
     model.eval()
     with torch.no_grad():
         for data in loader:
+            if _is_item_batch(data):
+                for item in data:
+                    x, y = _item_xy(item, model.graph, dev)
+                    model(x)
+                    ps.append(model.probs[..., 1].reshape(-1).float().cpu())
+                    ys.append(y.reshape(-1).cpu())
+                continue
             A, b, c, y = _to_device(data, dev)
             model.forward_batch(A, b, c)
             ps.append(model.probs[..., 1].reshape(-1).float().cpu())
@@ -86,6 +124,12 @@ def _probs_and_labels(loader, model):
     if was_training:
         model.train()
     return torch.cat(ys).numpy(), torch.cat(ps).numpy()
+
+
+def _loader_has_items(loader):
+    """True if the loader yields reference-format item lists (peeks at the dataset, not at a batch)."""
+    ds = getattr(loader, 'dataset', None)
+    return ds is not None and len(ds) > 0 and isinstance(ds[0], dict) and ('c_feats' in ds[0] or 'node_features' in ds[0])
 
 
 def _on_device(model):
@@ -126,7 +170,7 @@ def recall_one_threshold(loader, model):
     """train.py:118-150: threshold of the first ROC point whose TPR is 1.0 (keeps every active constraint).  sklearn's
     ROC thresholds are the scores themselves, so that point is the smallest predicted probability of a positive -- which
     is what the device pass returns."""
-    if _on_device(model):
+    if _on_device(model) and not _loader_has_items(loader):
         r = device_metrics(model, loader)
         return float(r[4]) if (r[6] > 0 and r[7] > 0) else 0.5
     y_true, y_prob = _probs_and_labels(loader, model)
@@ -147,7 +191,7 @@ def plot_roc(model, epoch, trainloader=None, testloader=None):
 
 def get_prob_recall_one(loader, model):
     """train.py:102-116: smallest predicted probability of a positive."""
-    if _on_device(model):
+    if _on_device(model) and not _loader_has_items(loader):
         r = device_metrics(model, loader)
         return float(r[4]) if r[6] > 0 else 0.5
     y_true, y_prob = _probs_and_labels(loader, model)
@@ -156,7 +200,7 @@ def get_prob_recall_one(loader, model):
 
 def performance(loader, model, criterion, prob_thresh=0.5):
     """train.py:174-246 (metric names and formulas unchanged)."""
-    if _on_device(model) and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum':
+    if _on_device(model) and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum' and not _loader_has_items(loader):
         r = device_metrics(model, loader, criterion, prob_thresh)
         return _metrics_dict(r[5], int(r[0]), int(r[1]), int(r[2]), int(r[3]))
     dev = _model_device(model)
@@ -166,6 +210,15 @@ def performance(loader, model, criterion, prob_thresh=0.5):
     tps = fps = tns = fns = 0
     with torch.no_grad():
         for data in loader:
+            if _is_item_batch(data):
+                for item in data:
+                    x, y = _item_xy(item, model.graph, dev)
+                    fx = model(x)
+                    total_loss += float(criterion(fx, y))
+                    pred = model.probs[..., 1] >= prob_thresh
+                    tps += int(((y == 1) & pred).sum()); fps += int(((y == 0) & pred).sum())
+                    tns += int(((y == 0) & ~pred).sum()); fns += int(((y == 1) & ~pred).sum())
+                continue
             A, b, c, y = _to_device(data, dev)
             fx = model.forward_batch(A, b, c)
             total_loss += float(criterion(fx.reshape(-1, 2), y.reshape(-1)))

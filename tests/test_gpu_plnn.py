@@ -104,3 +104,14 @@ def test_mps_solve_matches_highs_and_dataset_items(cuda_device, tmp_path):
     # has_matrix_inequalities / ineq_num bookkeeping
     d = LinProg.ineq_num(lps[0][0])
     assert d['num_constrs'] == len(lps[0][2]) and d['num_pos'] + d['num_inactive_ineq'] == d['num_ineq']
+    # the reference's own experiment driver on the MPS tree (src/benchmark.py:46-95): DatasetPLNN + per-item training loop
+    from deep_dantzig_b200 import benchmark
+    for graph in ('bipartite', 'complete'):
+        res, trained = benchmark.run_experiment_batch('plnn', graph, 'lp', None, 8, 2, epochs=2, batch_size=3, learning_rate=1e-3,
+                                                      momentum=0.9, weight_decay=0.0, seed=7, cuda=True, tag='t', root=root)
+        assert res['dataset'] == 'plnn' and set(res['out']['results']) == {'train', 'test'}
+        assert len(res['out']['results']['train']) == 2 and res['out']['lps']
+        for ep in res['out']['results']['train'] + res['out']['results']['test']:
+            assert math.isfinite(ep['total_loss']) and 0.0 <= ep['accuracy'] <= 1.0 and 0.0 <= ep['recall'] <= 1.0
+        assert res['out']['results']['train'][-1]['recall'] == 1.0          # the threshold is the train set's recall-1 point
+        assert all(torch.isfinite(q).all() for q in trained.parameters())

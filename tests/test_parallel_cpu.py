@@ -133,3 +133,39 @@ def test_numa_binding_is_best_effort():
     assert node is None or isinstance(node, int)
     if not torch.cuda.is_available():
         assert node is None and os.sched_getaffinity(0) == before
+
+
+def test_train_net_reference_item_batches_on_cpu():
+    """A DataLoader that yields LISTS of reference-format items (what DatasetPLNN + collate_items produce: one shape per
+    item) takes the reference's per-item accumulation loop (train.py:57-66); return schema and metrics as for tensors."""
+    from torch.utils.data import DataLoader
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200.ml.train import train_net, performance, collate_items
+    from oracle import randomlp as orl
+    from oracle import classifier as oc
+    for graph in ('bipartite', 'complete'):
+        items = []
+        for k, (m, n) in enumerate([(10, 5), (12, 4), (9, 6), (10, 5), (14, 5), (8, 3)]):        # shapes differ per item
+            A, b, c = orl.generate_instance(m, n, 100 + k)
+            ref = orl.solve_batch(A[None], b[None], c[None])
+            labels = ref['labels'][0].astype(int).tolist()
+            it = oc.item_bipartite(A, b, c, labels) if graph == 'bipartite' else oc.item_complete(A, b, c, labels)
+            if graph == 'bipartite':
+                it['c_feats'][0, 0] = 0.0                   # one equality row, kept out of the loss as gurobi_lp.py:164-177 does
+                it['in_loss'] = list(range(1, m))
+            items.append(it)
+        loader = DataLoader(items, batch_size=4, shuffle=False, collate_fn=collate_items)
+        torch.manual_seed(2)
+        model = Model(graph, 6, 2, verbose_init=False)
+        model.force_torch = True
+        crit = torch.nn.NLLLoss(weight=torch.tensor([0.3, 0.7]), reduction='sum')
+        before = performance(loader, model, crit, 0.5)
+        opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9)
+        hist = train_net(model, crit, opt, loader, loader, epochs=5, batch_size=4, verbose=False)
+        assert set(hist) == {'train', 'test'} and len(hist['train']) == 5
+        assert hist['train'][-1]['total_loss'] < before['total_loss']
+        assert hist['train'][-1]['recall'] == 1.0
+        n_rows = sum(len(it['in_loss']) for it in items)
+        last = hist['train'][-1]
+        assert abs((last['y_pos'] + last['y_neg']) - 1.0) < 1e-12 and abs(last['pred_pos'] + last['pred_neg'] - 1.0) < 1e-12
+        assert n_rows > 0
