@@ -543,40 +543,83 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
         __syncthreads();
 
         // ---- T rounds ----------------------------------------------------------------------------------------------------------
+        // mu ping-pongs between the two buffers; a round's update (base + t2rr mu_i + t2rc mu_c, relu) is the epilogue of the
+        // register-tiled product, and round 0 -- the embeddings start at zero -- is the base alone.  Padding nodes hold 0.
+        float* mu_cur = mu;
+        float* mu_nxt = mu2;
+        for (int l = tid; l < PP; l += nt) { muc[l] = 0.f; meanr[l] = 0.f; }
+        __syncthreads();
         for (int t = 0; t < a.T; ++t) {
+            if (t > 0) {
+                small_matvec(t2rc, p, muc, y1, warp, lane, nw);
+                small_matvec(t2cr, p, meanr, y2, warp, lane, nw);
+                __syncthreads();
+            }
+            {
+                const int NG = MP / 4, KG = PP / 4;
+                for (int w = tid; w < NG * KG; w += nt) {
+                    const int ng = w % NG, kg = w / NG;
+                    float acc[4][4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) acc[q][r] = 0.f;
+                    if (t > 0) {
+                        for (int l = 0; l < p; ++l) {
+                            const float4 xv = *reinterpret_cast<const float4*>(mu_cur + l * MP + 4 * ng);
+                            const float4 wv = *reinterpret_cast<const float4*>(t2rrT + l * PP + 4 * kg);
+                            const float xq[4] = {xv.x, xv.y, xv.z, xv.w};
+                            const float wr[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                                for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(wr[r], xq[q], acc[q][r]);
+                        }
+                    }
+                    float wpq[4], wnq[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int i = 4 * ng + q;
+                        wpq[q] = (i < m) ? Wp[i] : 0.f;
+                        wnq[q] = (i < m) ? Wn[i] : 0.f;
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const int l = 4 * kg + r;
+                        if (l < p) {
+                            const float add = __ldg(t0 + l) + __ldg(t1 + l) + scal[0] + (t > 0 ? y1[l] : 0.f);
+                            const float cp = w3p[l], cn = w3n[l];
+                            float o[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int i = 4 * ng + q;
+                                o[q] = (i < m) ? fmaxf(acc[q][r] + add + cp * wpq[q] + cn * wnq[q], 0.f) : 0.f;
+                            }
+                            *reinterpret_cast<float4*>(mu_nxt + l * MP + 4 * ng) = make_float4(o[0], o[1], o[2], o[3]);
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            // the cost node (its node feature is 0) and the mean over the row nodes of the NEW embeddings
+            for (int l = tid; l < p; l += nt) muc[l] = fmaxf(__ldg(t0 + l) + (t > 0 ? y2[l] : 0.f) + u3c[l], 0.f);
             for (int l = warp; l < p; l += nw) {
                 float sr = 0.f;
-                for (int i = lane; i < m; i += 32) sr += mu[l * MP + i];
+                for (int i = lane; i < m; i += 32) sr += mu_nxt[l * MP + i];
                 sr = warp_sumf(sr);
-                if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * MP + m]; }
+                if (lane == 0) meanr[l] = sr / (float)m;
             }
-            __syncthreads();
-            small_matvec(t2rc, p, muc, y1, warp, lane, nw);
-            small_matvec(t2cr, p, meanr, y2, warp, lane, nw);
-            node_matmul_tiled(t2rrT, PP, p, mu, MP, mu2, MP, pad4(m), tid, nt);   // t2rr . mu_r
-            __syncthreads();
-            for (int e = tid; e < p * MP; e += nt) {
-                const int l = e / MP, q = e - l * MP;
-                if (q >= M1) continue;
-                float val;
-                if (q < m) {
-                    val = __ldg(t0 + l) + __ldg(t1 + l) + mu2[e] + y1[l] + w3p[l] * Wp[q] + w3n[l] * Wn[q] + scal[0];
-                } else {
-                    val = __ldg(t0 + l) + y2[l] + u3c[l];                    // node feature of the cost node is 0
-                }
-                mu[e] = fmaxf(val, 0.f);
-            }
+            float* sw = mu_cur; mu_cur = mu_nxt; mu_nxt = sw;
             __syncthreads();
         }
+        if (a.T == 0) {
+            for (int e = tid; e < p * MP; e += nt) mu_cur[e] = 0.f;
+            __syncthreads();
+        }
+        mu = mu_cur;
+        mu2 = mu_nxt;
 
-        // ---- head -----------------------------------------------------------------------------------------------------------------
-        for (int l = warp; l < p; l += nw) {
-            float sr = 0.f;
-            for (int i = lane; i < m; i += 32) sr += mu[l * MP + i];
-            sr = warp_sumf(sr);
-            if (lane == 0) { meanr[l] = sr / (float)m; muc[l] = mu[l * MP + m]; }
-        }
-        __syncthreads();
+        // ---- head (meanr / muc are those of the final embeddings) ------------------------------------------------------------------
         small_matvec(t6r, p, meanr, tmp1, warp, lane, nw);
         small_matvec(t6c, p, muc, tmp2, warp, lane, nw);
         __syncthreads();
