@@ -23,6 +23,8 @@ cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, i
 bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
+bool quadcol_supported(int m, int n);
+cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st);
 #ifdef DDB_EXPERIMENTS   // `make experiments`: the measured negative results of round 1, not in the shipped library
 bool tile2d_supported(int m, int n);
 cudaError_t launch_simplex_tile2d(const SolveArgs& a, int sm_count, cudaStream_t st);
@@ -318,6 +320,8 @@ extern "C" int ddb_solve_plan(ddb_ctx* ctx, int m, int n) {
         return fail(DDB_EUNSUPPORTED, "software-pipelined row-per-thread kernel does not cover m=%d n=%d", m, n);
     if (plan == 6 && !ddb::cluster_supported(m, n))
         return fail(DDB_EUNSUPPORTED, "thread-block-cluster kernel does not cover m=%d n=%d", m, n);
+    if (plan == 7 && !ddb::quadcol_supported(m, n))
+        return fail(DDB_EUNSUPPORTED, "column-block-per-warp register kernel does not cover m=%d n=%d", m, n);
     return plan;
 }
 
@@ -330,7 +334,7 @@ extern "C" int ddb_set_fused_mode(ddb_ctx* ctx, int mode) {
 
 extern "C" int ddb_set_solve_plan(ddb_ctx* ctx, int plan) {
     if (!ctx) return fail(DDB_EINVAL, "ddb_set_solve_plan: ctx is NULL");
-    if (plan < -1 || plan > 6) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
+    if (plan < -1 || plan > 7) return fail(DDB_EINVAL, "ddb_set_solve_plan: plan %d", plan);
     ctx->forced_plan = plan;
     return DDB_OK;
 }
@@ -444,7 +448,7 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
     int rc;
 
-    if (plan == 0 || plan == 3 || plan == 4 || plan == 5) {
+    if (plan == 0 || plan == 3 || plan == 4 || plan == 5 || plan == 7) {
         // Register-resident kernels: row-per-thread (plan 0 default; hybrid register + shared-memory rows at (200,100)) and
         // the warp-tiled kernel (plan 4, the fallback of plan 0 for shapes the row kernel does not cover).  Plans 3 / 5
         // (2-D tile, software-pipelined rows) exist only in the `make experiments` build.
@@ -452,6 +456,7 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
         if (plan == 5) which = 3;
+        if (plan == 7) which = (row_mask || gen) ? 1 : 4;   // the column-block kernel takes neither row masks nor the in-solver generator
         if (gen) which = 1;                              // the caller checked rowreg_gen_supported
         const int grid = gen ? ddb::rowreg_gen_grid(m, n, ctx->sm_count) : ddb::rowreg_grid(m, n, ctx->sm_count);
         const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
@@ -474,6 +479,8 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
             CUDA_TRY(ddb::launch_simplex_rowreg(a, ctx->sm_count, st));
         else if (which == 3)
             CUDA_TRY(ddb::launch_simplex_rowpipe(a, ctx->sm_count, st));
+        else if (which == 4)
+            CUDA_TRY(ddb::launch_simplex_quadcol(a, ctx->sm_count, st));
         else
             CUDA_TRY(ddb::launch_simplex_regtile(a, ctx->sm_count, st));
         ctx->launches += 1;

@@ -1,0 +1,726 @@
+// Column-block-per-warp batched fp64 simplex (plan 7): one LP per CTA of four warps, the condensed tableau in the
+// REGISTER FILE as a 2-D distribution -- tableau ROWS over the LANES (four rows per lane), tableau COLUMNS over the WARPS
+// (25 columns per warp plus a private copy of the right-hand side).  A thread owns a 4 x 26 register tile.
+//
+// Why (measured on plan 0, profiles/ncu_r02_rowreg_summary.txt): with one whole row per thread every FMA of the rank-1
+// update needs its own broadcast operand from shared memory (97 shared-memory instructions per 101 DFMAs per warp and
+// pivot, load/store pipe 65 % busy), every warp repeats the per-pivot bookkeeping, and one lane publishes a whole row.
+// Here
+//   * a broadcast LDS.128 of the pivot row feeds EIGHT DFMAs (two columns x four rows): 13 loads per 104 DFMAs;
+//   * a warp needs the pivot row only in ITS columns, and it owns them: the owner lane publishes 26 doubles per warp
+//     (13 STS.128) into a warp-private buffer behind a __syncwarp -- no block barrier between choosing the row and
+//     using it;
+//   * the only quantity that crosses warps is the column of multipliers f_i = T_i[k] / p (one double per row).  Every
+//     warp computes it SPECULATIVELY for its own best candidate column before the pivot's single __syncthreads;
+//     afterwards all warps pick the same winner and read its multipliers.  One barrier per pivot in all three stages,
+//     and no warp idles while another one runs a serial section;
+//   * per-row state (lazy row scale lam, 1 / lam) is replicated per warp, per-column state (reduced costs g, ghat) sits
+//     in the lane that owns the column; the right-hand side copies stay bitwise identical because every warp applies
+//     the same operations to them, so phase 1's leaving row is found by every warp on its own.
+//
+// Same algorithm, tolerances and arithmetic per tableau entry as rowreg_kernel.cuh: static-order
+// crash as an explicit inverse (kept in shared memory, 4 blocks of 26 per row), P_N = -A_N D, phase 1 (most negative
+// slack leaves), phase 2 (Dantzig), lazily normalised rows; exact ties go to the lowest column / lowest tile row.
+// Covers n <= 100, m - n <= 128 without row masks; instances it cannot finish (singular static crash basis,
+// ill-conditioned vertex) are flagged status = -1 and re-solved by the generic kernel on the device (capi.cu).
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace ddb {
+namespace {
+
+constexpr int QW = 4;                 // warps = column blocks
+constexpr int QC = 25;                // tableau columns per warp
+constexpr int QP = QC + 1;            // + right-hand side: a thread's row slice, 13 x 16 bytes
+constexpr int QR = 4;                 // rows per lane
+constexpr int QNT = QW * 32;          // threads
+constexpr int QROWS = 32 * QR;        // tile rows
+constexpr int QNMAX = QW * QC;        // columns
+constexpr int QMMAX = 256;            // constraints (order / score arrays)
+constexpr int QDP = QW * QP;          // pitch of a row of D in shared memory
+constexpr int QCS = 4;                // column slots of the lane-distributed vectors of stages 0 and 4 (j = lane + 32 cs)
+
+struct QCand {                        // one per (buffer, warp): the warp's speculative candidate
+    unsigned long long key;           // crash: bits of |pivot|; phase 1: dkey(ratio); phase 2: dkey(g_k); KEY_INF / 0 = none
+    int k;                            // entering column
+    int r;                            // phase 2: leaving tile row (-1: column unblocked)
+    double p;                         // pivot entry (stored scale)
+    double gk;                        // g[k]
+    double ghk;                       // ghat[k] (phase 1)
+    double pad[3];
+};
+static_assert(sizeof(QCand) == 64, "candidate record");
+
+// fixed shared-memory layout (every offset is an immediate)
+constexpr size_t qalign(size_t v) { return (v + 15) / 16 * 16; }
+constexpr size_t Q_D = 0;
+constexpr size_t Q_PROW = Q_D + qalign((size_t)QNMAX * QDP * 8);
+constexpr size_t Q_F = Q_PROW + qalign((size_t)QW * QP * 8);
+constexpr size_t Q_CAND = Q_F + qalign((size_t)2 * QW * QROWS * 8);
+constexpr size_t Q_LAM = Q_CAND + qalign((size_t)2 * QW * sizeof(QCand));
+constexpr size_t Q_ILAM = Q_LAM + qalign((size_t)QW * QROWS * 8);
+constexpr size_t Q_SVAL = Q_ILAM + qalign((size_t)QW * QROWS * 8);
+constexpr size_t Q_SIG = Q_SVAL + qalign((size_t)QROWS * 8);
+constexpr size_t Q_XBUF = Q_SIG + qalign((size_t)QROWS * 8);
+constexpr size_t Q_GBUF = Q_XBUF + qalign((size_t)QROWS * 8);
+constexpr size_t Q_GNN = Q_GBUF + qalign((size_t)QMMAX * 8);
+constexpr size_t Q_ROWVAR = Q_GNN + qalign((size_t)QMMAX * 8);
+constexpr size_t Q_CV = Q_ROWVAR + qalign((size_t)QROWS * 4);
+constexpr size_t Q_COLVAR0 = Q_CV + qalign((size_t)QROWS * 4);
+constexpr size_t Q_PIVCOL = Q_COLVAR0 + qalign((size_t)QROWS * 4);
+constexpr size_t Q_ORDER = Q_PIVCOL + qalign((size_t)QROWS * 4);
+constexpr size_t Q_BASIC = Q_ORDER + qalign((size_t)QMMAX * 4);
+constexpr size_t Q_RED = Q_BASIC + qalign((size_t)QMMAX * 4);
+constexpr size_t Q_CUR = Q_RED + qalign((size_t)(3 * QW + 4) * 4);
+constexpr size_t Q_TOTAL = Q_CUR + 16;
+
+#define QCOLS(M) M(0) M(1) M(2) M(3) M(4) M(5) M(6) M(7) M(8) M(9) M(10) M(11) M(12) M(13) M(14) M(15) M(16) M(17) M(18) \
+    M(19) M(20) M(21) M(22) M(23) M(24)
+
+// my four entries in column kk of my block (warp-uniform kk): a jump table whose leaves are four moves
+__device__ __forceinline__ void col_get4(const double (&T)[QR][QP], int kk, double (&e)[QR]) {
+    e[0] = e[1] = e[2] = e[3] = 0.0;
+    switch (kk) {
+#define QCASE(I)                                                   \
+    case I:                                                        \
+        asm volatile("mov.f64 %0, %1;" : "=d"(e[0]) : "d"(T[0][I])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(e[1]) : "d"(T[1][I])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(e[2]) : "d"(T[2][I])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(e[3]) : "d"(T[3][I])); \
+        break;
+        QCOLS(QCASE)
+#undef QCASE
+        default: break;
+    }
+}
+__device__ __forceinline__ void col_set4(double (&T)[QR][QP], int kk, const double (&v)[QR]) {
+    switch (kk) {
+#define QCASE(I)                                                   \
+    case I:                                                        \
+        asm volatile("mov.f64 %0, %1;" : "=d"(T[0][I]) : "d"(v[0])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(T[1][I]) : "d"(v[1])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(T[2][I]) : "d"(v[2])); \
+        asm volatile("mov.f64 %0, %1;" : "=d"(T[3][I]) : "d"(v[3])); \
+        break;
+        QCOLS(QCASE)
+#undef QCASE
+        default: break;
+    }
+}
+__device__ __forceinline__ void store_row(double* pr, const double (&row)[QP]) {
+    double2* p2 = reinterpret_cast<double2*>(pr);
+#pragma unroll
+    for (int c2 = 0; c2 < QP / 2; ++c2) p2[c2] = make_double2(row[2 * c2], row[2 * c2 + 1]);
+}
+// the lane that owns tile row (lane, slot q) stores its slice of that row (warp-uniform q)
+__device__ __forceinline__ void publish_slot(double* pr, const double (&T)[QR][QP], int q) {
+    switch (q) {
+        case 0: store_row(pr, T[0]); break;
+        case 1: store_row(pr, T[1]); break;
+        case 2: store_row(pr, T[2]); break;
+        default: store_row(pr, T[3]); break;
+    }
+}
+__device__ __forceinline__ double sel4(const double (&v)[QR], int q) {
+    const double a = (q & 1) ? v[1] : v[0], b = (q & 1) ? v[3] : v[2];
+    return (q & 2) ? b : a;
+}
+
+__global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double* Dsm = reinterpret_cast<double*>(smem_raw + Q_D);           // [n][QW][QP]: crash inverse, x-vertex in slot QC of every block
+    double* prowS = reinterpret_cast<double*>(smem_raw + Q_PROW);      // [QW][QP]: a warp's slice of the current pivot row
+    double* fS = reinterpret_cast<double*>(smem_raw + Q_F);            // [2][QW][QROWS]: speculative multipliers
+    QCand* candS = reinterpret_cast<QCand*>(smem_raw + Q_CAND);        // [2][QW]
+    double* lamS = reinterpret_cast<double*>(smem_raw + Q_LAM);        // [QW][QROWS]: per-warp copy of the lazy row scales
+    double* ilamS = reinterpret_cast<double*>(smem_raw + Q_ILAM);      // [QW][QROWS]: 1 / lam
+    double* sval = reinterpret_cast<double*>(smem_raw + Q_SVAL);
+    double* sig = reinterpret_cast<double*>(smem_raw + Q_SIG);
+    double* xbuf = reinterpret_cast<double*>(smem_raw + Q_XBUF);
+    double* gbuf = reinterpret_cast<double*>(smem_raw + Q_GBUF);
+    double* gnn = reinterpret_cast<double*>(smem_raw + Q_GNN);
+    int* rowvarS = reinterpret_cast<int*>(smem_raw + Q_ROWVAR);        // tile row -> constraint whose slack is basic there
+    int* cvsm = reinterpret_cast<int*>(smem_raw + Q_CV);               // column -> constraint whose slack is nonbasic there
+    int* colvar0 = reinterpret_cast<int*>(smem_raw + Q_COLVAR0);
+    int* pivcol = reinterpret_cast<int*>(smem_raw + Q_PIVCOL);
+    int* order = reinterpret_cast<int*>(smem_raw + Q_ORDER);
+    int* basic_tile = reinterpret_cast<int*>(smem_raw + Q_BASIC);
+    int* red = reinterpret_cast<int*>(smem_raw + Q_RED);
+    long long* cur_lp = reinterpret_cast<long long*>(smem_raw + Q_CUR);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int m = a.m, n = a.n;
+    const int c0 = warp * QC;                     // first column of my block
+    const int col = c0 + lane;                    // the column whose costs I hold (lane < QC)
+    const bool hascol = lane < QC && col < n;
+    const int t0 = QR * lane;                     // my first tile row
+    double* prow = prowS + warp * QP;
+    double* lamW = lamS + warp * QROWS;
+    double* ilamW = ilamS + warp * QROWS;
+
+    double T[QR][QP];                             // my rows t0 .. t0+3, columns c0 .. c0+24, slot QC = right-hand side
+
+    // rank-1 update of my tile from my warp's slice of the (raw) pivot row:  T[q][c] -= f[q] * prow[c]
+    auto rank1 = [&](const double* pr, const double (&f)[QR]) {
+        const double2* p2 = reinterpret_cast<const double2*>(pr);
+        const double n0 = -f[0], n1 = -f[1], n2 = -f[2], n3 = -f[3];
+#pragma unroll
+        for (int c2 = 0; c2 < QP / 2; ++c2) {
+            const double2 v = p2[c2];
+            T[0][2 * c2] = fma(n0, v.x, T[0][2 * c2]);
+            T[0][2 * c2 + 1] = fma(n0, v.y, T[0][2 * c2 + 1]);
+            T[1][2 * c2] = fma(n1, v.x, T[1][2 * c2]);
+            T[1][2 * c2 + 1] = fma(n1, v.y, T[1][2 * c2 + 1]);
+            T[2][2 * c2] = fma(n2, v.x, T[2][2 * c2]);
+            T[2][2 * c2 + 1] = fma(n2, v.y, T[2][2 * c2 + 1]);
+            T[3][2 * c2] = fma(n3, v.x, T[3][2 * c2]);
+            T[3][2 * c2 + 1] = fma(n3, v.y, T[3][2 * c2 + 1]);
+        }
+    };
+    auto load4 = [&](const double* p, double (&v)[QR]) {          // p 32-byte aligned
+        const double2 u0 = reinterpret_cast<const double2*>(p)[0], u1 = reinterpret_cast<const double2*>(p)[1];
+        v[0] = u0.x; v[1] = u0.y; v[2] = u1.x; v[3] = u1.y;
+    };
+    auto store4 = [&](double* p, const double (&v)[QR]) {
+        reinterpret_cast<double2*>(p)[0] = make_double2(v[0], v[1]);
+        reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
+    };
+    // dot products of the rows of A with a lane-distributed vector, eight rows per warp in flight
+    auto row_dots = [&](const double* Ag, const double (&vl)[QCS], double* out1, double* out2) {
+        constexpr int RB = 8;
+        for (int base = 0; base < m; base += RB * QW) {
+            double v[RB][QCS];
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int i = base + r * QW + warp;
+#pragma unroll
+                for (int cs = 0; cs < QCS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    v[r][cs] = (i < m && j < n) ? __ldg(Ag + (size_t)i * n + j) : 0.0;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < RB; ++r) {
+                const int i = base + r * QW + warp;
+                double dot = 0.0, nn = 0.0;
+#pragma unroll
+                for (int cs = 0; cs < QCS; ++cs) {
+                    dot = fma(v[r][cs], vl[cs], dot);
+                    nn = fma(v[r][cs], v[r][cs], nn);
+                }
+                dot = warp_sum(dot);
+                if (out2) nn = warp_sum(nn);
+                if (lane == 0 && i < m) {
+                    out1[i] = dot;
+                    if (out2) out2[i] = nn;
+                }
+            }
+        }
+    };
+    // winner of the four candidates of buffer b: smallest key, lowest warp on ties
+    auto pick_min = [&](int b, unsigned long long& kbest) -> int {
+        const QCand* cd = candS + b * QW;
+        int w = 0;
+        kbest = cd[0].key;
+#pragma unroll
+        for (int q = 1; q < QW; ++q) {
+            const unsigned long long kq = cd[q].key;
+            if (kq < kbest) { kbest = kq; w = q; }
+        }
+        return w;
+    };
+
+    for (;;) {
+        if (tid == 0) *cur_lp = (long long)atomicAdd(a.counter, 1ull);
+        __syncthreads();
+        const long long lp = *cur_lp;
+        if (lp >= a.B) break;
+        const double* Ag = a.A + (size_t)lp * m * n;
+        const double* bg = a.b + (size_t)lp * m;
+        const double* cg = a.c + (size_t)lp * n;
+
+        // ---- stage 0: crash order by cosine score ------------------------------------------------------------------
+        {
+            double cl[QCS];
+#pragma unroll
+            for (int cs = 0; cs < QCS; ++cs) {
+                const int j = lane + 32 * cs;
+                cl[cs] = (j < n) ? __ldg(cg + j) : 0.0;
+            }
+            row_dots(Ag, cl, gbuf, gnn);
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += QNT) {
+            const double dot = gbuf[i], nn = gnn[i];
+            gnn[i] = nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5;
+        }
+        __syncthreads();
+        for (int i = tid; i < m; i += QNT) {
+            const double v = gnn[i];
+            int rank = 0;
+            for (int i2 = 0; i2 < m; ++i2) {
+                const double v2 = gnn[i2];
+                rank += (v2 < v) || (v2 == v && i2 < i);
+            }
+            order[rank] = i;
+            basic_tile[i] = -1;
+        }
+        __syncthreads();
+        const int nN = m - n;
+        bool need_generic = false;
+        int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
+        int status = ST_OPTIMAL;
+        int buf = 0;
+        double gj = 0.0, ghj = 0.0;               // reduced cost / phase-1 cost of my column
+
+        // ---- stage 1: rows order[0..n) of [A | b]; Gauss-Jordan to the inverse ----------------------------------------
+#pragma unroll
+        for (int q = 0; q < QR; ++q) {
+            const int t = t0 + q;
+            const bool have = t < n;
+            const int row = have ? order[t] : 0;
+            const double* Ar = Ag + (size_t)row * n + c0;
+#pragma unroll
+            for (int c = 0; c < QC; ++c) T[q][c] = (have && c0 + c < n) ? __ldg(Ar + c) : 0.0;
+            T[q][QC] = have ? __ldg(bg + row) : 0.0;
+            lamW[t] = 1.0;
+            ilamW[t] = 1.0;
+            if (warp == 0) rowvarS[t] = have ? row : -1;
+        }
+        gj = hascol ? __ldg(cg + col) : 0.0;
+        ghj = hascol ? 1.0 : 0.0;
+        bool colfree = hascol;                    // my column still holds a free x_j
+        if (tid < QROWS) cvsm[tid] = (tid < n) ? -1 : -2;
+        __syncthreads();
+
+        for (int t = 0; t < n; ++t) {
+            const int lt = t >> 2, qt = t & 3;
+            if (lane == lt) publish_slot(prow, T, qt);
+            __syncwarp();
+            // my warp's candidate: largest |entry| of row t among its free columns (lowest column on ties)
+            const double pl = (lane < QC) ? prow[lane] : 0.0;
+            unsigned long long kmin;
+            const unsigned long long key = colfree ? (unsigned long long)__double_as_longlong(fabs(pl)) : 0ull;
+            const int kkw = warp_argmin_key(~key, kmin);
+            const unsigned long long kabs = ~kmin;
+            const double pw = prow[kkw];
+            double e[QR], f[QR];
+            col_get4(T, kkw, e);
+            const double rpw = fast_rcp(kabs ? pw : 1.0);
+#pragma unroll
+            for (int q = 0; q < QR; ++q) f[q] = (t0 + q == t) ? 0.0 : e[q] * rpw;
+            store4(fS + ((size_t)buf * QW + warp) * QROWS + t0, f);
+            const double gkw = __shfl_sync(FULL, gj, kkw);
+            if (lane == 0) {
+                QCand* cd = candS + buf * QW + warp;
+                cd->key = ~kabs;                  // smallest complemented key = largest |pivot|
+                cd->k = c0 + kkw;
+                cd->p = pw;
+                cd->gk = gkw;
+            }
+            __syncthreads();
+            unsigned long long kbest;
+            const int wk = pick_min(buf, kbest);
+            if (__longlong_as_double((long long)~kbest) < kTolCrash) { need_generic = true; break; }
+            const QCand* cd = candS + buf * QW + wk;
+            const int k = cd->k;
+            const double p = cd->p, gk = cd->gk;
+            const double rp = fast_rcp(p);
+            load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
+            rank1(prow, f);
+            const double fg = gk * rp;
+            if (hascol) gj = (col == k) ? -fg : fma(-fg, pl, gj);
+            if (col == k) colfree = false;
+            if (warp == wk) {
+                double v[QR];
+#pragma unroll
+                for (int q = 0; q < QR; ++q) v[q] = (t0 + q == t) ? 1.0 : -f[q];
+                col_set4(T, k - c0, v);
+            }
+            if (lane == lt) {
+                lamW[t] = rp;
+                ilamW[t] = p;
+            }
+            if (tid == 0) {
+                pivcol[t] = k;
+                cvsm[k] = 0;
+            }
+            __syncwarp();                         // everybody is done with prow before the next row's owner overwrites it
+            buf ^= 1;
+            ++npiv_crash;
+        }
+
+        if (!need_generic) {
+            __syncthreads();
+            // dump D' (row of x_k stored at index k, true rows lam * T; slot QC of every block = the x-vertex) and the maps
+#pragma unroll
+            for (int q = 0; q < QR; ++q) {
+                const int t = t0 + q;
+                if (t < n) {
+                    const int k = pivcol[t];
+                    const double lam = lamW[t];
+                    double* dr = Dsm + (size_t)k * QDP + warp * QP;
+#pragma unroll
+                    for (int c = 0; c < QP; ++c) dr[c] = T[q][c] * lam;
+                    if (warp == 0) {
+                        colvar0[k] = rowvarS[t];
+                        cvsm[k] = rowvarS[t];
+                    }
+                }
+            }
+            __syncthreads();
+
+            // ---- stage 2: my rows of P_N = -A_N D, s_N = b_N - A_N xv ----------------------------------------------------
+            {
+                int rowq[QR];
+                bool liveq[QR];
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    liveq[q] = (t0 + q) < nN;
+                    rowq[q] = liveq[q] ? order[n + t0 + q] : 0;
+#pragma unroll
+                    for (int c = 0; c < QP; ++c) T[q][c] = 0.0;
+                }
+                if (t0 < nN) {                    // lanes beyond the live rows keep a zero tile
+                    double an[QR], av[QR];
+#pragma unroll
+                    for (int q = 0; q < QR; ++q) an[q] = liveq[q] ? __ldg(Ag + (size_t)rowq[q] * n) : 0.0;
+                    for (int k = 0; k < n; ++k) {
+#pragma unroll
+                        for (int q = 0; q < QR; ++q) {
+                            av[q] = an[q];
+                            an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (size_t)rowq[q] * n + k + 1) : 0.0;
+                        }
+                        rank1(Dsm + (size_t)k * QDP + warp * QP, av);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    if (liveq[q]) T[q][QC] += __ldg(bg + rowq[q]);
+                    lamW[t0 + q] = 1.0;
+                    ilamW[t0 + q] = 1.0;
+                    if (warp == 0) rowvarS[t0 + q] = liveq[q] ? rowq[q] : -1;
+                }
+            }
+            __syncthreads();
+
+            // ---- stage 3a: phase 1 (most negative slack leaves; ratio test along its row) ---------------------------------
+            for (;;) {
+                double lam[QR];
+                load4(lamW + t0, lam);
+                unsigned long long kloc = KEY_INF, kmin;
+                int qloc = 0;
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    const double s = lam[q] * T[q][QC];
+                    const unsigned long long kq = ((t0 + q) < nN && s < -kTolFeas) ? dkey(s) : KEY_INF;
+                    if (kq < kloc) { kloc = kq; qloc = q; }
+                }
+                const int ll = warp_argmin_key(kloc, kmin);
+                if (kmin == KEY_INF) break;                       // s >= 0 everywhere: phase 1 finished
+                if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const int qsel = __shfl_sync(FULL, qloc, ll);
+                const int r = QR * ll + qsel;
+                if (lane == ll) publish_slot(prow, T, qsel);
+                __syncwarp();
+                const double lam_r = lamW[r], il = ilamW[r];
+                // ratio test over my columns: min ghat_j / (-e_j) over e_j < -tol (true row lam_r * T_r)
+                const double pl = (lane < QC) ? prow[lane] : 0.0;
+                const double en = -lam_r * pl;
+                const bool ok = hascol && en > kTolPivot;
+                const double ratio = fmax(ghj, 0.0) * fast_rcp(ok ? en : 1.0);
+                unsigned long long kminc;
+                const int kl = warp_argmin_key(ok ? dkey(ratio) : KEY_INF, kminc);
+                const bool none = (kminc == KEY_INF);
+                const int kkw = none ? 0 : kl;
+                const double pw = prow[kkw];
+                const double rpw = fast_rcp(none ? 1.0 : pw);
+                double e[QR], f[QR];
+                col_get4(T, kkw, e);
+#pragma unroll
+                for (int q = 0; q < QR; ++q) f[q] = (t0 + q == r) ? 0.0 : e[q] * rpw;
+                store4(fS + ((size_t)buf * QW + warp) * QROWS + t0, f);
+                const double gkw = __shfl_sync(FULL, gj, kkw), ghkw = __shfl_sync(FULL, ghj, kkw);
+                if (lane == 0) {
+                    QCand* cd = candS + buf * QW + warp;
+                    cd->key = kminc;
+                    cd->k = c0 + kkw;
+                    cd->p = pw;
+                    cd->gk = gkw;
+                    cd->ghk = ghkw;
+                }
+                __syncthreads();
+                unsigned long long kbest;
+                const int wk = pick_min(buf, kbest);
+                if (kbest == KEY_INF) { status = ST_INFEASIBLE; break; }
+                const QCand* cd = candS + buf * QW + wk;
+                const int k = cd->k;
+                const double p = cd->p, gk = cd->gk, ghk = cd->ghk;
+                const double rp = fast_rcp(p);
+                load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
+                rank1(prow, f);
+                const double fv = ghk * rp, fg = gk * rp;
+                if (hascol) {
+                    ghj = (col == k) ? -fv * il : fma(-fv, pl, ghj);
+                    gj = (col == k) ? -fg * il : fma(-fg, pl, gj);
+                }
+                if (warp == wk) {
+                    double v[QR];
+#pragma unroll
+                    for (int q = 0; q < QR; ++q) v[q] = (t0 + q == r) ? il : -f[q] * il;
+                    col_set4(T, k - c0, v);
+                }
+                if (lane == ll) {
+                    lamW[r] = rp;
+                    ilamW[r] = p;
+                }
+                if (tid == ll) {                                  // warp 0's owner lane keeps the maps
+                    const int cv = cvsm[k];
+                    cvsm[k] = rowvarS[r];                         // the old slack becomes nonbasic in column k
+                    rowvarS[r] = cv;                              // column k's constraint becomes basic in row r
+                }
+                __syncwarp();
+                buf ^= 1;
+                ++npiv_p1;
+            }
+            __syncthreads();
+
+            // ---- stage 3b: phase 2 (Dantzig) ---------------------------------------------------------------------------
+            // every warp prices its own columns, runs the ratio test on its best column and leaves the multipliers of
+            // that pivot in fS; after the barrier all warps take the globally best column's record
+            auto speculate = [&]() {
+                unsigned long long kmin;
+                const int kl = warp_argmin_key(hascol ? dkey(gj) : KEY_INF, kmin);
+                const bool has = kmin < dkey(-kTolFeas);
+                const int kkw = has ? kl : 0;
+                double e[QR], lam[QR], f[QR];
+                col_get4(T, kkw, e);
+                load4(lamW + t0, lam);
+                unsigned long long kloc = KEY_INF, krow;
+                int qloc = 0;
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    const double et = lam[q] * e[q];                               // true entry / right-hand side of the row
+                    const double sc = fmax(lam[q] * T[q][QC], 0.0);
+                    const bool cand = (t0 + q) < nN && et > kTolPivot;
+                    const double ratio = sc * fast_rcp(cand ? et : 1.0);
+                    const unsigned long long kq = cand ? dkey(ratio) : KEY_INF;
+                    if (kq < kloc) { kloc = kq; qloc = q; }
+                }
+                const int ll = warp_argmin_key(kloc, krow);
+                const bool none = (krow == KEY_INF);
+                const int qsel = __shfl_sync(FULL, qloc, ll);
+                const int rw = none ? -1 : QR * ll + qsel;
+                const double pw = __shfl_sync(FULL, sel4(e, qsel), ll);
+                const double rpw = fast_rcp(none ? 1.0 : pw);
+#pragma unroll
+                for (int q = 0; q < QR; ++q) f[q] = (t0 + q == rw) ? 0.0 : e[q] * rpw;
+                store4(fS + ((size_t)buf * QW + warp) * QROWS + t0, f);
+                const double gkw = __shfl_sync(FULL, gj, kkw);
+                if (lane == 0) {
+                    QCand* cd = candS + buf * QW + warp;
+                    cd->key = has ? kmin : KEY_INF;
+                    cd->k = c0 + kkw;
+                    cd->r = rw;
+                    cd->p = pw;
+                    cd->gk = gkw;
+                }
+            };
+            if (status == ST_OPTIMAL) {
+                speculate();
+                __syncthreads();
+            }
+            while (status == ST_OPTIMAL) {
+                unsigned long long kbest;
+                const int wk = pick_min(buf, kbest);
+                if (kbest == KEY_INF) break;                       // g >= 0: optimal
+                const QCand* cd = candS + buf * QW + wk;
+                const int k = cd->k, r = cd->r;
+                if (r < 0) { status = ST_UNBOUNDED; break; }
+                if (npiv_p2 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
+                const double p = cd->p, gk = cd->gk;
+                const int ll = r >> 2, qsel = r & 3;
+                if (lane == ll) publish_slot(prow, T, qsel);
+                __syncwarp();
+                const double il = ilamW[r];
+                const double rp = fast_rcp(p);
+                double f[QR];
+                load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
+                rank1(prow, f);
+                const double pl = (lane < QC) ? prow[lane] : 0.0;
+                const double fg = gk * rp;
+                if (hascol) gj = (col == k) ? -fg * il : fma(-fg, pl, gj);
+                if (warp == wk) {
+                    double v[QR];
+#pragma unroll
+                    for (int q = 0; q < QR; ++q) v[q] = (t0 + q == r) ? il : -f[q] * il;
+                    col_set4(T, k - c0, v);
+                }
+                if (lane == ll) {
+                    lamW[r] = rp;
+                    ilamW[r] = p;
+                }
+                if (tid == ll) {
+                    const int cv = cvsm[k];
+                    cvsm[k] = rowvarS[r];
+                    rowvarS[r] = cv;
+                }
+                __syncwarp();
+                buf ^= 1;
+                ++npiv_p2;
+                speculate();
+                __syncthreads();
+            }
+        }
+
+        // ---- stage 4: x, objective, slacks, labels ------------------------------------------------------------------------
+        __syncthreads();
+        uint8_t* lab = a.labels + (size_t)lp * m;
+        int nact = 0, nties = 0, nviol = 0;
+        if (need_generic) {
+            status = -1;   // re-solved by the generic kernel (capi.cu)
+        } else if (status == ST_OPTIMAL) {
+            if (warp == 0) {
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    const int t = t0 + q;
+                    if (t < nN) {
+                        sval[t] = lamW[t] * T[q][QC];
+                        const int rv = rowvarS[t];
+                        if (rv >= 0) basic_tile[rv] = t;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int j = tid; j < n; j += QNT) {
+                const int bt = basic_tile[colvar0[j]];
+                sig[j] = (bt >= 0) ? sval[bt] : 0.0;
+            }
+            __syncthreads();
+            {
+                double sl[QCS];
+                int doff[QCS];
+#pragma unroll
+                for (int cs = 0; cs < QCS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    sl[cs] = (j < n) ? sig[j] : 0.0;
+                    const int jj = (j < n) ? j : 0;
+                    doff[cs] = (jj / QC) * QP + (jj % QC);
+                }
+                for (int k = warp; k < n; k += QW) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int cs = 0; cs < QCS; ++cs)
+                        if (lane + 32 * cs < n) acc = fma(Dsm[(size_t)k * QDP + doff[cs]], sl[cs], acc);
+                    acc = warp_sum(acc);
+                    if (lane == 0) xbuf[k] = Dsm[(size_t)k * QDP + QC] - acc;
+                }
+            }
+            __syncthreads();
+            double xl[QCS];
+#pragma unroll
+            for (int cs = 0; cs < QCS; ++cs) {
+                const int j = lane + 32 * cs;
+                xl[cs] = (j < n) ? xbuf[j] : 0.0;
+            }
+            if (warp == 0) {
+                double acc = 0.0;
+#pragma unroll
+                for (int cs = 0; cs < QCS; ++cs) {
+                    const int j = lane + 32 * cs;
+                    if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                }
+                acc = warp_sum(acc);
+                if (lane == 0 && a.obj) a.obj[lp] = acc;
+            }
+            if (a.x)
+                for (int j = tid; j < n; j += QNT) a.x[(size_t)lp * n + j] = xbuf[j];
+            // labels exactly as gurobi_lp.py:435-443 from the caller's A
+            row_dots(Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x
+            __syncthreads();
+            int nref = 0;
+            for (int i = tid; i < m; i += QNT) {
+                const double slack = __ldg(bg + i) - gbuf[i];
+                const double as = fabs(slack);
+                const int active = as <= a.thr;
+                lab[i] = (uint8_t)active;
+                nact += active;
+                int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
+                tie |= (active != (basic_tile[i] < 0));
+                nties += tie;
+                nviol += (slack < -a.thr);
+                nref += (basic_tile[i] < 0 && as > a.thr * 0.01);
+            }
+            // an active (nonbasic) row with a visible residual at this x: ill-conditioned vertex -> the generic kernel
+            // re-solves the instance with its step of iterative refinement
+            if (__syncthreads_or(nref > 0)) status = -1;
+        }
+        if (status != -1 && status != ST_OPTIMAL) {
+            for (int i = tid; i < m; i += QNT) lab[i] = 0;
+            if (a.x)
+                for (int j = tid; j < n; j += QNT) a.x[(size_t)lp * n + j] = 0.0;
+            if (tid == 0 && a.obj) a.obj[lp] = __longlong_as_double(0x7ff8000000000000ll);
+        }
+        nact = __reduce_add_sync(FULL, nact);
+        nties = __reduce_add_sync(FULL, nties);
+        nviol = __reduce_add_sync(FULL, nviol);
+        __syncthreads();
+        if (lane == 0) {
+            red[warp * 3 + 0] = nact;
+            red[warp * 3 + 1] = nties;
+            red[warp * 3 + 2] = nviol;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int s0 = 0, s1 = 0, s2 = 0;
+            for (int w = 0; w < QW; ++w) {
+                s0 += red[w * 3 + 0];
+                s1 += red[w * 3 + 1];
+                s2 += red[w * 3 + 2];
+            }
+            a.status[lp] = status;
+            if (status == -1) atomicAdd(a.flag_count, 1);
+            if (status != -1) {
+                if (a.n_active) a.n_active[lp] = s0;
+                if (a.ties) a.ties[lp] = s1;
+                if (a.violations) a.violations[lp] = s2;
+                if (a.pivots) {
+                    int* pv = a.pivots + (size_t)lp * 4;
+                    pv[0] = npiv_crash;
+                    pv[1] = npiv_p1;
+                    pv[2] = npiv_p2;
+                    pv[3] = npiv_crash + npiv_p1 + npiv_p2;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+bool quadcol_supported(int m, int n) { return n >= 1 && n <= QNMAX && m >= n && m - n <= QROWS && m <= QMMAX; }
+
+static int quadcol_ctas_per_sm() {
+    static int per_sm = -1;
+    if (per_sm < 0) {
+        int v = 0;
+        if (cudaFuncSetAttribute(simplex_quadcol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_TOTAL) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, simplex_quadcol_kernel, QNT, Q_TOTAL) != cudaSuccess)
+            v = 0;
+        per_sm = v;
+    }
+    return per_sm;
+}
+
+cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st) {
+    const int per_sm = quadcol_ctas_per_sm();
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    long long grid = (long long)sm_count * per_sm;
+    if (grid > a.B) grid = a.B;
+    simplex_quadcol_kernel<<<(int)grid, QNT, Q_TOTAL, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace ddb
