@@ -24,6 +24,8 @@ bool regtile_supported(int m, int n);
 cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_t st);
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
 bool quadcol_supported(int m, int n);
+int quadcol_grid(int sm_count);
+size_t quadcol_scratch_bytes(int grid);
 cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st);
 #ifdef DDB_EXPERIMENTS   // `make experiments`: the measured negative results of round 1, not in the shipped library
 bool tile2d_supported(int m, int n);
@@ -463,6 +465,7 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         const long long fgrid = generic_grid(ctx, m, n, fplan, B);
         size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count)
                                    : (which == 1 ? ddb::rowreg_rows_scratch_bytes(m, n, grid) : 0);
+        if (which == 4) need = ddb::quadcol_scratch_bytes(ddb::quadcol_grid(ctx->sm_count));
         const size_t fneed = generic_scratch_bytes(ctx, m, n, fplan, B);
         if (fneed > need) need = fneed;
         const size_t need_d = (which == 1) ? ddb::rowreg_d_scratch_bytes(m, n, grid) : 0;

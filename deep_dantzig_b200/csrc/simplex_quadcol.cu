@@ -24,6 +24,7 @@
 // Covers n <= 100, m - n <= 128 without row masks; instances it cannot finish (singular static crash basis,
 // ill-conditioned vertex) are flagged status = -1 and re-solved by the generic kernel on the device (capi.cu).
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -42,7 +43,7 @@ constexpr int QDP = QW * QP;          // pitch of a row of D in shared memory
 constexpr int QCS = 4;                // column slots of the lane-distributed vectors of stages 0 and 4 (j = lane + 32 cs)
 
 struct QCand {                        // one per (buffer, warp): the warp's speculative candidate
-    unsigned long long key;           // crash: bits of |pivot|; phase 1: dkey(ratio); phase 2: dkey(g_k); KEY_INF / 0 = none
+    unsigned long long unused;        // (the keys live in their own packed array keyS)
     int k;                            // entering column
     int r;                            // phase 2: leaving tile row (-1: column unblocked)
     double p;                         // pivot entry (stored scale)
@@ -58,7 +59,8 @@ constexpr size_t Q_D = 0;
 constexpr size_t Q_PROW = Q_D + qalign((size_t)QNMAX * QDP * 8);
 constexpr size_t Q_F = Q_PROW + qalign((size_t)QW * QP * 8);
 constexpr size_t Q_CAND = Q_F + qalign((size_t)2 * QW * QROWS * 8);
-constexpr size_t Q_LAM = Q_CAND + qalign((size_t)2 * QW * sizeof(QCand));
+constexpr size_t Q_KEYS = Q_CAND + qalign((size_t)2 * QW * sizeof(QCand));
+constexpr size_t Q_LAM = Q_KEYS + qalign((size_t)2 * QW * 8);
 constexpr size_t Q_ILAM = Q_LAM + qalign((size_t)QW * QROWS * 8);
 constexpr size_t Q_SVAL = Q_ILAM + qalign((size_t)QW * QROWS * 8);
 constexpr size_t Q_SIG = Q_SVAL + qalign((size_t)QROWS * 8);
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
     double* prowS = reinterpret_cast<double*>(smem_raw + Q_PROW);      // [QW][QP]: a warp's slice of the current pivot row
     double* fS = reinterpret_cast<double*>(smem_raw + Q_F);            // [2][QW][QROWS]: speculative multipliers
     QCand* candS = reinterpret_cast<QCand*>(smem_raw + Q_CAND);        // [2][QW]
+    unsigned long long* keyS = reinterpret_cast<unsigned long long*>(smem_raw + Q_KEYS);   // [2][QW]: the candidates' keys, packed
     double* lamS = reinterpret_cast<double*>(smem_raw + Q_LAM);        // [QW][QROWS]: per-warp copy of the lazy row scales
     double* ilamS = reinterpret_cast<double*>(smem_raw + Q_ILAM);      // [QW][QROWS]: 1 / lam
     double* sval = reinterpret_cast<double*>(smem_raw + Q_SVAL);
@@ -187,8 +190,8 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         reinterpret_cast<double2*>(p)[1] = make_double2(v[2], v[3]);
     };
     // dot products of the rows of A with a lane-distributed vector, eight rows per warp in flight
-    auto row_dots = [&](const double* Ag, const double (&vl)[QCS], double* out1, double* out2) {
-        constexpr int RB = 8;
+    auto row_dots = [&](auto rbt, const double* Ag, const double (&vl)[QCS], double* out1, double* out2) {
+        constexpr int RB = decltype(rbt)::value;
         for (int base = 0; base < m; base += RB * QW) {
             double v[RB][QCS];
 #pragma unroll
@@ -220,15 +223,13 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
     };
     // winner of the four candidates of buffer b: smallest key, lowest warp on ties
     auto pick_min = [&](int b, unsigned long long& kbest) -> int {
-        const QCand* cd = candS + b * QW;
-        int w = 0;
-        kbest = cd[0].key;
-#pragma unroll
-        for (int q = 1; q < QW; ++q) {
-            const unsigned long long kq = cd[q].key;
-            if (kq < kbest) { kbest = kq; w = q; }
-        }
-        return w;
+        const ulonglong2 k01 = reinterpret_cast<const ulonglong2*>(keyS + b * QW)[0];
+        const ulonglong2 k23 = reinterpret_cast<const ulonglong2*>(keyS + b * QW)[1];
+        const bool b1 = k01.y < k01.x, b3 = k23.y < k23.x;
+        const unsigned long long ka = b1 ? k01.y : k01.x, kb = b3 ? k23.y : k23.x;
+        const bool bb = kb < ka;
+        kbest = bb ? kb : ka;
+        return bb ? (b3 ? 3 : 2) : (b1 ? 1 : 0);
     };
 
     for (;;) {
@@ -248,7 +249,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const int j = lane + 32 * cs;
                 cl[cs] = (j < n) ? __ldg(cg + j) : 0.0;
             }
-            row_dots(Ag, cl, gbuf, gnn);
+            row_dots(std::integral_constant<int, 8>{}, Ag, cl, gbuf, gnn);
         }
         __syncthreads();
         for (int i = tid; i < m; i += QNT) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             const double gkw = __shfl_sync(FULL, gj, kkw);
             if (lane == 0) {
                 QCand* cd = candS + buf * QW + warp;
-                cd->key = ~kabs;                  // smallest complemented key = largest |pivot|
+                keyS[buf * QW + warp] = ~kabs;    // smallest complemented key = largest |pivot|
                 cd->k = c0 + kkw;
                 cd->p = pw;
                 cd->gk = gkw;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const double gkw = __shfl_sync(FULL, gj, kkw), ghkw = __shfl_sync(FULL, ghj, kkw);
                 if (lane == 0) {
                     QCand* cd = candS + buf * QW + warp;
-                    cd->key = kminc;
+                    keyS[buf * QW + warp] = kminc;
                     cd->k = c0 + kkw;
                     cd->p = pw;
                     cd->gk = gkw;
@@ -497,19 +498,22 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 double e[QR], lam[QR], f[QR];
                 col_get4(T, kkw, e);
                 load4(lamW + t0, lam);
-                unsigned long long kloc = KEY_INF, krow;
+                const double pinf = __longlong_as_double(0x7ff0000000000000ll);
+                double rbest = pinf;
+                unsigned long long krow;
                 int qloc = 0;
 #pragma unroll
                 for (int q = 0; q < QR; ++q) {
                     const double et = lam[q] * e[q];                               // true entry / right-hand side of the row
-                    const double sc = fmax(lam[q] * T[q][QC], 0.0);
+                    const double sr = lam[q] * T[q][QC];
+                    const double sc = (sr > 0.0) ? sr : 0.0;
                     const bool cand = (t0 + q) < nN && et > kTolPivot;
-                    const double ratio = sc * fast_rcp(cand ? et : 1.0);
-                    const unsigned long long kq = cand ? dkey(ratio) : KEY_INF;
-                    if (kq < kloc) { kloc = kq; qloc = q; }
+                    const double ratio = cand ? sc * fast_rcp(cand ? et : 1.0) : pinf;
+                    if (ratio < rbest) { rbest = ratio; qloc = q; }
                 }
-                const int ll = warp_argmin_key(kloc, krow);
-                const bool none = (krow == KEY_INF);
+                // ratios are >= +0: their bit patterns order like the values (same winner as with dkey)
+                const int ll = warp_argmin_key((unsigned long long)__double_as_longlong(rbest), krow);
+                const bool none = (krow == 0x7ff0000000000000ull);
                 const int qsel = __shfl_sync(FULL, qloc, ll);
                 const int rw = none ? -1 : QR * ll + qsel;
                 const double pw = __shfl_sync(FULL, sel4(e, qsel), ll);
@@ -520,7 +524,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const double gkw = __shfl_sync(FULL, gj, kkw);
                 if (lane == 0) {
                     QCand* cd = candS + buf * QW + warp;
-                    cd->key = has ? kmin : KEY_INF;
+                    keyS[buf * QW + warp] = has ? kmin : KEY_INF;
                     cd->k = c0 + kkw;
                     cd->r = rw;
                     cd->p = pw;
@@ -619,42 +623,107 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             }
             __syncthreads();
             double xl[QCS];
-#pragma unroll
-            for (int cs = 0; cs < QCS; ++cs) {
-                const int j = lane + 32 * cs;
-                xl[cs] = (j < n) ? xbuf[j] : 0.0;
-            }
-            if (warp == 0) {
-                double acc = 0.0;
+            auto take_x = [&]() {
 #pragma unroll
                 for (int cs = 0; cs < QCS; ++cs) {
                     const int j = lane + 32 * cs;
-                    if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                    xl[cs] = (j < n) ? xbuf[j] : 0.0;
                 }
-                acc = warp_sum(acc);
-                if (lane == 0 && a.obj) a.obj[lp] = acc;
+                if (warp == 0) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int cs = 0; cs < QCS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                    }
+                    acc = warp_sum(acc);
+                    if (lane == 0 && a.obj) a.obj[lp] = acc;
+                }
+                if (a.x)
+                    for (int j = tid; j < n; j += QNT) a.x[(size_t)lp * n + j] = xbuf[j];
+            };
+            // labels exactly as gurobi_lp.py:435-443 from the caller's A; returns whether an active (nonbasic) row has a
+            // visible residual at this x
+            auto label_pass = [&]() -> int {
+                row_dots(std::integral_constant<int, 2>{}, Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x (two rows in flight: the tile is alive)
+                __syncthreads();
+                nact = 0; nties = 0; nviol = 0;
+                int nref = 0;
+                for (int i = tid; i < m; i += QNT) {
+                    const double slack = __ldg(bg + i) - gbuf[i];
+                    const double as = fabs(slack);
+                    const int active = as <= a.thr;
+                    lab[i] = (uint8_t)active;
+                    nact += active;
+                    int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
+                    tie |= (active != (basic_tile[i] < 0));
+                    nties += tie;
+                    nviol += (slack < -a.thr);
+                    nref += (basic_tile[i] < 0 && as > a.thr * 0.01);
+                }
+                return nref;
+            };
+            take_x();
+            const int nref = label_pass();
+            if (__syncthreads_or(nref > 0)) {
+                // ---- one step of iterative refinement on the final active set (ill-conditioned vertex, ~0.06 % of the instances;
+                // same scheme as rowreg_kernel.cuh / simplex_generic.cu).  rho_j = slack of the nonbasic constraint of column j
+                // at the computed x; it should be 0: move the nonbasic slacks from rho to 0 through the tableau -- the tile is
+                // still in the registers (the label pass streams A two rows at a time), a row's dot product with rho is four per-warp partial sums -- and correct x through
+                // the crash inverse.
+                double* rho = gnn;            // the crash scores are dead by now
+                int* colpos = order;          // so is the crash order: constraint -> column where its slack is nonbasic
+                double* part = fS;            // [QW][QROWS]
+                for (int j = tid; j < QNMAX; j += QNT) {
+                    double rv = 0.0;
+                    if (j < n) {
+                        const int q = cvsm[j];
+                        rv = __ldg(bg + q) - gbuf[q];
+                        colpos[q] = j;
+                    }
+                    rho[j] = rv;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int q = 0; q < QR; ++q) {
+                    double d = 0.0;
+#pragma unroll
+                    for (int c = 0; c < QC; ++c) d = fma(T[q][c], rho[c0 + c], d);
+                    part[warp * QROWS + t0 + q] = d;
+                }
+                __syncthreads();
+                if (tid < nN)
+                    sval[tid] = lamS[tid] * (((part[tid] + part[QROWS + tid]) + part[2 * QROWS + tid]) + part[3 * QROWS + tid]);
+                __syncthreads();
+                for (int j0 = tid; j0 < n; j0 += QNT) {
+                    const int q0 = colvar0[j0];
+                    const int bt = basic_tile[q0];
+                    sig[j0] = (bt >= 0) ? sval[bt] : -rho[colpos[q0]];
+                }
+                __syncthreads();
+                {
+                    double sl[QCS];
+                    int doff[QCS];
+#pragma unroll
+                    for (int cs = 0; cs < QCS; ++cs) {
+                        const int j = lane + 32 * cs;
+                        sl[cs] = (j < n) ? sig[j] : 0.0;
+                        const int jj = (j < n) ? j : 0;
+                        doff[cs] = (jj / QC) * QP + (jj % QC);
+                    }
+                    for (int k = warp; k < n; k += QW) {
+                        double acc = 0.0;
+#pragma unroll
+                        for (int cs = 0; cs < QCS; ++cs)
+                            if (lane + 32 * cs < n) acc = fma(Dsm[(size_t)k * QDP + doff[cs]], sl[cs], acc);
+                        acc = warp_sum(acc);
+                        if (lane == 0) xbuf[k] -= acc;
+                    }
+                }
+                __syncthreads();
+                take_x();
+                label_pass();
             }
-            if (a.x)
-                for (int j = tid; j < n; j += QNT) a.x[(size_t)lp * n + j] = xbuf[j];
-            // labels exactly as gurobi_lp.py:435-443 from the caller's A
-            row_dots(Ag, xl, gbuf, nullptr);          // gbuf[i] = a_i . x
-            __syncthreads();
-            int nref = 0;
-            for (int i = tid; i < m; i += QNT) {
-                const double slack = __ldg(bg + i) - gbuf[i];
-                const double as = fabs(slack);
-                const int active = as <= a.thr;
-                lab[i] = (uint8_t)active;
-                nact += active;
-                int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
-                tie |= (active != (basic_tile[i] < 0));
-                nties += tie;
-                nviol += (slack < -a.thr);
-                nref += (basic_tile[i] < 0 && as > a.thr * 0.01);
-            }
-            // an active (nonbasic) row with a visible residual at this x: ill-conditioned vertex -> the generic kernel
-            // re-solves the instance with its step of iterative refinement
-            if (__syncthreads_or(nref > 0)) status = -1;
         }
         if (status != -1 && status != ST_OPTIMAL) {
             for (int i = tid; i < m; i += QNT) lab[i] = 0;
@@ -700,6 +769,9 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 
 }  // namespace
 
+size_t quadcol_scratch_bytes(int grid) { return (size_t)grid * QNT * QR * QC * sizeof(double); }
+int quadcol_grid(int sm_count);
+
 bool quadcol_supported(int m, int n) { return n >= 1 && n <= QNMAX && m >= n && m - n <= QROWS && m <= QMMAX; }
 
 static int quadcol_ctas_per_sm() {
@@ -712,6 +784,11 @@ static int quadcol_ctas_per_sm() {
         per_sm = v;
     }
     return per_sm;
+}
+
+int quadcol_grid(int sm_count) {
+    const int per_sm = quadcol_ctas_per_sm();
+    return sm_count * (per_sm > 0 ? per_sm : 1);
 }
 
 cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st) {

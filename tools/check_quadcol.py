@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from deep_dantzig_b200 import solver, _lib
 
-shapes = [(200, 100, 4096), (50, 20, 2048), (150, 100, 1024), (228, 100, 512), (125, 100, 512), (100, 50, 1024), (300, 100 - 0, 0)]
+shapes = [(200, 100, 32768), (50, 20, 2048), (150, 100, 1024), (228, 100, 512), (125, 100, 512), (100, 50, 1024), (300, 100 - 0, 0)]
 if len(sys.argv) > 3:
     shapes = [(int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]))]
 ctx = _lib.context(0)

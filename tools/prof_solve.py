@@ -8,6 +8,9 @@ m = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 1184
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
+if len(sys.argv) > 5:
+    from deep_dantzig_b200 import _lib
+    _lib.context(0).set_solve_plan(int(sys.argv[5]))
 A, b, c = solver.generate(42, 0, B, m, n)
 out = solver._alloc_outputs(B, m, n, A.device)
 for _ in range(1 + reps):
