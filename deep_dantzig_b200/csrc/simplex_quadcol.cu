@@ -40,6 +40,7 @@ constexpr int QROWS = 32 * QR;        // tile rows
 constexpr int QNMAX = QW * QC;        // columns
 constexpr int QMMAX = 256;            // constraints (order / score arrays)
 constexpr int QDP = QW * QP;          // pitch of a row of D in shared memory
+constexpr unsigned long long QINF = 0x7ff0000000000000ull;   // bit pattern of +inf: "no candidate" among non-negative ratios
 constexpr int QCS = 4;                // column slots of the lane-distributed vectors of stages 0 and 4 (j = lane + 32 cs)
 
 struct QCand {                        // one per (buffer, warp): the warp's speculative candidate
@@ -384,16 +385,18 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     for (int c = 0; c < QP; ++c) T[q][c] = 0.0;
                 }
                 if (t0 < nN) {                    // lanes beyond the live rows keep a zero tile
-                    double an[QR], av[QR];
+                    {
+                        double an[QR], av[QR];
 #pragma unroll
-                    for (int q = 0; q < QR; ++q) an[q] = liveq[q] ? __ldg(Ag + (size_t)rowq[q] * n) : 0.0;
-                    for (int k = 0; k < n; ++k) {
+                        for (int q = 0; q < QR; ++q) an[q] = liveq[q] ? __ldg(Ag + (size_t)rowq[q] * n) : 0.0;
+                        for (int k = 0; k < n; ++k) {
 #pragma unroll
-                        for (int q = 0; q < QR; ++q) {
-                            av[q] = an[q];
-                            an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (size_t)rowq[q] * n + k + 1) : 0.0;
+                            for (int q = 0; q < QR; ++q) {
+                                av[q] = an[q];
+                                an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (size_t)rowq[q] * n + k + 1) : 0.0;
+                            }
+                            rank1(Dsm + (size_t)k * QDP + warp * QP, av);
                         }
-                        rank1(Dsm + (size_t)k * QDP + warp * QP, av);
                     }
                 }
 #pragma unroll
@@ -410,15 +413,17 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             for (;;) {
                 double lam[QR];
                 load4(lamW + t0, lam);
-                unsigned long long kloc = KEY_INF, kmin;
+                // (rows beyond the live ones hold zeros: they are never candidates, here or in the ratio tests)
+                double sbest = 0.0;
+                unsigned long long kmin;
                 int qloc = 0;
 #pragma unroll
                 for (int q = 0; q < QR; ++q) {
                     const double s = lam[q] * T[q][QC];
-                    const unsigned long long kq = ((t0 + q) < nN && s < -kTolFeas) ? dkey(s) : KEY_INF;
-                    if (kq < kloc) { kloc = kq; qloc = q; }
+                    if (s < -kTolFeas && s < sbest) { sbest = s; qloc = q; }
                 }
-                const int ll = warp_argmin_key(kloc, kmin);
+                // dkey of a negative number is the complement of its bit pattern
+                const int ll = warp_argmin_key(sbest < 0.0 ? ~(unsigned long long)__double_as_longlong(sbest) : KEY_INF, kmin);
                 if (kmin == KEY_INF) break;                       // s >= 0 everywhere: phase 1 finished
                 if (npiv_p1 >= a.max_iter) { status = ST_ITERATION_LIMIT; break; }
                 const int qsel = __shfl_sync(FULL, qloc, ll);
@@ -430,10 +435,10 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const double pl = (lane < QC) ? prow[lane] : 0.0;
                 const double en = -lam_r * pl;
                 const bool ok = hascol && en > kTolPivot;
-                const double ratio = fmax(ghj, 0.0) * fast_rcp(ok ? en : 1.0);
-                unsigned long long kminc;
-                const int kl = warp_argmin_key(ok ? dkey(ratio) : KEY_INF, kminc);
-                const bool none = (kminc == KEY_INF);
+                const double ratio = (ghj > 0.0 ? ghj : 0.0) * fast_rcp(ok ? en : 1.0);
+                unsigned long long kminc;                          // ratios are >= +0: bit patterns order like the values
+                const int kl = warp_argmin_key(ok ? (unsigned long long)__double_as_longlong(ratio) : QINF, kminc);
+                const bool none = (kminc == QINF);
                 const int kkw = none ? 0 : kl;
                 const double pw = prow[kkw];
                 const double rpw = fast_rcp(none ? 1.0 : pw);
@@ -454,7 +459,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 __syncthreads();
                 unsigned long long kbest;
                 const int wk = pick_min(buf, kbest);
-                if (kbest == KEY_INF) { status = ST_INFEASIBLE; break; }
+                if (kbest == QINF) { status = ST_INFEASIBLE; break; }
                 const QCand* cd = candS + buf * QW + wk;
                 const int k = cd->k;
                 const double p = cd->p, gk = cd->gk, ghk = cd->ghk;
@@ -507,13 +512,13 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     const double et = lam[q] * e[q];                               // true entry / right-hand side of the row
                     const double sr = lam[q] * T[q][QC];
                     const double sc = (sr > 0.0) ? sr : 0.0;
-                    const bool cand = (t0 + q) < nN && et > kTolPivot;
+                    const bool cand = et > kTolPivot;
                     const double ratio = cand ? sc * fast_rcp(cand ? et : 1.0) : pinf;
                     if (ratio < rbest) { rbest = ratio; qloc = q; }
                 }
                 // ratios are >= +0: their bit patterns order like the values (same winner as with dkey)
                 const int ll = warp_argmin_key((unsigned long long)__double_as_longlong(rbest), krow);
-                const bool none = (krow == 0x7ff0000000000000ull);
+                const bool none = (krow == QINF);
                 const int qsel = __shfl_sync(FULL, qloc, ll);
                 const int rw = none ? -1 : QR * ll + qsel;
                 const double pw = __shfl_sync(FULL, sel4(e, qsel), ll);
