@@ -298,6 +298,10 @@ extern "C" int ddb_device_info(ddb_ctx* ctx, int* sm_count, int* cc_major, int* 
 extern "C" int64_t ddb_launch_count(ddb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 static int auto_plan(const ddb_ctx* ctx, int m, int n) {
+    // column-block-per-warp register kernel: measured faster than the row-per-thread kernel wherever that one needs its
+    // 101-column variants (n >= 72): 1.17x at (144,72) ... 1.27x at (200,100), 1.30x at (228,100); slower below (0.96x at (120,60))
+    static const bool no_quadcol = [] { const char* e = getenv("DDB_NO_QUADCOL"); return e && e[0] == '1'; }();
+    if (!no_quadcol && n >= 72 && ddb::quadcol_supported(m, n)) return 7;
     if (ddb::rowreg_supported(m, n) || ddb::regtile_supported(m, n)) return 0;
     if ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) return 1;
     static const bool no_cluster = [] { const char* e = getenv("DDB_NO_CLUSTER"); return e && e[0] == '1'; }();
@@ -788,7 +792,7 @@ static int fused_launch(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int6
     const bool inkernel = (mode == 1);
     const int plan = ddb_solve_plan(ctx, m, n);
     if (plan < 0) return plan;
-    if (inkernel && plan == 0 && ctx->forced_plan < 0 && ddb::rowreg_gen_supported(m, n) &&
+    if (inkernel && (plan == 0 || plan == 7) && ctx->forced_plan < 0 && ddb::rowreg_gen_supported(m, n) &&
         (!keep || ((reinterpret_cast<uintptr_t>(A_out) | reinterpret_cast<uintptr_t>(c_out)) & 15) == 0)) {
         GenSpec g{key, first_instance, density};
         return solve_launch(ctx, B, m, n, keep ? A_out : nullptr, keep ? b_out : nullptr, keep ? c_out : nullptr, threshold,

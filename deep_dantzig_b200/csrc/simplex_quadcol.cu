@@ -50,7 +50,8 @@ struct QCand {                        // one per (buffer, warp): the warp's spec
     double p;                         // pivot entry (stored scale)
     double gk;                        // g[k]
     double ghk;                       // ghat[k] (phase 1)
-    double pad[3];
+    double rp;                        // 1 / p as the producer computed it
+    double pad[2];
 };
 static_assert(sizeof(QCand) == 64, "candidate record");
 
@@ -224,10 +225,14 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
     };
     // winner of the four candidates of buffer b: smallest key, lowest warp on ties
     auto pick_min = [&](int b, unsigned long long& kbest) -> int {
-        const ulonglong2 k01 = reinterpret_cast<const ulonglong2*>(keyS + b * QW)[0];
-        const ulonglong2 k23 = reinterpret_cast<const ulonglong2*>(keyS + b * QW)[1];
-        const bool b1 = k01.y < k01.x, b3 = k23.y < k23.x;
-        const unsigned long long ka = b1 ? k01.y : k01.x, kb = b3 ? k23.y : k23.x;
+        // (opaque loads: otherwise the compiler proves the keys warp-uniform and runs the comparisons on the uniform
+        //  datapath -- 32 instructions with R2UR round trips instead of 12)
+        unsigned long long k0, k1, k2, k3;
+        const uint32_t ka32 = smem_u32(keyS + b * QW);
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k0), "=l"(k1) : "r"(ka32));
+        asm volatile("ld.shared.v2.u64 {%0, %1}, [%2+16];" : "=l"(k2), "=l"(k3) : "r"(ka32));
+        const bool b1 = k1 < k0, b3 = k3 < k2;
+        const unsigned long long ka = b1 ? k1 : k0, kb = b3 ? k3 : k2;
         const bool bb = kb < ka;
         kbest = bb ? kb : ka;
         return bb ? (b3 ? 3 : 2) : (b1 ? 1 : 0);
@@ -320,6 +325,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 cd->k = c0 + kkw;
                 cd->p = pw;
                 cd->gk = gkw;
+                cd->rp = rpw;
             }
             __syncthreads();
             unsigned long long kbest;
@@ -328,7 +334,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             const QCand* cd = candS + buf * QW + wk;
             const int k = cd->k;
             const double p = cd->p, gk = cd->gk;
-            const double rp = fast_rcp(p);
+            const double rp = cd->rp;
             load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
             rank1(prow, f);
             const double fg = gk * rp;
@@ -387,13 +393,17 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 if (t0 < nN) {                    // lanes beyond the live rows keep a zero tile
                     {
                         double an[QR], av[QR];
+                        int offq[QR];
 #pragma unroll
-                        for (int q = 0; q < QR; ++q) an[q] = liveq[q] ? __ldg(Ag + (size_t)rowq[q] * n) : 0.0;
+                        for (int q = 0; q < QR; ++q) {
+                            offq[q] = rowq[q] * n;
+                            an[q] = liveq[q] ? __ldg(Ag + offq[q]) : 0.0;
+                        }
                         for (int k = 0; k < n; ++k) {
 #pragma unroll
                             for (int q = 0; q < QR; ++q) {
                                 av[q] = an[q];
-                                an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (size_t)rowq[q] * n + k + 1) : 0.0;
+                                an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (offq[q] + k + 1)) : 0.0;
                             }
                             rank1(Dsm + (size_t)k * QDP + warp * QP, av);
                         }
@@ -435,7 +445,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const double pl = (lane < QC) ? prow[lane] : 0.0;
                 const double en = -lam_r * pl;
                 const bool ok = hascol && en > kTolPivot;
-                const double ratio = (ghj > 0.0 ? ghj : 0.0) * fast_rcp(ok ? en : 1.0);
+                const double ratio = ((__double_as_longlong(ghj) < 0) ? 0.0 : ghj) * fast_rcp(ok ? en : 1.0);
                 unsigned long long kminc;                          // ratios are >= +0: bit patterns order like the values
                 const int kl = warp_argmin_key(ok ? (unsigned long long)__double_as_longlong(ratio) : QINF, kminc);
                 const bool none = (kminc == QINF);
@@ -455,6 +465,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     cd->p = pw;
                     cd->gk = gkw;
                     cd->ghk = ghkw;
+                    cd->rp = rpw;
                 }
                 __syncthreads();
                 unsigned long long kbest;
@@ -463,7 +474,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 const QCand* cd = candS + buf * QW + wk;
                 const int k = cd->k;
                 const double p = cd->p, gk = cd->gk, ghk = cd->ghk;
-                const double rp = fast_rcp(p);
+                const double rp = cd->rp;
                 load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
                 rank1(prow, f);
                 const double fv = ghk * rp, fg = gk * rp;
@@ -511,7 +522,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 for (int q = 0; q < QR; ++q) {
                     const double et = lam[q] * e[q];                               // true entry / right-hand side of the row
                     const double sr = lam[q] * T[q][QC];
-                    const double sc = (sr > 0.0) ? sr : 0.0;
+                    const double sc = (__double_as_longlong(sr) < 0) ? 0.0 : sr;     // max(sr, 0) without the NaN handling of fmax
                     const bool cand = et > kTolPivot;
                     const double ratio = cand ? sc * fast_rcp(cand ? et : 1.0) : pinf;
                     if (ratio < rbest) { rbest = ratio; qloc = q; }
@@ -534,6 +545,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     cd->r = rw;
                     cd->p = pw;
                     cd->gk = gkw;
+                    cd->rp = rpw;
                 }
             };
             if (status == ST_OPTIMAL) {
@@ -553,7 +565,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 if (lane == ll) publish_slot(prow, T, qsel);
                 __syncwarp();
                 const double il = ilamW[r];
-                const double rp = fast_rcp(p);
+                const double rp = cd->rp;
                 double f[QR];
                 load4(fS + ((size_t)buf * QW + wk) * QROWS + t0, f);
                 rank1(prow, f);

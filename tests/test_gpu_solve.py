@@ -514,15 +514,16 @@ def test_dropin_dataset_and_linprog(cuda_device):
 _EXPERIMENTS = os.environ.get('DDB_EXPERIMENTS') == '1'      # `make -C deep_dantzig_b200/csrc experiments` build loaded
 
 
-@pytest.mark.parametrize('plan0', [0, 4] + ([3, 5] if _EXPERIMENTS else []))
+@pytest.mark.parametrize('plan0', [0, 4, 7] + ([3, 5] if _EXPERIMENTS else []))
 @pytest.mark.parametrize('m,n,N', [(10, 5, 300), (50, 20, 300), (100, 50, 100), (200, 100, 200)])
 def test_register_resident_and_generic_kernels_agree(cuda_device, m, n, N, plan0):
-    """The register-resident kernels (0: row per thread -- hybrid register + shared-memory rows at (200,100) --, 4: warp-tiled;
+    """The register-resident kernels (0: row per thread -- hybrid register + shared-memory rows at (200,100) --, 4: warp-tiled,
+    7: rows over lanes and columns over warps, the default from n = 72;
     with DDB_EXPERIMENTS=1 also the measured negative results 3: 2-D register tile, 5: software-pipelined rows) and plan 1
     (tableau in shared memory) implement the same algorithm: same statuses, labels and pivot path."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
-    assert ctx.solve_plan(m, n) == 0
+    assert ctx.solve_plan(m, n) == (7 if n >= 72 else 0)
     A, b, c = _numpy_batch(m, n, [17 + 3 * i for i in range(N)])
     dA, db, dc = _dev(A, b, c)
     try:
@@ -553,7 +554,10 @@ def test_fused_in_kernel_generator_is_bit_identical(cuda_device):
             for (m, n, B, dens) in [(200, 100, 700, 1.0), (50, 20, 3000, 1.0), (150, 100, 300, 0.5), (64, 32, 500, 1.0),
                                     (125, 100, 900, 0.1), (75, 20, 1000, 1.0)]:
                 A, b, c = solver.generate(5150, 100, B, m, n, density=dens)
+                if mode == 1:
+                    ctx.set_solve_plan(0)        # the in-solver generator lives in the row-per-thread kernel: compare with that kernel
                 want = _to_np(solver.solve_label(A, b, c))
+                ctx.set_solve_plan(-1)
                 keep = solver.generate_solve_label(5150, 100, B, m, n, density=dens, keep_instances=True)
                 assert (keep['A'] == A).all() and (keep['b'] == b).all() and (keep['c'] == c).all()
                 lean = _to_np(solver.generate_solve_label(5150, 100, B, m, n, density=dens))
@@ -567,6 +571,7 @@ def test_fused_in_kernel_generator_is_bit_identical(cuda_device):
                     assert np.all(eq), (mode, m, n, k, 'tail')
     finally:
         ctx.set_fused_mode(0)
+        ctx.set_solve_plan(-1)
     # odd n: the two-kernel fallback, same contract
     r = _to_np(solver.generate_solve_label(9, 0, 200, 33, 17))
     A, b, c = solver.generate(9, 0, 200, 33, 17)

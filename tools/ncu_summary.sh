@@ -8,7 +8,7 @@ HERE=$(cd "$(dirname "$0")/.." && pwd)
   python $HERE/tools/ncu_brief.py $REP $UNITS $UNIT $ALG
   echo
   echo "## stall samples by source line (outer attribution), top 30"
-  mkdir -p /tmp/sass && cd /tmp/sass && rm -f *.cubin && cuobjdump -xelf all $BIN >/dev/null 2>&1 && nvdisasm -gi -c *.cubin > all.dis 2>/dev/null
+  mkdir -p /tmp/sass && cd /tmp/sass && rm -f *.cubin && cuobjdump -xelf all $BIN >/dev/null 2>&1 && for f in *.cubin; do nvdisasm -gi -c $f 2>/dev/null; done > all.dis
   python - "$SYM" <<'PY'
 import sys
 sym=sys.argv[1]
