@@ -18,7 +18,8 @@ class DdbError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, _LIB_NAME)
+    # DDB200_LIBRARY: development switch (A/B builds of the library); the shipped path is the in-tree libddb200.so
+    return os.environ.get('DDB200_LIBRARY') or os.path.join(_HERE, _LIB_NAME)
 
 
 _lock = threading.Lock()

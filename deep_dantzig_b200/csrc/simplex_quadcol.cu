@@ -131,6 +131,44 @@ __device__ __forceinline__ double sel4(const double (&v)[QR], int q) {
     return (q & 2) ? b : a;
 }
 
+// Sums of RB per-lane values over the warp with a halving butterfly: RB - 1 + (5 - log2 RB) shuffles instead of 5 RB.  The
+// addition tree of every sum is the xor-16, 8, 4, 2, 1 tree of warp_sum (fp addition is commutative), so the results are
+// bitwise the same.  The lane ends up with the sum of value  rsel = its lane bits 4.. (RB = 8: bits 4, 3, 2; RB = 2: bit 4).
+template <int RB>
+__device__ __forceinline__ double reduce_rows(const double (&v)[RB], int lane, int& rsel) {
+    static_assert(RB == 8 || RB == 2, "batch sizes of row_dots");
+    double w1;
+    if constexpr (RB == 8) {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        double w4[4], w2[2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double send = b4 ? v[j] : v[j + 4], keep = b4 ? v[j + 4] : v[j];
+            w4[j] = keep + __shfl_xor_sync(FULL, send, 16);
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const double send = b3 ? w4[j] : w4[j + 2], keep = b3 ? w4[j + 2] : w4[j];
+            w2[j] = keep + __shfl_xor_sync(FULL, send, 8);
+        }
+        {
+            const double send = b2 ? w2[0] : w2[1], keep = b2 ? w2[1] : w2[0];
+            w1 = keep + __shfl_xor_sync(FULL, send, 4);
+        }
+        rsel = (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0);
+    } else {
+        const bool b4 = lane & 16;
+        const double send = b4 ? v[0] : v[1], keep = b4 ? v[1] : v[0];
+        w1 = keep + __shfl_xor_sync(FULL, send, 16);
+        w1 += __shfl_xor_sync(FULL, w1, 8);
+        w1 += __shfl_xor_sync(FULL, w1, 4);
+        rsel = b4 ? 1 : 0;
+    }
+    w1 += __shfl_xor_sync(FULL, w1, 2);
+    w1 += __shfl_xor_sync(FULL, w1, 1);
+    return w1;
+}
+
 __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Dsm = reinterpret_cast<double*>(smem_raw + Q_D);           // [n][QW][QP]: crash inverse, x-vertex in slot QC of every block
@@ -205,22 +243,28 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     v[r][cs] = (i < m && j < n) ? __ldg(Ag + (size_t)i * n + j) : 0.0;
                 }
             }
+            double dot[RB], nn[RB];
 #pragma unroll
             for (int r = 0; r < RB; ++r) {
-                const int i = base + r * QW + warp;
-                double dot = 0.0, nn = 0.0;
+                dot[r] = 0.0;
+                nn[r] = 0.0;
 #pragma unroll
                 for (int cs = 0; cs < QCS; ++cs) {
-                    dot = fma(v[r][cs], vl[cs], dot);
-                    nn = fma(v[r][cs], v[r][cs], nn);
-                }
-                dot = warp_sum(dot);
-                if (out2) nn = warp_sum(nn);
-                if (lane == 0 && i < m) {
-                    out1[i] = dot;
-                    if (out2) out2[i] = nn;
+                    dot[r] = fma(v[r][cs], vl[cs], dot[r]);
+                    nn[r] = fma(v[r][cs], v[r][cs], nn[r]);
                 }
             }
+            // all RB row sums with one halving butterfly (same addition tree as warp_sum, so the same bits): afterwards the
+            // lane holds the sum of row  rsel  of the batch
+            int rsel;
+            const double d1 = reduce_rows<RB>(dot, lane, rsel);
+            const int i = base + rsel * QW + warp;
+            const bool writer = (lane & (RB == 8 ? 3 : 15)) == 0;      // one lane per row of the batch
+            if (out2) {
+                const double n1 = reduce_rows<RB>(nn, lane, rsel);
+                if (writer && i < m) out2[i] = n1;
+            }
+            if (writer && i < m) out1[i] = d1;
         }
     };
     // winner of the four candidates of buffer b: smallest key, lowest warp on ties
@@ -390,23 +434,24 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 #pragma unroll
                     for (int c = 0; c < QP; ++c) T[q][c] = 0.0;
                 }
+                // (staging A_N through shared memory -- one 32-byte sector per row and chunk, two LDS.128 per column instead of
+                //  four scattered 8-byte loads -- was measured: 578 k against 604 k LP/s; the per-chunk barriers cost more than
+                //  the loads, which the other LP of the SM hides)
                 if (t0 < nN) {                    // lanes beyond the live rows keep a zero tile
-                    {
-                        double an[QR], av[QR];
-                        int offq[QR];
+                    double an[QR], av[QR];
+                    int offq[QR];
+#pragma unroll
+                    for (int q = 0; q < QR; ++q) {
+                        offq[q] = rowq[q] * n;
+                        an[q] = liveq[q] ? __ldg(Ag + offq[q]) : 0.0;
+                    }
+                    for (int k = 0; k < n; ++k) {
 #pragma unroll
                         for (int q = 0; q < QR; ++q) {
-                            offq[q] = rowq[q] * n;
-                            an[q] = liveq[q] ? __ldg(Ag + offq[q]) : 0.0;
+                            av[q] = an[q];
+                            an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (offq[q] + k + 1)) : 0.0;
                         }
-                        for (int k = 0; k < n; ++k) {
-#pragma unroll
-                            for (int q = 0; q < QR; ++q) {
-                                av[q] = an[q];
-                                an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (offq[q] + k + 1)) : 0.0;
-                            }
-                            rank1(Dsm + (size_t)k * QDP + warp * QP, av);
-                        }
+                        rank1(Dsm + (size_t)k * QDP + warp * QP, av);
                     }
                 }
 #pragma unroll
@@ -812,6 +857,9 @@ cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_
     const int per_sm = quadcol_ctas_per_sm();
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     long long grid = (long long)sm_count * per_sm;
+    // DDB_QUADCOL_ONE_PER_SM=1: measurement switch (one LP per SM: how much of the throughput is latency hiding between LPs)
+    static const bool one = [] { const char* e = getenv("DDB_QUADCOL_ONE_PER_SM"); return e && e[0] == '1'; }();
+    if (one) grid = sm_count;
     if (grid > a.B) grid = a.B;
     simplex_quadcol_kernel<<<(int)grid, QNT, Q_TOTAL, st>>>(a);
     return cudaGetLastError();
