@@ -255,6 +255,46 @@ def test_cluster_kernel_agrees_with_the_streamed_plan(cuda_device, m, n, N):
         assert np.abs(r6['obj'][ok] - r2['obj'][ok]).max() <= 1e-9 * np.abs(r2['obj'][ok]).max()
 
 
+@pytest.mark.parametrize('m,n,N,density', [(200, 100, 3000, 1.0), (228, 100, 400, 1.0), (100, 100, 300, 1.0), (101, 100, 300, 1.0),
+                                           (173, 87, 400, 1.0), (144, 72, 400, 1.0), (151, 75, 300, 1.0), (90, 30, 500, 1.0),
+                                           (12, 5, 300, 1.0), (200, 100, 600, 0.5), (150, 100, 400, 0.1), (228, 100, 300, 0.1)])
+def test_column_block_kernel_agrees_with_row_per_thread(cuda_device, m, n, N, density):
+    """Plan 7 (rows over lanes, columns over warps; the automatic choice for 72 <= n <= 100) runs the algorithm of plan 0 with the
+    same arithmetic per tableau entry: same statuses, labels, ties and PIVOT COUNTS on every instance, x / objective to 1e-9
+    (in practice to the last bits) -- at its largest tile (m - n = 128), with no live rows (m = n), at odd and small n, and on
+    sparse instances, where singular static crash bases are flagged by both kernels and re-solved by the generic one."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    assert ctx.solve_plan(m, n) == (7 if n >= 72 else 0)
+    dA, db, dc = solver.generate(9001, 0, N, m, n, density=density)
+    try:
+        ctx.set_solve_plan(7)
+        r7 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(0)
+        r0 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    for k in ('status', 'labels', 'n_active', 'ties', 'violations', 'pivots'):
+        assert (r7[k] == r0[k]).all(), k
+    assert set(np.unique(r7['status'])) <= {2, 3, 5}
+    ok = r7['status'] == 2
+    if ok.any():
+        assert np.abs(r7['x'][ok] - r0['x'][ok]).max() <= 1e-9 * np.abs(r0['x'][ok]).max()
+        assert np.abs(r7['obj'][ok] - r0['obj'][ok]).max() <= 1e-9 * np.abs(r0['obj'][ok]).max()
+    # a row mask sends the call to the row-per-thread kernel: same answer as forcing plan 0
+    if m > n + 8:
+        mask = torch.ones(N, m, dtype=torch.uint8, device=dA.device)
+        mask[:, -4:] = 0
+        try:
+            ctx.set_solve_plan(7)
+            q7 = _to_np(solver.solve_label(dA, db, dc, row_mask=mask))
+            ctx.set_solve_plan(0)
+            q0 = _to_np(solver.solve_label(dA, db, dc, row_mask=mask))
+        finally:
+            ctx.set_solve_plan(-1)
+        assert (q7['status'] == q0['status']).all() and (q7['labels'] == q0['labels']).all()
+
+
 def test_plans_agree_bit_for_bit(cuda_device):
     """shared-memory and global-memory tableau kernels run the same arithmetic."""
     from deep_dantzig_b200 import solver, _lib
