@@ -86,6 +86,7 @@ __global__ void __launch_bounds__(256) generate_fused_kernel(uint64_t key, long 
     extern __shared__ double gsm[];
     double* x0s = gsm;                       // [n]
     double* tile = gsm + ((n + 1) & ~1);     // [kGenRows][n]
+    double* eps = tile + (size_t)kGenRows * n;   // [m]: |eps_i|, drawn up front by all threads, one Box-Muller pair per two rows
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const int half = n / 2;                  // pairs per row
     for (long long k = blockIdx.x; k < B; k += gridDim.x) {
@@ -98,6 +99,14 @@ __global__ void __launch_bounds__(256) generate_fused_kernel(uint64_t key, long 
             normal_pair(key, inst, STREAM_C, (uint32_t)pr, z0, z1);
             c[k * n + 2 * pr] = fabs(z0);
             c[k * n + 2 * pr + 1] = fabs(z1);
+        }
+        // (round 2: this used to be one pair per ROW drawn by lane 0 of the row's warp inside the accumulation loop --
+        //  200 warp-wide calls per instance instead of 100 / 32, 30 % of the kernel's instructions)
+        for (int pr = tid; pr < (m + 1) / 2; pr += blockDim.x) {
+            double z0, z1;
+            normal_pair(key, inst, STREAM_EPS, (uint32_t)pr, z0, z1);
+            eps[2 * pr] = fabs(z0);
+            if (2 * pr + 1 < m) eps[2 * pr + 1] = fabs(z1);
         }
         double* Ak = A + k * (long long)m * n;
         for (int r0 = 0; r0 < m; r0 += kGenRows) {
@@ -123,11 +132,7 @@ __global__ void __launch_bounds__(256) generate_fused_kernel(uint64_t key, long 
                 double acc = 0.0;
                 for (int j = lane; j < n; j += 32) acc = fma(tile[ri * n + j], x0s[j], acc);
                 acc = warp_sum(acc);
-                if (lane == 0) {
-                    double z0, z1;
-                    normal_pair(key, inst, STREAM_EPS, (uint32_t)(i >> 1), z0, z1);
-                    b[k * m + i] = acc + fabs((i & 1) ? z1 : z0);
-                }
+                if (lane == 0) b[k * m + i] = acc + eps[i];
             }
         }
         if (x0out)
@@ -139,7 +144,7 @@ __global__ void __launch_bounds__(256) generate_fused_kernel(uint64_t key, long 
 cudaError_t launch_generate(uint64_t key, long long first, long long B, int m, int n, double density, double* A,
                             double* b, double* c, double* x0, int sm_count, cudaStream_t st, int* launches) {
     // even n, 16-byte aligned A: the fused one-pass kernel (A written once and never read back)
-    const size_t fsm = ((size_t)((n + 1) & ~1) + (size_t)kGenRows * n) * sizeof(double);
+    const size_t fsm = ((size_t)((n + 1) & ~1) + (size_t)kGenRows * n + (size_t)((m + 1) & ~1)) * sizeof(double);
     if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0 && fsm <= 200 * 1024) {
         cudaError_t e0 = cudaFuncSetAttribute(generate_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm);
         if (e0 != cudaSuccess) return e0;
