@@ -48,6 +48,7 @@ SIGNATURES = {
                                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_s2v_param_count': (C.c_int, [C.c_int, C.c_int]),
     'ddb_s2v_forward_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'ddb_s2v_forward_flags_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_s2v_loss_grad_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                         C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     'ddb_s2v_metrics_dev': (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp]),

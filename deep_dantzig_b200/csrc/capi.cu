@@ -912,9 +912,28 @@ extern "C" int ddb_s2v_param_count(int graph, int p) {
     return DDB_EINVAL;
 }
 
+static int s2v_forward_impl(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A, const double* b,
+                            const double* c, const float* params, const uint8_t* row_ineq, const uint8_t* row_bound, float* logp,
+                            float* probs, void* stream);
+
 extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
                                    const double* b, const double* c, const float* params, float* logp, float* probs,
                                    void* stream) {
+    return s2v_forward_impl(ctx, graph, B, m, n, p, T, A, b, c, params, nullptr, nullptr, logp, probs, stream);
+}
+
+extern "C" int ddb_s2v_forward_flags_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
+                                         const double* b, const double* c, const float* params, const uint8_t* row_ineq,
+                                         const uint8_t* row_bound, float* logp, float* probs, void* stream) {
+    if (graph == 1 && ((row_ineq == nullptr) != (row_bound == nullptr)))
+        return fail(DDB_EINVAL, "ddb_s2v_forward_flags_dev: bipartite items carry both row flags or none");
+    return s2v_forward_impl(ctx, graph, B, m, n, p, T, A, b, c, params, row_ineq, graph == 1 ? row_bound : nullptr, logp, probs,
+                            stream);
+}
+
+static int s2v_forward_impl(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A, const double* b,
+                            const double* c, const float* params, const uint8_t* row_ineq, const uint8_t* row_bound, float* logp,
+                            float* probs, void* stream) {
     if (!ctx || !A || !b || !c || !params || !logp) return fail(DDB_EINVAL, "ddb_s2v_forward_dev: NULL argument");
     if (graph != 0 && graph != 1) return fail(DDB_EINVAL, "ddb_s2v_forward_dev: Graph not recognised (%d)", graph);
     if (B < 0 || m < 1 || n < 1 || p < 1 || T < 0)
@@ -933,10 +952,12 @@ extern "C" int ddb_s2v_forward_dev(ddb_ctx* ctx, int graph, int64_t B, int m, in
     a.error_flag = err; a.store_A = 0;
     a.gram = nullptr; a.gram_pitch = 0;
     a.inst_flag = nullptr; a.flag_count = nullptr; a.only_flagged = 0;
+    a.row_ineq = row_ineq; a.row_bound = row_bound;
     // bipartite variant: dense instances (the reference's distribution) go through the HBM-streaming kernel; it flags
-    // instances with zero coefficients and the general kernel below then processes exactly those
+    // instances with zero coefficients and the general kernel below then processes exactly those.  Items with row flags
+    // (MPS / PLNN: equality rows, bound rows -- sparse by nature) go to the general kernel directly.
     static const bool no_dense = [] { const char* e = getenv("DDB_S2V_NO_DENSE"); return e && e[0] == '1'; }();
-    if (graph == 1 && !no_dense && ddb::s2v_bipartite_dense_supported(m, n, p, A, ctx->smem_optin)) {
+    if (graph == 1 && !no_dense && !row_ineq && ddb::s2v_bipartite_dense_supported(m, n, p, A, ctx->smem_optin)) {
         const size_t need = (size_t)B * sizeof(int);
         if (need > ctx->s2vflag.cap) CUDA_TRY(cudaStreamSynchronize(st));
         int rc = ensure(ctx->s2vflag, need);

@@ -66,6 +66,11 @@ struct S2vArgs {
     int* inst_flag;            // bipartite: [B] set to 1 by the dense kernel for instances with a zero coefficient
     int* flag_count;           // number of flagged instances
     int only_flagged;          // general bipartite kernel: process only instances whose inst_flag is 1
+    // node flags of items that are not plain random LPs (MPS / PLNN items: equality rows, bound rows), [B, m] 0 / 1, nullable:
+    //   bipartite: c_feats[:, 0] = is_inequality (default 1), c_feats[:, 2] = is_bound (default 0)   (gurobi_lp.py:157-158)
+    //   complete : node_features of the row nodes = is_inequality (default 1)                        (gurobi_lp.py:329, 360)
+    const uint8_t* row_ineq;
+    const uint8_t* row_bound;
 };
 
 // ---------------------------------------------------------------------------------------------------------

@@ -299,7 +299,9 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
                 const int l = e / NP, q = e - l * NP;
                 float val = __ldg(t0 + l);
                 if (q < m) {
-                    val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
+                    const float fi = a.row_ineq ? (float)a.row_ineq[(size_t)lp * m + q] : 1.f;
+                    const float fb = a.row_bound ? (float)a.row_bound[(size_t)lp * m + q] : 0.f;
+                    val += __ldg(t1c + 4 * l) * fi + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 2) * fb + __ldg(t1c + 4 * l + 3) * cosv[q];
                     val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
                 } else {
                     const int j = q - m;
@@ -350,9 +352,11 @@ __global__ void __launch_bounds__(256) s2v_bipartite_kernel(S2vArgs a) {
                     }
                 }
             }
-            const float f0 = 1.f, f1 = rb[i], f3 = cosv[i];   // c_feats = [is_inequality, rhs', is_bound = 0, cosine]
-            s0 += __ldg(t8 + 2 * p) * f0 + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 3) * f3;
-            s1 += __ldg(t8 + W8 + 2 * p) * f0 + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 3) * f3;
+            // c_feats = [is_inequality, rhs', is_bound, cosine]  (flags: 1 / 0 on random LPs, per row on MPS / PLNN items)
+            const float f0 = a.row_ineq ? (float)a.row_ineq[(size_t)lp * m + i] : 1.f, f1 = rb[i];
+            const float f2 = a.row_bound ? (float)a.row_bound[(size_t)lp * m + i] : 0.f, f3 = cosv[i];
+            s0 += __ldg(t8 + 2 * p) * f0 + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 2) * f2 + __ldg(t8 + 2 * p + 3) * f3;
+            s1 += __ldg(t8 + W8 + 2 * p) * f0 + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 2) * f2 + __ldg(t8 + W8 + 2 * p + 3) * f3;
             const float mx = fmaxf(s0, s1);
             const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
             float* lo = a.logp + ((size_t)lp * m + i) * 2;
@@ -576,24 +580,27 @@ __global__ void __launch_bounds__(256) s2v_complete_kernel(S2vArgs a) {
                                 for (int r = 0; r < 4; ++r) acc[q][r] = fmaf(wr[r], xq[q], acc[q][r]);
                         }
                     }
-                    float wpq[4], wnq[4];
+                    float wpq[4], wnq[4], nfq[4];      // nfq: node feature of the row node (1 = inequality row; s2v.py:100 u1 = t0 + t1 feat)
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         const int i = 4 * ng + q;
                         wpq[q] = (i < m) ? Wp[i] : 0.f;
                         wnq[q] = (i < m) ? Wn[i] : 0.f;
+                        nfq[q] = (a.row_ineq && i < m) ? (float)a.row_ineq[(size_t)lp * m + i] : 1.f;
                     }
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const int l = 4 * kg + r;
                         if (l < p) {
-                            const float add = __ldg(t0 + l) + __ldg(t1 + l) + scal[0] + (t > 0 ? y1[l] : 0.f);
+                            const float t0l = __ldg(t0 + l), t1l = __ldg(t1 + l), y1l = (t > 0 ? y1[l] : 0.f);
+                            const float add = t0l + t1l + scal[0] + y1l;          // every row an inequality (random LPs)
                             const float cp = w3p[l], cn = w3n[l];
                             float o[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
                                 const int i = 4 * ng + q;
-                                o[q] = (i < m) ? fmaxf(acc[q][r] + add + cp * wpq[q] + cn * wnq[q], 0.f) : 0.f;
+                                const float addq = a.row_ineq ? ((t0l + t1l * nfq[q]) + scal[0]) + y1l : add;
+                                o[q] = (i < m) ? fmaxf(acc[q][r] + addq + cp * wpq[q] + cn * wnq[q], 0.f) : 0.f;
                             }
                             *reinterpret_cast<float4*>(mu_nxt + l * MP + 4 * ng) = make_float4(o[0], o[1], o[2], o[3]);
                         }

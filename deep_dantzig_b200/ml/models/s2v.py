@@ -82,7 +82,9 @@ class Model(nn.Module):
             return self.forward_batch_torch(A, b, c)
         return self.forward_batch_cuda(A, b, c)
 
-    def forward_batch_cuda(self, A, b, c):
+    def forward_batch_cuda(self, A, b, c, feats=None):
+        """CUDA forward.  ``feats`` = node flags of MPS / PLNN items (see ``forward_batch_torch``): they go to
+        ``ddb_s2v_forward_flags_dev`` as uint8 [B,m] arrays."""
         if not (A.is_cuda and b.is_cuda and c.is_cuda):
             raise _lib.DdbError('the classifier forward kernel needs CUDA tensors; there is no CPU fallback')
         B, m, n = A.shape
@@ -94,9 +96,17 @@ class Model(nn.Module):
         logp = torch.empty(B, m, 2, dtype=torch.float32, device=dev)
         probs = torch.empty(B, m, 2, dtype=torch.float32, device=dev)
         vp = lambda t: C.c_void_p(t.data_ptr())
-        rc = ctx.lib.ddb_s2v_forward_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
-                                         vp(params), vp(logp), vp(probs),
-                                         C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if feats is None:
+            rc = ctx.lib.ddb_s2v_forward_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
+                                             vp(params), vp(logp), vp(probs),
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        else:
+            fl = (feats, None) if torch.is_tensor(feats) else feats
+            ineq = fl[0].to(device=dev).reshape(B, m).ne(0).to(torch.uint8).contiguous()
+            bound = None if fl[1] is None else fl[1].to(device=dev).reshape(B, m).ne(0).to(torch.uint8).contiguous()
+            rc = ctx.lib.ddb_s2v_forward_flags_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
+                                                   vp(params), vp(ineq), vp(bound) if bound is not None else None,
+                                                   vp(logp), vp(probs), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, 'ddb_s2v_forward_dev')
         self.probs = probs
         return logp
@@ -265,10 +275,13 @@ class Model(nn.Module):
         if feats is None:
             logp = self.forward_batch(A.to(dev), b.to(dev), c.to(dev))
         else:
-            # MPS / PLNN items (equality rows, bound rows): the batched torch restatement with the item's node flags --
-            # library kernels; the hand-written CUDA kernels cover the random-LP flags only
+            # MPS / PLNN items (equality rows, bound rows): the same CUDA kernels with the item's node flags
+            # (ddb_s2v_forward_flags_dev); the differentiable torch restatement only while autograd is recording
             feats = feats.to(dev) if torch.is_tensor(feats) else tuple(f.to(dev) for f in feats)
-            logp = self.forward_batch_torch(A.to(dev), b.to(dev), c.to(dev), feats)
+            if self.force_torch or (torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters())):
+                logp = self.forward_batch_torch(A.to(dev), b.to(dev), c.to(dev), feats)
+            else:
+                logp = self.forward_batch_cuda(A.to(dev), b.to(dev), c.to(dev), feats)
         in_loss = [int(q) for q in item['in_loss']]
         self.probs = self.probs[0, in_loss]
         return logp[0, in_loss]

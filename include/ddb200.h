@@ -153,6 +153,15 @@ int ddb_s2v_param_count(int graph, int p);
 int ddb_s2v_forward_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p, int T,
                         const double *A, const double *b, const double *c, const float *params,
                         float *logp, float *probs, void *stream);
+/* The same forward for items that are not plain random LPs -- MPS / PLNN items (src/data/gurobi_lp.py:127-187, 326-366)
+ * with equality rows and bound rows: row_ineq[B,m], row_bound[B,m] (0 / 1) are the per-row node flags the reference keeps
+ * in c_feats[:, 0] (is_inequality) and c_feats[:, 2] (is_bound) of a bipartite item, row_ineq alone the node_features of
+ * the row nodes of a complete item (row_bound is ignored for graph 0).  NULL flags = the random-LP values (1 and 0), i.e.
+ * ddb_s2v_forward_dev.  Bipartite items carry both flags or none; they run on the general-adjacency kernel. */
+int ddb_s2v_forward_flags_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p, int T,
+                              const double *A, const double *b, const double *c, const float *params,
+                              const uint8_t *row_ineq, const uint8_t *row_bound,
+                              float *logp, float *probs, void *stream);
 
 /*
  * (5) CLASSIFIER LOSS + GRADIENT -- replaces the per-instance accumulation loop of train_net

@@ -348,3 +348,58 @@ def test_training_trajectory_matches_the_reference_loop(cuda_device, golden_dir,
     for k, v in model.named_parameters():
         want = g['final_' + k]
         assert np.abs(v.detach().cpu().numpy() - want).max() <= 2e-3 * max(1.0, np.abs(want).max()), k
+
+
+def test_flagged_items_run_on_the_cuda_kernels(cuda_device, golden_dir):
+    """MPS / PLNN items -- equality rows, bound rows, 0 / 1 node features -- through Model.forward on the GPU: the CUDA kernels
+    with the item's row flags (ddb_s2v_forward_flags_dev) against the outputs of the UNMODIFIED reference model
+    (tests/golden/s2v_plnn_items.npz), and against the torch restatement on a larger random sparse batch."""
+    from deep_dantzig_b200.ml.models.s2v import Model
+    from deep_dantzig_b200 import _lib
+    g = np.load(os.path.join(golden_dir, 's2v_plnn_items.npz'))
+    ctx = _lib.context(0)
+    for ci in range(int(g['ncases'])):
+        pre = 'bip%d_' % ci
+        m, n, p, T = [int(v) for v in g[pre + 'dims']]
+        A = g[pre + 'A']
+        idx = [[i, j] for i in range(m) for j in range(n) if A[i, j] != 0]
+        item = {'c_feats': torch.from_numpy(g[pre + 'c_feats'].copy()), 'v_feats': torch.from_numpy(g[pre + 'v_feats']),
+                'e_feats': {'i': idx, 'coeffs': [float(A[i, j]) for i, j in idx]}, 'in_loss': [int(q) for q in g[pre + 'in_loss']],
+                'dims': {'m': m, 'n': n}}
+        model = Model('bipartite', p, T, on_cuda=True, verbose_init=False)
+        model.load_state_dict({k[len(pre) + 6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + 'param_')})
+        model.cuda()
+        n0 = ctx.launch_count()
+        with torch.no_grad():
+            got = model.forward(item).cpu().numpy()
+        assert ctx.launch_count() > n0, 'the item did not go through the C ABI'
+        assert got.shape == g[pre + 'logp'].shape and np.abs(got - g[pre + 'logp']).max() <= 5e-5
+        pre = 'cmp%d_' % ci
+        item = {'A': torch.from_numpy(g[pre + 'A']).unsqueeze(0), 'b': torch.from_numpy(g[pre + 'b']).unsqueeze(0),
+                'c': torch.from_numpy(g[pre + 'c']).unsqueeze(0), 'node_features': torch.from_numpy(g[pre + 'node_features']).unsqueeze(0),
+                'in_loss': [int(q) for q in g[pre + 'in_loss']]}
+        model = Model('complete', p, T, on_cuda=True, verbose_init=False)
+        model.load_state_dict({k[len(pre) + 6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(pre + 'param_')})
+        model.cuda()
+        n0 = ctx.launch_count()
+        with torch.no_grad():
+            got = model.forward(item).cpu().numpy()
+        assert ctx.launch_count() > n0
+        assert got.shape == g[pre + 'logp'].shape and np.abs(got - g[pre + 'logp']).max() <= 5e-5
+    # batched, larger shapes: random sparse instances with random row flags, both graphs, kernels against the restatement
+    from deep_dantzig_b200 import solver
+    gen = torch.Generator(device='cuda').manual_seed(5)
+    for graph, (B, m, n, p, T) in (('bipartite', (48, 60, 24, 16, 3)), ('complete', (48, 60, 24, 16, 2)), ('bipartite', (6, 200, 100, 40, 3)),
+                                   ('complete', (6, 200, 100, 40, 3))):
+        A, b, c = solver.generate(31, 0, B, m, n, density=0.3)
+        ineq = (torch.rand(B, m, device='cuda', generator=gen) < 0.7).float()
+        bound = (torch.rand(B, m, device='cuda', generator=gen) < 0.2).float()
+        feats = (ineq, bound) if graph == 'bipartite' else ineq
+        torch.manual_seed(11)
+        model = Model(graph, p, T, on_cuda=True, verbose_init=False)
+        with torch.no_grad():
+            want = model.forward_batch_torch(A, b, c, feats)
+            wprobs = model.probs
+            got = model.forward_batch_cuda(A, b, c, feats)
+        assert (got - want).abs().max().item() <= 5e-5 + 1e-5 * want.abs().max().item(), (graph, m, n)
+        assert (model.probs - wprobs).abs().max().item() <= 5e-5
