@@ -51,6 +51,8 @@ SIGNATURES = {
     'ddb_s2v_forward_flags_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'ddb_s2v_loss_grad_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp,
                                         C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
+    'ddb_s2v_loss_grad_flags_dev': (C.c_int, [_vp, C.c_int, _i64, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                              C.c_float, C.c_float, _vp, _vp, _vp, _vp]),
     'ddb_s2v_metrics_dev': (C.c_int, [_vp, _i64, _vp, _vp, _vp, C.c_float, C.c_float, C.c_float, _vp, _vp]),
     'ddb_launch_count': (_i64, [_vp]),
 }

@@ -81,6 +81,8 @@ struct S2vGGradArgs {
     float w0, w1;
     float* grad;
     double* loss;
+    const uint8_t* row_ineq;
+    const uint8_t* row_bound;
     const int* inst_flag;
     const int* flag_count;
     float* scratch;
@@ -100,6 +102,7 @@ struct S2vCGradArgs {
     int gram_pitch;
     const float* params;
     const uint8_t* labels;
+    const uint8_t* row_ineq;
     float w0, w1;
     float* grad;
     double* loss;
@@ -996,9 +999,32 @@ static int s2v_forward_impl(ddb_ctx* ctx, int graph, int64_t B, int m, int n, in
 // ---------------------------------------------------------------------------------------------------------
 // classifier loss + gradient (training step of the reference: src/ml/train.py:59-66, criterion src/benchmark.py:70-75)
 // ---------------------------------------------------------------------------------------------------------
+static int s2v_loss_grad_impl(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A, const double* b,
+                              const double* c, const float* params, const uint8_t* labels, const uint8_t* row_ineq,
+                              const uint8_t* row_bound, float w0, float w1, float* grad, double* loss, int32_t* not_dense,
+                              void* stream);
+
 extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
                                      const double* b, const double* c, const float* params, const uint8_t* labels,
                                      float w0, float w1, float* grad, double* loss, int32_t* not_dense, void* stream) {
+    return s2v_loss_grad_impl(ctx, graph, B, m, n, p, T, A, b, c, params, labels, nullptr, nullptr, w0, w1, grad, loss, not_dense,
+                              stream);
+}
+
+extern "C" int ddb_s2v_loss_grad_flags_dev(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A,
+                                           const double* b, const double* c, const float* params, const uint8_t* labels,
+                                           const uint8_t* row_ineq, const uint8_t* row_bound, float w0, float w1, float* grad,
+                                           double* loss, int32_t* not_dense, void* stream) {
+    if (graph == 1 && ((row_ineq == nullptr) != (row_bound == nullptr)))
+        return fail(DDB_EINVAL, "ddb_s2v_loss_grad_flags_dev: bipartite items carry both row flags or none");
+    return s2v_loss_grad_impl(ctx, graph, B, m, n, p, T, A, b, c, params, labels, row_ineq, graph == 1 ? row_bound : nullptr, w0, w1,
+                              grad, loss, not_dense, stream);
+}
+
+static int s2v_loss_grad_impl(ddb_ctx* ctx, int graph, int64_t B, int m, int n, int p, int T, const double* A, const double* b,
+                              const double* c, const float* params, const uint8_t* labels, const uint8_t* row_ineq,
+                              const uint8_t* row_bound, float w0, float w1, float* grad, double* loss, int32_t* not_dense,
+                              void* stream) {
     if (!ctx || !A || !b || !c || !params || !labels || !grad || !loss || !not_dense)
         return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: NULL argument");
     if (graph != 0 && graph != 1) return fail(DDB_EINVAL, "ddb_s2v_loss_grad_dev: Graph not recognised (%d)", graph);
@@ -1026,7 +1052,7 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
         ddb::S2vCGradArgs g;
         g.B = B; g.m = m; g.p = p; g.T = T;
         g.gram = (const float*)ctx->gram.p; g.gram_pitch = (int)(ddb::s2v_gram_out_floats(m) / 3);
-        g.params = params; g.labels = labels; g.w0 = w0; g.w1 = w1; g.grad = grad; g.loss = loss;
+        g.params = params; g.labels = labels; g.row_ineq = row_ineq; g.w0 = w0; g.w1 = w1; g.grad = grad; g.loss = loss;
         const char* why = "";
         cudaError_t e = ddb::launch_s2v_complete_grad(g, ctx->sm_count, ctx->smem_optin, st, &why);
         if (e != cudaSuccess) {
@@ -1053,7 +1079,7 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
     CUDA_TRY(cudaMemsetAsync(a.inst_flag, 0, need_flag, st));
     const char* why = "";
     static const bool no_dense_grad = [] { const char* e = getenv("DDB_S2V_NO_DENSE"); return e && e[0] == '1'; }();
-    bool all_general = no_dense_grad;
+    bool all_general = no_dense_grad || row_ineq != nullptr;      // items with row flags: the general-adjacency kernel takes them all
     if (!all_general) {
         cudaError_t e = ddb::launch_s2v_bipartite_grad(a, npar, ctx->sm_count, ctx->smem_optin, st, &why);
         if (e == cudaErrorInvalidValue && why[0]) {
@@ -1069,6 +1095,7 @@ extern "C" int ddb_s2v_loss_grad_dev(ddb_ctx* ctx, int graph, int64_t B, int m, 
     g.B = B; g.m = m; g.n = n; g.p = p; g.T = T;
     g.A = A; g.b = b; g.c = c; g.params = params; g.labels = labels; g.w0 = w0; g.w1 = w1;
     g.grad = grad; g.loss = loss;
+    g.row_ineq = row_ineq; g.row_bound = row_bound;
     g.inst_flag = all_general ? nullptr : a.inst_flag;
     g.flag_count = all_general ? nullptr : a.inst_flag + B;
     g.scratch = (float*)ctx->s2vgscr.p;

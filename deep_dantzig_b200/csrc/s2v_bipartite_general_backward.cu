@@ -29,6 +29,8 @@ struct S2vGGradArgs {
     float w0, w1;
     float* grad;
     double* loss;
+    const uint8_t* row_ineq;   // [B, m] node flags of MPS / PLNN items (c_feats[:, 0] / c_feats[:, 2]), nullable = 1 / 0; a label
+    const uint8_t* row_bound;  // value of 2 marks a row outside the item's in_loss set (no loss, no gradient from it)
     const int* inst_flag;      // [B]: process only instances whose flag is set (nullable: all)
     const int* flag_count;     // number of flagged instances (nullable)
     float* scratch;            // [grid][s2v_general_grad_scratch_floats]
@@ -37,6 +39,7 @@ struct S2vGGradArgs {
 namespace {
 
 constexpr int kGT = 256;
+constexpr int kPartSlots = 12;       // per-warp partial-sum slots of the parameter reductions
 
 __host__ __device__ inline int gpad4(int v) { return (v + 3) & ~3; }
 
@@ -78,7 +81,7 @@ __host__ __device__ inline GGradLayout ggrad_layout(int m, int n, int p) {
     L.adj = off;  off += (size_t)m * ((n + 31) / 32);
     L.adjT = off; off += (size_t)n * ((m + 31) / 32);
     L.vecs = off;
-    off += (size_t)8 * m + 5 * n + (size_t)40 * PP + (size_t)(kGT / 32) * 10 * PP + 64;
+    off += (size_t)8 * m + 5 * n + (size_t)40 * PP + (size_t)(kGT / 32) * kPartSlots * PP + 64;
     L.total = off;
     return L;
 }
@@ -115,7 +118,7 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
     float* gw3 = v;    v += 4 * PP;             // d w3cp, d w3cn, d w3vp, d w3vn
     float* g_t0 = v;   v += PP;  float* g_t1c = v; v += 4 * PP;   float* g_t1v = v; v += PP;
     float* g_t8 = v;   v += 8 * PP;             // [c][u6 block | z block | 4 features (at 2 PP)] , c = 0 at 0, c = 1 at 4 PP
-    float* part = v;   v += (size_t)(kGT / 32) * 10 * PP;        // [warp][10][PP] per-warp partial sums
+    float* part = v;   v += (size_t)(kGT / 32) * kPartSlots * PP;        // [warp][10][PP] per-warp partial sums
     float* scal = v;
 
     const int tid = threadIdx.x, nt = kGT, lane = tid & 31, warp = tid >> 5, nw = kGT / 32;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
     auto fold_part = [&](int slot, float* dst) {
         for (int l = tid; l < p; l += nt) {
             float s = 0.f;
-            for (int w = 0; w < nw; ++w) s += part[((size_t)w * 10 + slot) * PP + l];
+            for (int w = 0; w < nw; ++w) s += part[((size_t)w * kPartSlots + slot) * PP + l];
             dst[l] += s;
         }
     };
@@ -254,6 +257,11 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
         const uint8_t* yl = a.labels + (size_t)lp * m;
+        // row flags of MPS / PLNN items (random LPs: every row a non-bound inequality)
+        const uint8_t* fil = a.row_ineq ? a.row_ineq + (size_t)lp * m : nullptr;
+        const uint8_t* fbl = a.row_bound ? a.row_bound + (size_t)lp * m : nullptr;
+        auto fiq = [&](int i) -> float { return fil ? (float)fil[i] : 1.f; };
+        auto fbq = [&](int i) -> float { return fbl ? (float)fbl[i] : 0.f; };
         for (int j = tid; j < n; j += nt) { cj[j] = (float)cg[j]; Cp[j] = 0.f; Cn[j] = 0.f; ccnt[j] = 0.f; }
         for (int e = tid; e < n * MW32; e += nt) adjT[e] = 0u;
         __syncthreads();
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
             if (l < p) {
                 val = __ldg(t0 + l);
                 if (q < m) {
-                    val += __ldg(t1c + 4 * l) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 3) * cosv[q];
+                    val += __ldg(t1c + 4 * l) * fiq(q) + __ldg(t1c + 4 * l + 1) * rb[q] + __ldg(t1c + 4 * l + 2) * fbq(q) + __ldg(t1c + 4 * l + 3) * cosv[q];
                     val += w3cp[l] * Sp[q] + w3cn[l] * Sn[q];
                 } else {
                     const int j = q - m;
@@ -350,8 +358,8 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
                     if (q < m) { c0 += x0; c1 += x1; } else { v0 += x0; v1 += x1; }
                 }
             }
-            if (lane < PP) { part[((size_t)warp * 10 + 0) * PP + lane] = c0; part[((size_t)warp * 10 + 1) * PP + lane] = v0; }
-            if (lane + 32 < PP) { part[((size_t)warp * 10 + 0) * PP + lane + 32] = c1; part[((size_t)warp * 10 + 1) * PP + lane + 32] = v1; }
+            if (lane < PP) { part[((size_t)warp * kPartSlots + 0) * PP + lane] = c0; part[((size_t)warp * kPartSlots + 1) * PP + lane] = v0; }
+            if (lane + 32 < PP) { part[((size_t)warp * kPartSlots + 0) * PP + lane + 32] = c1; part[((size_t)warp * kPartSlots + 1) * PP + lane + 32] = v1; }
         }
         for (int l = tid; l < PP; l += nt) { meanc[l] = 0.f; meanv[l] = 0.f; }
         __syncthreads();
@@ -387,14 +395,14 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
                 s0 = fmaf(__ldg(t8 + p + k), z, s0);
                 s1 = fmaf(__ldg(t8 + W8 + p + k), z, s1);
             }
-            const float f1 = rb[i], f3 = cosv[i];
-            s0 += __ldg(t8 + 2 * p) + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 3) * f3;
-            s1 += __ldg(t8 + W8 + 2 * p) + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 3) * f3;
+            const float f0 = fiq(i), f1 = rb[i], f2 = fbq(i), f3 = cosv[i];
+            s0 += __ldg(t8 + 2 * p) * f0 + __ldg(t8 + 2 * p + 1) * f1 + __ldg(t8 + 2 * p + 2) * f2 + __ldg(t8 + 2 * p + 3) * f3;
+            s1 += __ldg(t8 + W8 + 2 * p) * f0 + __ldg(t8 + W8 + 2 * p + 1) * f1 + __ldg(t8 + W8 + 2 * p + 2) * f2 + __ldg(t8 + W8 + 2 * p + 3) * f3;
             const float mx = fmaxf(s0, s1);
             const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
             const float p0 = expf(s0 - lse), p1 = expf(s1 - lse);
-            const int y = yl[i] ? 1 : 0;
-            const float w = y ? a.w1 : a.w0;
+            const int y = (yl[i] == 1) ? 1 : 0;
+            const float w = (yl[i] >= 2) ? 0.f : (y ? a.w1 : a.w0);      // label 2: row outside in_loss
             lossn[i] = -w * (y ? (s1 - lse) : (s0 - lse));
             ds0[i] = w * (p0 - (y == 0 ? 1.f : 0.f));
             ds1[i] = w * (p1 - (y == 1 ? 1.f : 0.f));
@@ -403,17 +411,20 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
 
         // ---- head backward ------------------------------------------------------------------------------------------------
         if (warp == 0) {
-            float s0 = 0.f, s1 = 0.f, ls = 0.f, f1a = 0.f, f1b = 0.f, f3a = 0.f, f3b = 0.f;
+            float s0 = 0.f, s1 = 0.f, ls = 0.f, f0a = 0.f, f0b = 0.f, f1a = 0.f, f1b = 0.f, f2a = 0.f, f2b = 0.f, f3a = 0.f, f3b = 0.f;
             for (int i = lane; i < m; i += 32) {
                 s0 += ds0[i]; s1 += ds1[i]; ls += lossn[i];
+                f0a += ds0[i] * fiq(i); f0b += ds1[i] * fiq(i); f2a += ds0[i] * fbq(i); f2b += ds1[i] * fbq(i);
                 f1a += ds0[i] * rb[i]; f1b += ds1[i] * rb[i]; f3a += ds0[i] * cosv[i]; f3b += ds1[i] * cosv[i];
             }
             s0 = gwsum(s0); s1 = gwsum(s1); ls = gwsum(ls);
+            f0a = gwsum(f0a); f0b = gwsum(f0b); f2a = gwsum(f2a); f2b = gwsum(f2b);
             f1a = gwsum(f1a); f1b = gwsum(f1b); f3a = gwsum(f3a); f3b = gwsum(f3b);
             if (lane == 0) {
                 scal[0] = s0; scal[1] = s1; loss_cta += (double)ls;
-                g_t8[2 * PP + 0] += s0;   g_t8[4 * PP + 2 * PP + 0] += s1;
+                g_t8[2 * PP + 0] += f0a;  g_t8[4 * PP + 2 * PP + 0] += f0b;
                 g_t8[2 * PP + 1] += f1a;  g_t8[4 * PP + 2 * PP + 1] += f1b;
+                g_t8[2 * PP + 2] += f2a;  g_t8[4 * PP + 2 * PP + 2] += f2b;
                 g_t8[2 * PP + 3] += f3a;  g_t8[4 * PP + 2 * PP + 3] += f3b;
             }
         }
@@ -432,8 +443,8 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
                     }
                 }
             }
-            if (lane < PP) { part[((size_t)warp * 10 + 2) * PP + lane] = g00; part[((size_t)warp * 10 + 3) * PP + lane] = g10; }
-            if (lane + 32 < PP) { part[((size_t)warp * 10 + 2) * PP + lane + 32] = g01; part[((size_t)warp * 10 + 3) * PP + lane + 32] = g11; }
+            if (lane < PP) { part[((size_t)warp * kPartSlots + 2) * PP + lane] = g00; part[((size_t)warp * kPartSlots + 3) * PP + lane] = g10; }
+            if (lane + 32 < PP) { part[((size_t)warp * kPartSlots + 2) * PP + lane + 32] = g01; part[((size_t)warp * kPartSlots + 3) * PP + lane + 32] = g11; }
         }
         __syncthreads();
         fold_part(2, g_t8 + PP);
@@ -495,9 +506,9 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
 
         // ---- base parameters: reductions of DP over the nodes (lanes over l, warps stride over the nodes) --------------------
         {
-            float r[9][2];
+            float r[11][2];                 // 9, 10: d base weighted by the row flags (t1c columns 0 and 2)
 #pragma unroll
-            for (int q = 0; q < 9; ++q) { r[q][0] = 0.f; r[q][1] = 0.f; }
+            for (int q = 0; q < 11; ++q) { r[q][0] = 0.f; r[q][1] = 0.f; }
             for (int q = warp; q < NP; q += nw) {
                 const float* d = DP + (size_t)q * PP;
 #pragma unroll
@@ -507,6 +518,7 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
                         const float dv = d[l];
                         if (q < m) {
                             r[0][h] += dv;
+                            r[9][h] = fmaf(dv, fiq(q), r[9][h]); r[10][h] = fmaf(dv, fbq(q), r[10][h]);
                             r[1][h] = fmaf(dv, rb[q], r[1][h]); r[2][h] = fmaf(dv, cosv[q], r[2][h]);
                             r[3][h] = fmaf(dv, Sp[q], r[3][h]); r[4][h] = fmaf(dv, Sn[q], r[4][h]);
                         } else {
@@ -518,21 +530,21 @@ __global__ void __launch_bounds__(kGT, 2) s2v_bipartite_general_grad_kernel(S2vG
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                if (lane < PP) part[((size_t)warp * 10 + q) * PP + lane] = r[q][0];
-                if (lane + 32 < PP) part[((size_t)warp * 10 + q) * PP + lane + 32] = r[q][1];
+            for (int q = 0; q < 11; ++q) {
+                if (lane < PP) part[((size_t)warp * kPartSlots + q) * PP + lane] = r[q][0];
+                if (lane + 32 < PP) part[((size_t)warp * kPartSlots + q) * PP + lane + 32] = r[q][1];
             }
         }
         __syncthreads();
         for (int l = tid; l < p; l += nt) {
-            float s[9];
+            float s[11];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) {
+            for (int q = 0; q < 11; ++q) {
                 s[q] = 0.f;
-                for (int w = 0; w < nw; ++w) s[q] += part[((size_t)w * 10 + q) * PP + l];
+                for (int w = 0; w < nw; ++w) s[q] += part[((size_t)w * kPartSlots + q) * PP + l];
             }
             g_t0[l] += s[0] + s[5];
-            g_t1c[0 * PP + l] += s[0]; g_t1c[1 * PP + l] += s[1]; g_t1c[3 * PP + l] += s[2];
+            g_t1c[0 * PP + l] += s[9]; g_t1c[1 * PP + l] += s[1]; g_t1c[2 * PP + l] += s[10]; g_t1c[3 * PP + l] += s[2];
             gw3[l] += s[3]; gw3[PP + l] += s[4];
             g_t1v[l] += s[6]; gw3[2 * PP + l] += s[7]; gw3[3 * PP + l] += s[8];
         }

@@ -26,7 +26,8 @@ struct S2vCGradArgs {
     const float* gram;         // [B][3][gram_pitch]: Wp, Wn, wc from the Gram kernel
     int gram_pitch;
     const float* params;
-    const uint8_t* labels;     // [B, m] 0 / 1
+    const uint8_t* labels;     // [B, m] 0 / 1; 2 = row outside the item's in_loss set (no loss, no gradient from it)
+    const uint8_t* row_ineq;   // [B, m] node features of the row nodes of MPS / PLNN items (1 = inequality row), nullable = all 1
     float w0, w1;
     float* grad;               // [param_count], accumulated with atomics (zeroed by the caller)
     double* loss;              // scalar, accumulated with atomics (zeroed by the caller)
@@ -113,7 +114,7 @@ __host__ __device__ inline CGradLayout cgrad_layout(int m, int p, int T) {
     L.X = off;   off += (size_t)p * MP;
     L.Y = off;   off += (size_t)p * MP;
     L.vecs = off;
-    off += (size_t)6 * MP + (size_t)(32 + 2 * (T + 1)) * PP + 64;
+    off += (size_t)7 * MP + (size_t)(33 + 2 * (T + 1)) * PP + 64;
     L.total = off;
     return L;
 }
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
     float* v = sm + L.vecs;
     float* Wp = v;     v += MP;   float* Wn = v;     v += MP;   float* wc = v;    v += MP;
     float* ds0 = v;    v += MP;   float* ds1 = v;    v += MP;   float* lossn = v; v += MP;
+    float* nfs = v;    v += MP;   // node feature of every row node (1 on random LPs), 0 on the padding nodes
     float* w3p = v;    v += PP;   float* w3n = v;    v += PP;   float* r4p = v;   v += PP;   float* r4n = v;   v += PP;
     float* k0 = v;     v += PP;   float* u3c = v;    v += PP;   float* relucr = v; v += PP;  float* y1 = v;    v += PP;
     float* y2 = v;     v += PP;   float* u6pre = v;  v += PP;   float* u6r = v;   v += PP;   float* du6 = v;   v += PP;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
     float* swn = v;    v += PP;   float* dpc = v;    v += PP;   float* dmuc = v;  v += PP;   float* gu3i = v;  v += PP;
     float* g_t0 = v;   v += PP;   float* g_t1 = v;   v += PP;   float* g_w3p = v; v += PP;   float* g_w3n = v; v += PP;
     float* g_t4rc = v; v += PP;   float* g_t4cr = v; v += PP;   float* g_t8 = v;  v += 4 * PP;
+    float* sfl = v;    v += PP;   // per-coordinate sums of d pre weighted by the node features (gradient of t1)
     float* mucs = v;   v += (size_t)(T + 1) * PP;     // mu_c before round 0 (zero), after round 0, ...
     float* means = v;  v += (size_t)(T + 1) * PP;     // mean_i mu_r, same indexing
     float* scal = v;                                   // [0] s (B10), [1] S+, [2] S-, [3] S0, [4] S1, [5] d s of this instance
@@ -253,6 +256,7 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
             Wp[i] = (i < m) ? __ldg(gr + i) : 0.f;
             Wn[i] = (i < m) ? __ldg(gr + a.gram_pitch + i) : 0.f;
             wc[i] = (i < m) ? __ldg(gr + 2 * a.gram_pitch + i) : 0.f;
+            nfs[i] = (i < m) ? (a.row_ineq ? (float)a.row_ineq[(size_t)lp * m + i] : 1.f) : 0.f;
         }
         for (int l = tid; l < PP; l += nt) gu3i[l] = 0.f;
         __syncthreads();
@@ -284,7 +288,8 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
             float* mu1 = mus;
             for (int e = tid; e < p * MP; e += nt) {
                 const int l = e / MP, i = e - l * MP;
-                mu1[e] = (i < m) ? fmaxf(k0[l] + w3p[l] * Wp[i] + w3n[l] * Wn[i] + sB, 0.f) : 0.f;
+                const float kq = a.row_ineq ? __ldg(t0 + l) + __ldg(t1 + l) * nfs[i] : k0[l];
+                mu1[e] = (i < m) ? fmaxf(kq + w3p[l] * Wp[i] + w3n[l] * Wn[i] + sB, 0.f) : 0.f;
             }
             for (int l = tid; l < p; l += nt) mucs[PP + l] = fmaxf(__ldg(t0 + l) + u3c[l], 0.f);
             __syncthreads();
@@ -299,12 +304,14 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
             __syncthreads();
             tile_product(t2T, PP, p, mu_in, MP, tid, nt, [&](int k, int i0, float v0, float v1, float v2, float v3) {
                 const float add = k0[k] + y1[k] + sB, wp = w3p[k], wn = w3n[k];
+                const float t0k = __ldg(t0 + k), t1k = __ldg(t1 + k), y1k = y1[k];
                 const float vv[4] = {v0, v1, v2, v3};
                 float o[4];
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     const int i = i0 + q;
-                    o[q] = (i < m) ? fmaxf(vv[q] + add + wp * Wp[i] + wn * Wn[i], 0.f) : 0.f;
+                    const float addq = a.row_ineq ? (t0k + t1k * nfs[i < m ? i : 0]) + y1k + sB : add;
+                    o[q] = (i < m) ? fmaxf(vv[q] + addq + wp * Wp[i] + wn * Wn[i], 0.f) : 0.f;
                 }
                 *reinterpret_cast<float4*>(mu_out + k * MP + i0) = make_float4(o[0], o[1], o[2], o[3]);
             });
@@ -350,8 +357,8 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
                 const float mx = fmaxf(s0, s1);
                 const float lse = mx + logf(expf(s0 - mx) + expf(s1 - mx));
                 const float p0 = expf(s0 - lse), p1 = expf(s1 - lse);
-                const int y = yl[i] ? 1 : 0;
-                const float w = y ? a.w1 : a.w0;
+                const int y = (yl[i] == 1) ? 1 : 0;
+                const float w = (yl[i] >= 2) ? 0.f : (y ? a.w1 : a.w0);      // label 2: row outside in_loss
                 ln = -w * (y ? (s1 - lse) : (s0 - lse));
                 d0 = w * (p0 - (y == 0 ? 1.f : 0.f));
                 d1 = w * (p1 - (y == 1 ? 1.f : 0.f));
@@ -413,17 +420,18 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
             const float* mu_out = mus + (size_t)t * p * MP;
             // d pre = d mu . [mu > 0], in place; per-coordinate sums over the nodes
             for (int l = warp; l < p; l += nw) {
-                float s_all = 0.f, s_p = 0.f, s_n = 0.f;
+                float s_all = 0.f, s_p = 0.f, s_n = 0.f, s_f = 0.f;
                 for (int i = lane; i < MP; i += 32) {
                     const float d = (mu_out[l * MP + i] > 0.f) ? dcur[l * MP + i] : 0.f;
                     dcur[l * MP + i] = d;
                     s_all += d;
+                    s_f = fmaf(d, nfs[i], s_f);
                     s_p = fmaf(d, Wp[i], s_p);
                     s_n = fmaf(d, Wn[i], s_n);
                 }
-                s_all = cwsum(s_all); s_p = cwsum(s_p); s_n = cwsum(s_n);
+                s_all = cwsum(s_all); s_p = cwsum(s_p); s_n = cwsum(s_n); s_f = cwsum(s_f);
                 if (lane == 0) {
-                    srow[l] = s_all; swp[l] = s_p; swn[l] = s_n;
+                    srow[l] = s_all; swp[l] = s_p; swn[l] = s_n; sfl[l] = s_f;
                     dpc[l] = (mucs[(t + 1) * PP + l] > 0.f) ? dmuc[l] : 0.f;
                 }
             }
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(kCT, 1) s2v_complete_grad_kernel(S2vCGradArgs 
             }
             for (int l = tid; l < p; l += nt) {
                 g_t0[l] += srow[l] + dpc[l];
-                g_t1[l] += srow[l];
+                g_t1[l] += a.row_ineq ? sfl[l] : srow[l];
                 g_w3p[l] += swp[l];
                 g_w3n[l] += swn[l];
                 gu3i[l] += dpc[l];

@@ -118,11 +118,13 @@ class Model(nn.Module):
         (``DdbError`` "do not fit") trains through ``forward_batch_torch`` + autograd."""
         return self.graph in GRAPH_CODE and self.p <= 64 and A.is_cuda and not self.force_torch
 
-    def loss_and_grad_batch(self, A, b, c, labels, weight):
+    def loss_and_grad_batch(self, A, b, c, labels, weight, feats=None):
         """One training step's loss and gradient on the device: ``ddb_s2v_loss_grad_dev``.  Replaces the reference's
         per-instance ``loss = criterion(model(x), y); loss.backward()`` accumulation (train.py:59-65) with
         ``criterion = NLLLoss(weight, size_average=False)`` (benchmark.py:70-75).  labels [B,m] (0/1), weight = [w0, w1].
-        ACCUMULATES into ``param.grad`` like ``backward()`` does and returns the summed loss (0-dim fp64 tensor on the device)."""
+        ACCUMULATES into ``param.grad`` like ``backward()`` does and returns the summed loss (0-dim fp64 tensor on the device).
+        ``feats`` = node flags of MPS / PLNN items (see ``forward_batch_torch``; ``ddb_s2v_loss_grad_flags_dev``); a label of 2
+        marks a row outside the item's ``in_loss`` set."""
         if not (A.is_cuda and b.is_cuda and c.is_cuda):
             raise _lib.DdbError('the classifier backward kernel needs CUDA tensors; there is no CPU fallback')
         B, m, n = A.shape
@@ -135,9 +137,18 @@ class Model(nn.Module):
         loss = torch.empty((), dtype=torch.float64, device=dev)
         flag = torch.empty(1, dtype=torch.int32, device=dev)
         vp = lambda t: C.c_void_p(t.data_ptr())
-        rc = ctx.lib.ddb_s2v_loss_grad_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
-                                           vp(params), vp(y), float(weight[0]), float(weight[1]), vp(grad), vp(loss), vp(flag),
-                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        if feats is None:
+            rc = ctx.lib.ddb_s2v_loss_grad_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
+                                               vp(params), vp(y), float(weight[0]), float(weight[1]), vp(grad), vp(loss), vp(flag),
+                                               C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        else:
+            fl = (feats, None) if torch.is_tensor(feats) else feats
+            ineq = fl[0].to(device=dev).reshape(B, m).ne(0).to(torch.uint8).contiguous()
+            bound = None if fl[1] is None else fl[1].to(device=dev).reshape(B, m).ne(0).to(torch.uint8).contiguous()
+            rc = ctx.lib.ddb_s2v_loss_grad_flags_dev(ctx.handle, GRAPH_CODE[self.graph], B, m, n, self.p, self.T, vp(A), vp(b), vp(c),
+                                                     vp(params), vp(y), vp(ineq), vp(bound) if bound is not None else None,
+                                                     float(weight[0]), float(weight[1]), vp(grad), vp(loss), vp(flag),
+                                                     C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
         _lib.check(rc, 'ddb_s2v_loss_grad_dev')
         self._last_grad_flag = flag
         off = 0
@@ -265,6 +276,23 @@ class Model(nn.Module):
         b = cf[:, 1].double().cpu()
         c = item['v_feats'].reshape(-1).double().cpu()
         return A.unsqueeze(0), b.unsqueeze(0), c.unsqueeze(0)
+
+    def loss_and_grad_item(self, item, weight):
+        """``loss_and_grad_batch`` for ONE reference-format item (MPS / PLNN LPs: any shape, equality / bound flags, an
+        ``in_loss`` subset of the rows): what ``criterion(model(item), y).backward()`` does in the reference's loop
+        (train.py:59-65), on the hand-written kernels."""
+        A, b, c = self._item_to_abc(item)
+        dev = self.t0.device
+        m = A.shape[1]
+        lab = item['node_labels'] if self.graph == 'complete' else item['c_labels']
+        lab = torch.as_tensor(np.asarray(lab)).reshape(-1) if not torch.is_tensor(lab) else lab.reshape(-1)
+        in_loss = torch.as_tensor([int(q) for q in item['in_loss']], dtype=torch.long)
+        y = torch.full((m,), 2, dtype=torch.uint8)
+        y[in_loss] = lab[in_loss].to(torch.uint8)
+        feats = self._item_feats(item)
+        if feats is not None:
+            feats = feats.to(dev) if torch.is_tensor(feats) else tuple(f.to(dev) for f in feats)
+        return self.loss_and_grad_batch(A.to(dev), b.to(dev), c.to(dev), y.reshape(1, m).to(dev), weight, feats)
 
     def forward(self, item):
         if self.graph not in GRAPH_CODE:

@@ -58,9 +58,18 @@ def train_net(model, criterion, optimizer, trainloader, testloader, epochs, batc
                 # the reference's own loop (train.py:57-66): one forward / backward per item, gradients accumulate
                 optimizer.zero_grad()
                 for item in data:
-                    x, y = _item_xy(item, model.graph, dev)
-                    loss = criterion(model(x), y)
-                    loss.backward()
+                    loss = None
+                    if _device_backward_ok_item(model, criterion):
+                        # hand-written loss + gradient kernels with the item's row flags (ddb_s2v_loss_grad_flags_dev)
+                        try:
+                            loss = model.loss_and_grad_item(item, [float(criterion.weight[0]), float(criterion.weight[1])])
+                        except _lib.DdbError as exc:
+                            if 'do not fit' not in str(exc):
+                                raise
+                    if loss is None:
+                        x, y = _item_xy(item, model.graph, dev)
+                        loss = criterion(model(x), y)
+                        loss.backward()
                 parallel.allreduce_gradients(model)
                 optimizer.step()
                 running_loss += float(loss.detach())                  # the last item's loss, as train.py:68-69 records it
@@ -99,6 +108,14 @@ def _device_backward_ok(model, criterion, A):
     bipartite model on dense instances and for the complete model; anything else goes through autograd."""
     return (hasattr(model, 'device_backward_supported') and not getattr(model, '_no_device_backward', False)
             and model.device_backward_supported(A)
+            and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum'
+            and criterion.weight is not None and criterion.ignore_index < 0)
+
+
+def _device_backward_ok_item(model, criterion):
+    """The same for one reference-format item (MPS / PLNN): model on the GPU, the reference's criterion."""
+    return (hasattr(model, 'loss_and_grad_item') and not getattr(model, 'force_torch', False) and model.p <= 64
+            and next(model.parameters()).is_cuda
             and isinstance(criterion, torch.nn.NLLLoss) and criterion.reduction == 'sum'
             and criterion.weight is not None and criterion.ignore_index < 0)
 

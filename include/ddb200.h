@@ -180,6 +180,13 @@ int ddb_s2v_loss_grad_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int 
                           const double *A, const double *b, const double *c, const float *params,
                           const uint8_t *labels, float w0, float w1,
                           float *grad, double *loss, int32_t *not_dense, void *stream);
+/* The same step for MPS / PLNN items: per-row node flags as in ddb_s2v_forward_flags_dev, and a label value of 2 marks a row
+ * outside the item's in_loss set (it contributes neither loss nor gradient).  Bipartite items run on the general-adjacency
+ * kernel. */
+int ddb_s2v_loss_grad_flags_dev(ddb_ctx *ctx, int graph, int64_t B, int m, int n, int p, int T,
+                                const double *A, const double *b, const double *c, const float *params,
+                                const uint8_t *labels, const uint8_t *row_ineq, const uint8_t *row_bound,
+                                float w0, float w1, float *grad, double *loss, int32_t *not_dense, void *stream);
 
 /*
  * (6) CLASSIFIER EVALUATION METRICS -- replaces the host side of the per-epoch evaluation: the recall-1 threshold

@@ -403,3 +403,37 @@ def test_flagged_items_run_on_the_cuda_kernels(cuda_device, golden_dir):
             got = model.forward_batch_cuda(A, b, c, feats)
         assert (got - want).abs().max().item() <= 5e-5 + 1e-5 * want.abs().max().item(), (graph, m, n)
         assert (model.probs - wprobs).abs().max().item() <= 5e-5
+
+
+@pytest.mark.parametrize('graph,B,m,n,p,T', [('bipartite', 5, 30, 12, 8, 2), ('bipartite', 3, 90, 40, 24, 3), ('complete', 5, 30, 12, 8, 2),
+                                             ('complete', 3, 90, 40, 24, 3), ('bipartite', 2, 200, 100, 40, 3), ('complete', 2, 200, 100, 40, 3)])
+def test_loss_grad_with_row_flags_matches_autograd(cuda_device, graph, B, m, n, p, T):
+    """ddb_s2v_loss_grad_flags_dev (MPS / PLNN items: equality / bound rows, rows outside in_loss marked by label 2) against
+    autograd through the batched restatement with the same flags: loss and every parameter gradient."""
+    from deep_dantzig_b200 import solver
+    from deep_dantzig_b200.ml.models.s2v import Model
+    gen = torch.Generator(device='cuda').manual_seed(3)
+    A, b, c = solver.generate(77, 0, B, m, n, density=0.35)
+    ineq = (torch.rand(B, m, device='cuda', generator=gen) < 0.7).float()
+    bound = (torch.rand(B, m, device='cuda', generator=gen) < 0.2).float()
+    feats = (ineq, bound) if graph == 'bipartite' else ineq
+    y = (torch.rand(B, m, device='cuda', generator=gen) < 0.4).to(torch.uint8)
+    out = torch.rand(B, m, device='cuda', generator=gen) < 0.25          # rows outside in_loss
+    y2 = torch.where(out, torch.full_like(y, 2), y)
+    w = [0.3, 0.7]
+    torch.manual_seed(4)
+    model = Model(graph, p, T, on_cuda=True, verbose_init=False)
+    model.zero_grad()
+    l_dev = model.loss_and_grad_batch(A, b, c, y2, w, feats)
+    g_dev = {k: q.grad.clone() for k, q in model.named_parameters()}
+    model.zero_grad()
+    logp = model.forward_batch_torch(A, b, c, feats)
+    crit = torch.nn.NLLLoss(weight=torch.tensor(w, device='cuda'), reduction='sum')
+    keep = ~out
+    l_ref = crit(logp[keep], y[keep].long())
+    l_ref.backward()
+    assert abs(float(l_dev) - float(l_ref.detach())) <= 2e-4 * abs(float(l_ref.detach())) + 1e-5
+    ref = {k: (q.grad if q.grad is not None else torch.zeros_like(q)) for k, q in model.named_parameters()}   # unused parameters: no grad
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    for k in ref:
+        assert float((g_dev[k] - ref[k]).abs().max()) <= 2e-4 * gmax + 1e-6, k
