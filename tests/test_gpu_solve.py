@@ -350,6 +350,44 @@ def test_host_and_device_flavours_agree(cuda_device):
     assert (rh['x'][ok] == rd['x'][ok]).all()
 
 
+def test_degeneracies_and_infeasibility_at_the_column_block_kernel_shape(cuda_device):
+    """The hand-made cases of the test above at a shape the column-block-per-warp kernel takes automatically (170 x 80), plus
+    infeasible instances (a row and its negation with contradictory right-hand sides: phase 1 must prove status 3) -- against
+    the polished oracle."""
+    from deep_dantzig_b200 import solver, _lib
+    m, n, N = 170, 80, 120
+    assert _lib.context(0).solve_plan(m, n) == 7
+    A, b, c = _numpy_batch(m, n, [577 * i + 11 for i in range(N)])
+    rng = np.random.RandomState(8)
+    infeasible = np.zeros(N, bool)
+    for i in range(N):
+        kind = i % 5
+        score = (A[i] @ c[i]) / np.linalg.norm(A[i], axis=1)
+        first = int(np.argsort(score)[0])
+        if kind == 0:
+            z = int(rng.randint(m)); A[i, z] = 0.0; b[i, z] = abs(b[i, z]) + 0.1
+        elif kind == 1:
+            src, dst = rng.choice(m, 2, replace=False); A[i, dst] = A[i, src]; b[i, dst] = b[i, src]
+        elif kind == 2:
+            A[i, first, int(np.abs(A[i, first]).argmax())] = 0.0
+        elif kind == 3:
+            keep = rng.choice(n, 2, replace=False); row = np.zeros(n); row[keep] = A[i, first, keep]; A[i, first] = row
+        else:                                                   # a_s x <= b_s and -a_s x <= -b_s - 1: empty feasible set
+            src, dst = rng.choice(m, 2, replace=False); A[i, dst] = -A[i, src]; b[i, dst] = -b[i, src] - 1.0
+            infeasible[i] = True
+    r = solver.solve_label_host(A, b, c)
+    ref = oracle.solve_batch(A, b, c)
+    ok = ref['status'] == 2
+    assert ((r['status'] == 2) == ok).all()
+    assert (r['status'][infeasible] == 3).all() and (ref['status'][infeasible] != 2).all()
+    assert (r['labels'][~ok] == 0).all()
+    assert (r['labels'][ok] == ref['labels'][ok]).all()
+    assert (r['n_active'][ok] == ref['n_active'][ok]).all()
+    if ok.any():
+        assert np.abs(r['obj'][ok] - ref['obj'][ok]).max() <= REL_TOL * np.abs(ref['obj'][ok]).max()
+        assert np.abs(r['x'][ok] - ref['x'][ok]).max() <= REL_TOL * np.abs(ref['x'][ok]).max()
+
+
 def test_edge_cases(cuda_device):
     from deep_dantzig_b200 import solver, _lib
     # empty batch
