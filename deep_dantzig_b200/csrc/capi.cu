@@ -465,7 +465,7 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
         if (plan == 5) which = 3;
-        if (plan == 7) which = (row_mask || gen) ? 1 : 4;   // the column-block kernel takes neither row masks nor the in-solver generator
+        if (plan == 7) which = gen ? 1 : 4;                  // the in-solver generator lives in the row-per-thread kernel
         if (gen) which = 1;                              // the caller checked rowreg_gen_supported
         const int grid = gen ? ddb::rowreg_gen_grid(m, n, ctx->sm_count) : ddb::rowreg_grid(m, n, ctx->sm_count);
         const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;

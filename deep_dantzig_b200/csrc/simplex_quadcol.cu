@@ -21,7 +21,7 @@
 // Same algorithm, tolerances and arithmetic per tableau entry as rowreg_kernel.cuh: static-order
 // crash as an explicit inverse (kept in shared memory, 4 blocks of 26 per row), P_N = -A_N D, phase 1 (most negative
 // slack leaves), phase 2 (Dantzig), lazily normalised rows; exact ties go to the lowest column / lowest tile row.
-// Covers n <= 100, m - n <= 128 without row masks; instances it cannot finish (singular static crash basis,
+// Covers n <= 100, m - n <= 128, with or without row masks (reduced LPs); instances it cannot finish (singular static crash basis,
 // ill-conditioned vertex) are flagged status = -1 and re-solved by the generic kernel on the device (capi.cu).
 #include <cstdlib>
 #include <type_traits>
@@ -290,6 +290,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         const double* Ag = a.A + (size_t)lp * m * n;
         const double* bg = a.b + (size_t)lp * m;
         const double* cg = a.c + (size_t)lp * n;
+        const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;      // reduced LP: rows with mask 0 are left out
 
         // ---- stage 0: crash order by cosine score ------------------------------------------------------------------
         {
@@ -304,7 +305,8 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         __syncthreads();
         for (int i = tid; i < m; i += QNT) {
             const double dot = gbuf[i], nn = gnn[i];
-            gnn[i] = nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5;
+            const bool excl = mask && mask[i] == 0;
+            gnn[i] = excl ? kInf : (nn > 0.0 ? dot / sqrt(nn) : kInf * 0.5);        // excluded rows rank last
         }
         __syncthreads();
         for (int i = tid; i < m; i += QNT) {
@@ -318,8 +320,13 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             basic_tile[i] = -1;
         }
         __syncthreads();
-        const int nN = m - n;
-        bool need_generic = false;
+        int m_eff = m;
+        if (mask) {
+            m_eff = 0;
+            for (int i = 0; i < m; ++i) m_eff += (gnn[i] < kInf);     // uniform, only for reduced LPs
+        }
+        const int nN = m_eff - n;                                      // live rows; order[m_eff ..) are the excluded ones
+        bool need_generic = nN < 0;                                    // fewer kept rows than columns: the generic kernel's business
         int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
         int status = ST_OPTIMAL;
         int buf = 0;
@@ -345,7 +352,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         if (tid < QROWS) cvsm[tid] = (tid < n) ? -1 : -2;
         __syncthreads();
 
-        for (int t = 0; t < n; ++t) {
+        for (int t = 0; t < n && !need_generic; ++t) {
             const int lt = t >> 2, qt = t & 3;
             if (lane == lt) publish_slot(prow, T, qt);
             __syncwarp();
@@ -718,10 +725,11 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     lab[i] = (uint8_t)active;
                     nact += active;
                     int tie = (as >= a.thr * 0.1 && as <= a.thr * 10.0);
-                    tie |= (active != (basic_tile[i] < 0));
+                    const bool excl = mask && mask[i] == 0;
+                    if (!excl) tie |= (active != (basic_tile[i] < 0));
                     nties += tie;
                     nviol += (slack < -a.thr);
-                    nref += (basic_tile[i] < 0 && as > a.thr * 0.01);
+                    nref += (!excl && basic_tile[i] < 0 && as > a.thr * 0.01);
                 }
                 return nref;
             };

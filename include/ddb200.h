@@ -61,8 +61,8 @@ int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, i
  * (row-per-thread kernel, falling back to the other register kernels for shapes it does not cover),
  * 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau, 6 = thread-block-cluster kernel (the live
  * tableau in the distributed shared memory of 1-8 SMs: shapes beyond one SM such as (500,250)), 7 = tableau in the
- * register file, rows over lanes and columns over warps (72 <= n <= 100, m - n <= 128, e.g. (200,100); calls with a row
- * mask and the in-solver generator run on the row-per-thread kernel of plan 0); <0 = error. */
+ * register file, rows over lanes and columns over warps (72 <= n <= 100, m - n <= 128, e.g. (200,100), with or without a
+ * row mask; the in-solver generator runs on the row-per-thread kernel of plan 0); <0 = error. */
 int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
 /* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 4 = warp-tiled register kernel (the fallback of plan 0
  * for 100 < n <= 111).  3 (2-D register tile) and 5 (software-pipelined rows) are measured negative results that only the
