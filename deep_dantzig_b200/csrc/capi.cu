@@ -25,7 +25,9 @@ cudaError_t launch_simplex_regtile(const SolveArgs& a, int sm_count, cudaStream_
 size_t regtile_scratch_bytes(int m, int n, int sm_count);
 bool quadcol_supported(int m, int n);
 int quadcol_grid(int sm_count);
-size_t quadcol_scratch_bytes(int grid);
+int quadcol_gen_grid(int sm_count);
+bool quadcol_gen_supported(int m, int n);
+cudaError_t launch_simplex_quadcol_gen(const SolveArgs& a, int sm_count, cudaStream_t st);
 cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st);
 #ifdef DDB_EXPERIMENTS   // `make experiments`: the measured negative results of round 1, not in the shipped library
 bool tile2d_supported(int m, int n);
@@ -465,14 +467,18 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
         if (plan == 5) which = 3;
-        if (plan == 7) which = gen ? 1 : 4;                  // the in-solver generator lives in the row-per-thread kernel
-        if (gen) which = 1;                              // the caller checked rowreg_gen_supported
-        const int grid = gen ? ddb::rowreg_gen_grid(m, n, ctx->sm_count) : ddb::rowreg_grid(m, n, ctx->sm_count);
+        if (plan == 7) which = 4;
+        // in-solver generator (the caller checked *_gen_supported): in the column-block kernel at its shapes, else in the
+        // row-per-thread kernel
+        const bool qgen = gen && plan == 7 && ddb::quadcol_gen_supported(m, n);
+        if (gen) which = qgen ? 4 : 1;
+        const int grid = qgen ? ddb::quadcol_gen_grid(ctx->sm_count)
+                              : (which == 4 ? ddb::quadcol_grid(ctx->sm_count)
+                                            : (gen ? ddb::rowreg_gen_grid(m, n, ctx->sm_count) : ddb::rowreg_grid(m, n, ctx->sm_count)));
         const int fplan = ((int64_t)ddb::generic_smem_bytes(m, n, true) <= ctx->smem_optin) ? 1 : 2;
         const long long fgrid = generic_grid(ctx, m, n, fplan, B);
         size_t need = (which == 2) ? ddb::regtile_scratch_bytes(m, n, ctx->sm_count)
                                    : (which == 1 ? ddb::rowreg_rows_scratch_bytes(m, n, grid) : 0);
-        if (which == 4) need = ddb::quadcol_scratch_bytes(ddb::quadcol_grid(ctx->sm_count));
         const size_t fneed = generic_scratch_bytes(ctx, m, n, fplan, B);
         if (fneed > need) need = fneed;
         const size_t need_d = (which == 1) ? ddb::rowreg_d_scratch_bytes(m, n, grid) : 0;
@@ -481,7 +487,9 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         a.gtab = (double*)ctx->scratch.p;
         a.dscr = (double*)ctx->dscr.p;
         a.slab = (double*)ctx->slab.p;
-        if (gen)
+        if (qgen)
+            CUDA_TRY(ddb::launch_simplex_quadcol_gen(a, ctx->sm_count, st));
+        else if (gen)
             CUDA_TRY(ddb::launch_simplex_rowreg_gen(a, ctx->sm_count, st));
         else if (which == 0)
             CUDA_TRY(ddb::launch_simplex_tile2d(a, ctx->sm_count, st));
@@ -795,7 +803,8 @@ static int fused_launch(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int6
     const bool inkernel = (mode == 1);
     const int plan = ddb_solve_plan(ctx, m, n);
     if (plan < 0) return plan;
-    if (inkernel && (plan == 0 || plan == 7) && ctx->forced_plan < 0 && ddb::rowreg_gen_supported(m, n) &&
+    if (inkernel && (plan == 0 || plan == 7) && ctx->forced_plan < 0 &&
+        ((plan == 7 && ddb::quadcol_gen_supported(m, n)) || ddb::rowreg_gen_supported(m, n)) &&
         (!keep || ((reinterpret_cast<uintptr_t>(A_out) | reinterpret_cast<uintptr_t>(c_out)) & 15) == 0)) {
         GenSpec g{key, first_instance, density};
         return solve_launch(ctx, B, m, n, keep ? A_out : nullptr, keep ? b_out : nullptr, keep ? c_out : nullptr, threshold,

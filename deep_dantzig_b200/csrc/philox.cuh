@@ -147,7 +147,7 @@ __host__ __device__ constexpr size_t gen_smem_doubles(int m, int n) {
 }
 // TAG: one copy per calling kernel, so that each copy is compiled under its caller's register budget (a shared copy would
 // have to live with the tightest launch bound of all the solver variants).
-template <int TAG>
+template <int TAG, int CHAINS = kGenChains>
 static __device__ DDB_GEN_FN void generate_instance_cta(uint64_t key, uint64_t inst, int m, int n, double density, double* Aw,
                                                           double* bw, double* cw, double* x0w, double* tile, double* dotc,
                                                           double* nn) {
@@ -180,10 +180,10 @@ static __device__ DDB_GEN_FN void generate_instance_cta(uint64_t key, uint64_t i
         // kGenChains independent Philox + Box-Muller chains per thread and trip.  More chains were measured SLOWER inside the
         // solver (the solver kernel runs at ~11 warp-cycles per issued instruction whatever the instruction, so time follows
         // the instruction count, and the unrolled body only adds rounding-up waste and instruction-cache misses)
-        for (int t0 = tid; t0 < npair; t0 += kGenChains * nt) {
-            double z0[kGenChains], z1[kGenChains];
+        for (int t0 = tid; t0 < npair; t0 += CHAINS * nt) {
+            double z0[CHAINS], z1[CHAINS];
 #pragma unroll
-            for (int u = 0; u < kGenChains; ++u) {
+            for (int u = 0; u < CHAINS; ++u) {
                 const int t = t0 + u * nt;
                 const uint32_t pair = (uint32_t)(r0 * half + (t < npair ? t : 0));
                 normal_pair(key, inst, STREAM_A, pair, z0[u], z1[u]);
@@ -196,7 +196,7 @@ static __device__ DDB_GEN_FN void generate_instance_cta(uint64_t key, uint64_t i
                 }
             }
 #pragma unroll
-            for (int u = 0; u < kGenChains; ++u) {
+            for (int u = 0; u < CHAINS; ++u) {
                 const int t = t0 + u * nt;
                 if (t < npair) {
                     *reinterpret_cast<double2*>(Aw + (size_t)r0 * n + 2 * (size_t)t) = make_double2(z0[u], z1[u]);

@@ -27,6 +27,7 @@
 #include <type_traits>
 
 #include "common.cuh"
+#include "philox.cuh"
 
 namespace ddb {
 namespace {
@@ -41,6 +42,7 @@ constexpr int QNMAX = QW * QC;        // columns
 constexpr int QMMAX = 256;            // constraints (order / score arrays)
 constexpr int QDP = QW * QP;          // pitch of a row of D in shared memory
 constexpr unsigned long long QINF = 0x7ff0000000000000ull;   // bit pattern of +inf: "no candidate" among non-negative ratios
+constexpr int kQuadGenChains = 2;     // independent Box-Muller chains per thread of the in-solver generator
 constexpr int QCS = 4;                // column slots of the lane-distributed vectors of stages 0 and 4 (j = lane + 32 cs)
 
 struct QCand {                        // one per (buffer, warp): the warp's speculative candidate
@@ -169,6 +171,21 @@ __device__ __forceinline__ double reduce_rows(const double (&v)[RB], int lane, i
     return w1;
 }
 
+// instance data: read-only path when the caller supplied it; plain loads when this kernel wrote it (GEN)
+template <bool GEN>
+__device__ __forceinline__ double qld(const double* p) {
+    if constexpr (GEN) return *p;
+    else return __ldg(p);
+}
+
+// GEN (fused generate -> solve -> label): the CTA draws its instance itself (philox.cuh: generate_instance_cta, the same
+// counters and summation order as the generator kernels, so the same bits) into the caller's A / b / c or, when those are
+// not asked for, into a per-CTA slab that is rewritten by every LP and therefore lives in L2 -- A never makes an HBM round
+// trip, no generator kernel runs, and the crash scores come out of the generator's shared-memory tile.  At stage 0 the
+// tile registers are free, so the generator runs several independent Box-Muller chains per thread.
+// MASK: reduced LPs (row masks) -- its own instantiation, so that the unmasked kernel carries no trace of it (the kernel sits
+// at the 255-register limit: the two live registers of the mask pointer cost 3.7 % of the throughput)
+template <bool GEN, bool MASK>
 __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double* Dsm = reinterpret_cast<double*>(smem_raw + Q_D);           // [n][QW][QP]: crash inverse, x-vertex in slot QC of every block
@@ -240,7 +257,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 #pragma unroll
                 for (int cs = 0; cs < QCS; ++cs) {
                     const int j = lane + 32 * cs;
-                    v[r][cs] = (i < m && j < n) ? __ldg(Ag + (size_t)i * n + j) : 0.0;
+                    v[r][cs] = (i < m && j < n) ? qld<GEN>(Ag + (size_t)i * n + j) : 0.0;
                 }
             }
             double dot[RB], nn[RB];
@@ -287,18 +304,29 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         __syncthreads();
         const long long lp = *cur_lp;
         if (lp >= a.B) break;
-        const double* Ag = a.A + (size_t)lp * m * n;
-        const double* bg = a.b + (size_t)lp * m;
-        const double* cg = a.c + (size_t)lp * n;
-        const uint8_t* mask = a.row_mask ? a.row_mask + (size_t)lp * m : nullptr;      // reduced LP: rows with mask 0 are left out
+        const double* Ag;
+        const double* bg;
+        const double* cg;
+        const uint8_t* mask = MASK ? a.row_mask + (size_t)lp * m : nullptr;            // reduced LP: rows with mask 0 are left out
 
         // ---- stage 0: crash order by cosine score ------------------------------------------------------------------
-        {
+        if constexpr (GEN) {
+            double* slab = a.slab + (size_t)blockIdx.x * slab_doubles(m, n);
+            double* Aw = a.A ? const_cast<double*>(a.A) + (size_t)lp * m * n : slab;
+            double* bw = a.A ? const_cast<double*>(a.b) + (size_t)lp * m : slab + slab_b_offset(m, n);
+            double* cw = a.A ? const_cast<double*>(a.c) + (size_t)lp * n : slab + slab_c_offset(m, n);
+            generate_instance_cta<7, kQuadGenChains>((uint64_t)a.gen_key, (uint64_t)(a.gen_first + lp), m, n, a.gen_density, Aw, bw, cw,
+                                                     nullptr, Dsm, gbuf, gnn);          // the tile overlays the (dead) crash inverse
+            Ag = Aw; bg = bw; cg = cw;
+        } else {
+            Ag = a.A + (size_t)lp * m * n;
+            bg = a.b + (size_t)lp * m;
+            cg = a.c + (size_t)lp * n;
             double cl[QCS];
 #pragma unroll
             for (int cs = 0; cs < QCS; ++cs) {
                 const int j = lane + 32 * cs;
-                cl[cs] = (j < n) ? __ldg(cg + j) : 0.0;
+                cl[cs] = (j < n) ? qld<GEN>(cg + j) : 0.0;
             }
             row_dots(std::integral_constant<int, 8>{}, Ag, cl, gbuf, gnn);
         }
@@ -321,12 +349,12 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
         }
         __syncthreads();
         int m_eff = m;
-        if (mask) {
+        if constexpr (MASK) {
             m_eff = 0;
             for (int i = 0; i < m; ++i) m_eff += (gnn[i] < kInf);     // uniform, only for reduced LPs
         }
         const int nN = m_eff - n;                                      // live rows; order[m_eff ..) are the excluded ones
-        bool need_generic = nN < 0;                                    // fewer kept rows than columns: the generic kernel's business
+        bool need_generic = MASK ? (nN < 0) : false;                   // fewer kept rows than columns: the generic kernel's business
         int npiv_crash = 0, npiv_p1 = 0, npiv_p2 = 0;
         int status = ST_OPTIMAL;
         int buf = 0;
@@ -340,19 +368,22 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
             const int row = have ? order[t] : 0;
             const double* Ar = Ag + (size_t)row * n + c0;
 #pragma unroll
-            for (int c = 0; c < QC; ++c) T[q][c] = (have && c0 + c < n) ? __ldg(Ar + c) : 0.0;
-            T[q][QC] = have ? __ldg(bg + row) : 0.0;
+            for (int c = 0; c < QC; ++c) T[q][c] = (have && c0 + c < n) ? qld<GEN>(Ar + c) : 0.0;
+            T[q][QC] = have ? qld<GEN>(bg + row) : 0.0;
             lamW[t] = 1.0;
             ilamW[t] = 1.0;
             if (warp == 0) rowvarS[t] = have ? row : -1;
         }
-        gj = hascol ? __ldg(cg + col) : 0.0;
+        gj = hascol ? qld<GEN>(cg + col) : 0.0;
         ghj = hascol ? 1.0 : 0.0;
         bool colfree = hascol;                    // my column still holds a free x_j
         if (tid < QROWS) cvsm[tid] = (tid < n) ? -1 : -2;
         __syncthreads();
 
-        for (int t = 0; t < n && !need_generic; ++t) {
+        for (int t = 0; t < n; ++t) {
+            if constexpr (MASK) {
+                if (need_generic) break;
+            }
             const int lt = t >> 2, qt = t & 3;
             if (lane == lt) publish_slot(prow, T, qt);
             __syncwarp();
@@ -450,20 +481,20 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 #pragma unroll
                     for (int q = 0; q < QR; ++q) {
                         offq[q] = rowq[q] * n;
-                        an[q] = liveq[q] ? __ldg(Ag + offq[q]) : 0.0;
+                        an[q] = liveq[q] ? qld<GEN>(Ag + offq[q]) : 0.0;
                     }
                     for (int k = 0; k < n; ++k) {
 #pragma unroll
                         for (int q = 0; q < QR; ++q) {
                             av[q] = an[q];
-                            an[q] = (liveq[q] && k + 1 < n) ? __ldg(Ag + (offq[q] + k + 1)) : 0.0;
+                            an[q] = (liveq[q] && k + 1 < n) ? qld<GEN>(Ag + (offq[q] + k + 1)) : 0.0;
                         }
                         rank1(Dsm + (size_t)k * QDP + warp * QP, av);
                     }
                 }
 #pragma unroll
                 for (int q = 0; q < QR; ++q) {
-                    if (liveq[q]) T[q][QC] += __ldg(bg + rowq[q]);
+                    if (liveq[q]) T[q][QC] += qld<GEN>(bg + rowq[q]);
                     lamW[t0 + q] = 1.0;
                     ilamW[t0 + q] = 1.0;
                     if (warp == 0) rowvarS[t0 + q] = liveq[q] ? rowq[q] : -1;
@@ -703,7 +734,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 #pragma unroll
                     for (int cs = 0; cs < QCS; ++cs) {
                         const int j = lane + 32 * cs;
-                        if (j < n) acc = fma(__ldg(cg + j), xl[cs], acc);
+                        if (j < n) acc = fma(qld<GEN>(cg + j), xl[cs], acc);
                     }
                     acc = warp_sum(acc);
                     if (lane == 0 && a.obj) a.obj[lp] = acc;
@@ -719,7 +750,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                 nact = 0; nties = 0; nviol = 0;
                 int nref = 0;
                 for (int i = tid; i < m; i += QNT) {
-                    const double slack = __ldg(bg + i) - gbuf[i];
+                    const double slack = qld<GEN>(bg + i) - gbuf[i];
                     const double as = fabs(slack);
                     const int active = as <= a.thr;
                     lab[i] = (uint8_t)active;
@@ -748,7 +779,7 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
                     double rv = 0.0;
                     if (j < n) {
                         const int q = cvsm[j];
-                        rv = __ldg(bg + q) - gbuf[q];
+                        rv = qld<GEN>(bg + q) - gbuf[q];
                         colpos[q] = j;
                     }
                     rho[j] = rv;
@@ -839,17 +870,16 @@ __global__ void __launch_bounds__(QNT, 2) simplex_quadcol_kernel(SolveArgs a) {
 
 }  // namespace
 
-size_t quadcol_scratch_bytes(int grid) { return (size_t)grid * QNT * QR * QC * sizeof(double); }
-int quadcol_grid(int sm_count);
 
 bool quadcol_supported(int m, int n) { return n >= 1 && n <= QNMAX && m >= n && m - n <= QROWS && m <= QMMAX; }
 
+template <bool GEN, bool MASK>
 static int quadcol_ctas_per_sm() {
     static int per_sm = -1;
     if (per_sm < 0) {
         int v = 0;
-        if (cudaFuncSetAttribute(simplex_quadcol_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_TOTAL) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, simplex_quadcol_kernel, QNT, Q_TOTAL) != cudaSuccess)
+        if (cudaFuncSetAttribute(simplex_quadcol_kernel<GEN, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_TOTAL) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, simplex_quadcol_kernel<GEN, MASK>, QNT, Q_TOTAL) != cudaSuccess)
             v = 0;
         per_sm = v;
     }
@@ -857,20 +887,34 @@ static int quadcol_ctas_per_sm() {
 }
 
 int quadcol_grid(int sm_count) {
-    const int per_sm = quadcol_ctas_per_sm();
+    const int per_sm = quadcol_ctas_per_sm<false, false>();
     return sm_count * (per_sm > 0 ? per_sm : 1);
 }
+int quadcol_gen_grid(int sm_count) {
+    const int per_sm = quadcol_ctas_per_sm<true, false>();
+    return sm_count * (per_sm > 0 ? per_sm : 1);
+}
+// the in-solver generator draws pairs: even n; its tile (32 rows + x0 + c + eps) overlays the crash inverse
+bool quadcol_gen_supported(int m, int n) {
+    return quadcol_supported(m, n) && (n & 1) == 0 && gen_smem_doubles(m, n) * sizeof(double) <= (size_t)QNMAX * QDP * 8;
+}
 
-cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st) {
-    const int per_sm = quadcol_ctas_per_sm();
+template <bool GEN, bool MASK>
+static cudaError_t launch_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st) {
+    const int per_sm = quadcol_ctas_per_sm<GEN, MASK>();
     if (per_sm < 1) return cudaErrorLaunchOutOfResources;
     long long grid = (long long)sm_count * per_sm;
     // DDB_QUADCOL_ONE_PER_SM=1: measurement switch (one LP per SM: how much of the throughput is latency hiding between LPs)
     static const bool one = [] { const char* e = getenv("DDB_QUADCOL_ONE_PER_SM"); return e && e[0] == '1'; }();
     if (one) grid = sm_count;
     if (grid > a.B) grid = a.B;
-    simplex_quadcol_kernel<<<(int)grid, QNT, Q_TOTAL, st>>>(a);
+    simplex_quadcol_kernel<GEN, MASK><<<(int)grid, QNT, Q_TOTAL, st>>>(a);
     return cudaGetLastError();
 }
+
+cudaError_t launch_simplex_quadcol(const SolveArgs& a, int sm_count, cudaStream_t st) {
+    return a.row_mask ? launch_quadcol<false, true>(a, sm_count, st) : launch_quadcol<false, false>(a, sm_count, st);
+}
+cudaError_t launch_simplex_quadcol_gen(const SolveArgs& a, int sm_count, cudaStream_t st) { return launch_quadcol<true, false>(a, sm_count, st); }
 
 }  // namespace ddb

@@ -62,7 +62,7 @@ int ddb_device_info(ddb_ctx *ctx, int *sm_count, int *cc_major, int *cc_minor, i
  * 1 = shared-memory tableau, 2 = global-memory (L2/HBM streamed) tableau, 6 = thread-block-cluster kernel (the live
  * tableau in the distributed shared memory of 1-8 SMs: shapes beyond one SM such as (500,250)), 7 = tableau in the
  * register file, rows over lanes and columns over warps (72 <= n <= 100, m - n <= 128, e.g. (200,100), with or without a
- * row mask; the in-solver generator runs on the row-per-thread kernel of plan 0); <0 = error. */
+ * row mask, with or without the in-solver generator); <0 = error. */
 int ddb_solve_plan(ddb_ctx *ctx, int m, int n);
 /* Force a kernel family for testing (-1 = automatic).  Beyond 0..2: 4 = warp-tiled register kernel (the fallback of plan 0
  * for 100 < n <= 111).  3 (2-D register tile) and 5 (software-pipelined rows) are measured negative results that only the
@@ -122,7 +122,7 @@ int ddb_solve_label_host(ddb_ctx *ctx, int64_t B, int m, int n,
  *   mode 2 (automatic choice, the measured-faster one): generator kernel (1) into context scratch, chunk by chunk, chunk
  *          i + 1 generated on a side stream while chunk i is solved;
  *   mode 1: ONE kernel launch -- the thread block that solves instance i draws it first into a per-block slab that stays
- *          in L2, so A never travels through HBM (even n, shapes of the row-per-thread kernel).
+ *          in L2, so A never travels through HBM (even n; shapes of the register-resident kernels, plans 0 and 7).
  * ddb_set_fused_mode(ctx, 0 | 1 | 2) selects (0 = automatic).  A_out/b_out/c_out (device; all three or none) receive the
  * instances when the caller wants them.
  */

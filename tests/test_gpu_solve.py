@@ -638,10 +638,7 @@ def test_fused_in_kernel_generator_is_bit_identical(cuda_device):
             for (m, n, B, dens) in [(200, 100, 700, 1.0), (50, 20, 3000, 1.0), (150, 100, 300, 0.5), (64, 32, 500, 1.0),
                                     (125, 100, 900, 0.1), (75, 20, 1000, 1.0)]:
                 A, b, c = solver.generate(5150, 100, B, m, n, density=dens)
-                if mode == 1:
-                    ctx.set_solve_plan(0)        # the in-solver generator lives in the row-per-thread kernel: compare with that kernel
                 want = _to_np(solver.solve_label(A, b, c))
-                ctx.set_solve_plan(-1)
                 keep = solver.generate_solve_label(5150, 100, B, m, n, density=dens, keep_instances=True)
                 assert (keep['A'] == A).all() and (keep['b'] == b).all() and (keep['c'] == c).all()
                 lean = _to_np(solver.generate_solve_label(5150, 100, B, m, n, density=dens))
