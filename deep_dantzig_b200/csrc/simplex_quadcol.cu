@@ -42,7 +42,7 @@ constexpr int QNMAX = QW * QC;        // columns
 constexpr int QMMAX = 256;            // constraints (order / score arrays)
 constexpr int QDP = QW * QP;          // pitch of a row of D in shared memory
 constexpr unsigned long long QINF = 0x7ff0000000000000ull;   // bit pattern of +inf: "no candidate" among non-negative ratios
-constexpr int kQuadGenChains = 2;     // independent Box-Muller chains per thread of the in-solver generator
+constexpr int kQuadGenChains = 1;     // Box-Muller chains per thread of the in-solver generator (measured: 1 chain 522 k LP/s, 2 chains 495 k, 4 chains 459 k)
 constexpr int QCS = 4;                // column slots of the lane-distributed vectors of stages 0 and 4 (j = lane + 32 cs)
 
 struct QCand {                        // one per (buffer, warp): the warp's speculative candidate
@@ -181,8 +181,8 @@ __device__ __forceinline__ double qld(const double* p) {
 // GEN (fused generate -> solve -> label): the CTA draws its instance itself (philox.cuh: generate_instance_cta, the same
 // counters and summation order as the generator kernels, so the same bits) into the caller's A / b / c or, when those are
 // not asked for, into a per-CTA slab that is rewritten by every LP and therefore lives in L2 -- A never makes an HBM round
-// trip, no generator kernel runs, and the crash scores come out of the generator's shared-memory tile.  At stage 0 the
-// tile registers are free, so the generator runs several independent Box-Muller chains per thread.
+// trip, no generator kernel runs, and the crash scores come out of the generator's shared-memory tile.  More independent Box-Muller
+// chains per thread were measured slower here too (rounding-up waste, instruction-cache pressure), although the tile registers are idle at stage 0.
 // MASK: reduced LPs (row masks) -- its own instantiation, so that the unmasked kernel carries no trace of it (the kernel sits
 // at the 255-register limit: the two live registers of the mask pointer cost 3.7 % of the throughput)
 template <bool GEN, bool MASK>
