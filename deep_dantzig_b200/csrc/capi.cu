@@ -813,7 +813,8 @@ static int fused_launch(ddb_ctx* ctx, uint64_t key, int64_t first_instance, int6
     // Fallback (odd n, shapes outside plan 0): generator kernel -> chunk buffers in context scratch -> solver, chunk i + 1
     // generated on a side stream while chunk i is solved.
     const size_t per_lp = ((size_t)m * n + m + n) * sizeof(double);
-    static const long long chunk_mb = [] { const char* e = getenv("DDB_FUSED_CHUNK_MB"); return e ? atoll(e) : 512ll; }();
+    // (measured on plan 7, 262 144 instances of (200,100): 512 MB 548 k LP/s, 1 GB 554 k, 2 GB 557 k, 4 GB 559 k, 8 GB 561 k)
+    static const long long chunk_mb = [] { const char* e = getenv("DDB_FUSED_CHUNK_MB"); return e ? atoll(e) : 2048ll; }();
     int64_t chunk = (int64_t)((size_t)(chunk_mb << 20) / per_lp);
     const int64_t min_chunk = (int64_t)ctx->sm_count * 4;
     if (chunk < min_chunk) chunk = min_chunk;
