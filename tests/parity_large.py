@@ -1,5 +1,5 @@
 """Large-sample parity run (not collected by pytest: no test_ prefix): GPU generate -> solve -> label against the CPU
-oracle (HiGHS dual simplex + the reference's labelling) on tens of thousands of instances; one JSON line per shape.
+oracle (HiGHS dual simplex, polished to the certified vertex, + the reference's labelling) on tens of thousands of instances; one JSON line per shape.
     python tests/parity_large.py [count_200x100] [count_50x20]
 Lives under tests/ because it executes oracle/ (test infrastructure)."""
 import json, multiprocessing as mp, os, sys, time
@@ -12,7 +12,7 @@ def _worker(args):
     from oracle import randomlp as oracle
     A, b, c = args
     r = oracle.solve_batch(A, b, c)
-    return r['status'], r['labels'], r['obj'], r['x']
+    return r['status'], r['labels'], r['obj'], r['x'], r['oracle_tie'], r['certified']
 
 
 def main():
@@ -31,6 +31,7 @@ def main():
         dt = time.perf_counter() - t0
         cst = np.concatenate([o[0] for o in out]); clab = np.concatenate([o[1] for o in out])
         cobj = np.concatenate([o[2] for o in out]); cx = np.concatenate([o[3] for o in out])
+        otie = np.concatenate([o[4] for o in out]); cert = np.concatenate([o[5] for o in out])
         gst = res['status'].cpu().numpy(); glab = res['labels'].cpu().numpy()
         gobj = res['obj'].cpu().numpy(); gx = res['x'].cpu().numpy(); ties = res['ties'].cpu().numpy()
         opt = cst == 2
@@ -45,7 +46,9 @@ def main():
                           'label_match_pct': 100.0 * float((same_status & same_labels).mean()),
                           'max_rel_obj_diff': float(relobj.max()), 'max_rel_x_diff': float(relx.max()),
                           'optimal_with_exactly_n_labels': int((nact == n).sum()), 'ties_reported': int(ties[both].sum()),
-                          'cpu_seconds': dt, 'cpu_cores': cores, 'oracle': 'scipy HiGHS dual simplex + reference labelling (1e-7 threshold)'}), flush=True)
+                          'oracle_ties': int(otie.sum()), 'oracle_uncertified': int((opt & ~cert.astype(bool)).sum()),
+                          'cpu_seconds': dt, 'cpu_cores': cores,
+                          'oracle': 'scipy HiGHS dual simplex, then the certified extended-precision vertex of its active set (oracle/randomlp.py: polish_vertex) + reference labelling (1e-7 threshold)'}), flush=True)
     pool.close(); pool.join()
 
 
