@@ -1107,6 +1107,9 @@ const RowVariant* row_variants(int* count) {
         DDB_ROW_VARIANT(101, 46, 4, 3, GEN), DDB_ROW_VARIANT(101, 0, 4, 2, GEN),
 #ifndef DDB_ROWREG_ONLY_BIG
         DDB_ROW_VARIANT(101, 0, 8, 1, GEN),
+        // up to 384 live rows ((400,100): the m/n = 4 cells of the configs[2] sweep): hybrid rows at the register budget of
+        // the three-LPs-per-SM variant (65 536 / 384 = 170), one LP per SM, the shared-memory columns take rows x 46 x 8 bytes
+        DDB_ROW_VARIANT(101, 46, 12, 1, GEN),
 #endif
     };
     *count = (int)(sizeof(v) / sizeof(v[0]));

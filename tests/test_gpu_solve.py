@@ -226,6 +226,31 @@ def test_parity_large_global_tableau(cuda_device):
     assert (r['status'] == r2['status']).all() and (r['labels'] == r2['labels']).all()
 
 
+@pytest.mark.parametrize('m,n,N', [(400, 100, 600), (357, 100, 300), (484, 100, 300), (470, 86, 300), (385, 73, 300)])
+def test_twelve_warp_row_variant_agrees_with_the_cluster_kernel(cuda_device, m, n, N):
+    """Shapes with 256 < m - n <= 384 live rows and n <= 100 (the m/n = 4 cells of the configs[2] sweep) run on the hybrid
+    row-per-thread kernel with twelve warps, one LP per SM (plan 0), instead of the thread-block-cluster kernel: same
+    statuses, labels and pivot counts as plan 6 on the same Philox batch, x and objective within 1e-9."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    assert ctx.solve_plan(m, n) == 0
+    dA, db, dc = solver.generate(99, 0, N, m, n)
+    try:
+        ctx.set_solve_plan(0)
+        r0 = _to_np(solver.solve_label(dA, db, dc))
+        ctx.set_solve_plan(6)
+        r6 = _to_np(solver.solve_label(dA, db, dc))
+    finally:
+        ctx.set_solve_plan(-1)
+    for k in ('status', 'labels', 'n_active'):
+        assert (r0[k] == r6[k]).all(), k
+    assert (r0['pivots'] == r6['pivots']).all(axis=1).mean() >= 0.99
+    ok = r0['status'] == 2
+    assert ok.sum() > 0
+    assert np.abs(r0['x'][ok] - r6['x'][ok]).max() <= 1e-9 * np.abs(r6['x'][ok]).max()
+    assert np.abs(r0['obj'][ok] - r6['obj'][ok]).max() <= 1e-9 * np.abs(r6['obj'][ok]).max()
+
+
 @pytest.mark.parametrize('m,n,N', [(300, 150, 200), (400, 100, 150), (500, 250, 80), (260, 130, 200), (450, 200, 60), (600, 300, 24),
                                    (301, 151, 100)])
 def test_cluster_kernel_agrees_with_the_streamed_plan(cuda_device, m, n, N):
@@ -234,7 +259,7 @@ def test_cluster_kernel_agrees_with_the_streamed_plan(cuda_device, m, n, N):
     x and objective within 1e-9."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
-    assert ctx.solve_plan(m, n) == 6
+    assert ctx.solve_plan(m, n) == (0 if (n <= 100 and m - n <= 384) else 6)   # (400,100): the 12-warp row-per-thread variant
     dA, db, dc = solver.generate(4711, 0, N, m, n)
     try:
         ctx.set_solve_plan(6)
