@@ -249,6 +249,26 @@ def test_twelve_warp_row_variant_agrees_with_the_cluster_kernel(cuda_device, m, 
     assert ok.sum() > 0
     assert np.abs(r0['x'][ok] - r6['x'][ok]).max() <= 1e-9 * np.abs(r6['x'][ok]).max()
     assert np.abs(r0['obj'][ok] - r6['obj'][ok]).max() <= 1e-9 * np.abs(r6['obj'][ok]).max()
+    # the same on a sparse cell of the sweep (density 0.1) and on reduced LPs (labels + 30 % random rows kept)
+    import torch
+    sA, sb, sc = solver.generate(100, 0, N // 2, m, n, density=0.1)
+    keep = torch.maximum(torch.from_numpy(r0['labels']).to(dA.device),
+                         (torch.rand(N, m, device=dA.device) < 0.3).to(torch.uint8)).contiguous()
+    try:
+        ctx.set_solve_plan(0)
+        s0 = _to_np(solver.solve_label(sA, sb, sc))
+        m0 = _to_np(solver.solve_label(dA, db, dc, row_mask=keep))
+        ctx.set_solve_plan(6)
+        s6 = _to_np(solver.solve_label(sA, sb, sc))
+        m6 = _to_np(solver.solve_label(dA, db, dc, row_mask=keep))
+    finally:
+        ctx.set_solve_plan(-1)
+    for k in ('status', 'labels', 'n_active', 'violations'):
+        assert (s0[k] == s6[k]).all(), ('sparse', k)
+        assert (m0[k] == m6[k]).all(), ('masked', k)
+    assert (m0['status'] == 2).all() and (m0['violations'] == 0).all() and (m0['labels'] == r0['labels']).all()
+    sok = s0['status'] == 2
+    assert np.abs(s0['x'][sok] - s6['x'][sok]).max() <= 1e-9 * np.abs(s6['x'][sok]).max()
 
 
 @pytest.mark.parametrize('m,n,N', [(300, 150, 200), (400, 100, 150), (500, 250, 80), (260, 130, 200), (450, 200, 60), (600, 300, 24),
