@@ -1106,6 +1106,7 @@ const RowVariant* row_variants(int* count) {
 #endif
         DDB_ROW_VARIANT(101, 46, 4, 3, GEN), DDB_ROW_VARIANT(101, 0, 4, 2, GEN),
 #ifndef DDB_ROWREG_ONLY_BIG
+        DDB_ROW_VARIANT(101, 46, 6, 2, GEN),      // up to 192 live rows: hybrid rows, two LPs per SM (DDB_ROWREG_HYBRID=0: the next one)
         DDB_ROW_VARIANT(101, 0, 8, 1, GEN),
         // up to 384 live rows ((400,100): the m/n = 4 cells of the configs[2] sweep): hybrid rows at the register budget of
         // the three-LPs-per-SM variant (65 536 / 384 = 170), one LP per SM, the shared-memory columns take rows x 46 x 8 bytes
