@@ -463,7 +463,8 @@ static int solve_launch(ddb_ctx* ctx, int64_t B, int m, int n, const double* A, 
         // Register-resident kernels: row-per-thread (plan 0 default; hybrid register + shared-memory rows at (200,100)) and
         // the warp-tiled kernel (plan 4, the fallback of plan 0 for shapes the row kernel does not cover).  Plans 3 / 5
         // (2-D tile, software-pipelined rows) exist only in the `make experiments` build.
-        int which = ddb::rowreg_supported(m, n) ? 1 : 2;
+        // (shapes of the warp-tiled kernel, 100 < n <= 111 with few live rows, stay on it)
+        int which = (ddb::rowreg_supported(m, n) && !(n > 100 && ddb::regtile_supported(m, n))) ? 1 : 2;
         if (plan == 3) which = 0;
         if (plan == 4) which = 2;
         if (plan == 5) which = 3;

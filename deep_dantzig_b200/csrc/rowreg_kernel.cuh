@@ -1111,6 +1111,8 @@ const RowVariant* row_variants(int* count) {
         // up to 384 live rows ((400,100): the m/n = 4 cells of the configs[2] sweep): hybrid rows at the register budget of
         // the three-LPs-per-SM variant (65 536 / 384 = 170), one LP per SM, the shared-memory columns take rows x 46 x 8 bytes
         DDB_ROW_VARIANT(101, 46, 12, 1, GEN),
+        // 100 < n <= 150 ((300,150), (260,130)): hybrid rows, 77 columns in registers and 74 in shared memory, one LP per SM
+        DDB_ROW_VARIANT(151, 74, 5, 1, GEN), DDB_ROW_VARIANT(151, 74, 8, 1, GEN),
 #endif
     };
     *count = (int)(sizeof(v) / sizeof(v[0]));

@@ -227,11 +227,12 @@ def test_parity_large_global_tableau(cuda_device):
 
 
 @pytest.mark.parametrize('m,n,N', [(400, 100, 600), (357, 100, 300), (484, 100, 300), (470, 86, 300), (385, 73, 300),
-                                   (250, 100, 400), (292, 100, 300), (229, 100, 300), (265, 80, 300)])
+                                   (250, 100, 400), (292, 100, 300), (229, 100, 300), (265, 80, 300),
+                                   (300, 150, 300), (260, 130, 300), (280, 120, 300), (400, 150, 200), (380, 125, 200)])
 def test_wide_row_variants_agree_with_the_cluster_kernel(cuda_device, m, n, N):
     """Shapes with 256 < m - n <= 384 live rows and n <= 100 (the m/n = 4 cells of the configs[2] sweep) run on the hybrid
     row-per-thread kernel with twelve warps, one LP per SM (plan 0), instead of the thread-block-cluster kernel; shapes
-    with 128 < m - n <= 192 on its six-warp variant, two LPs per SM: same statuses, labels and pivot counts as plan 6 on
+    with 128 < m - n <= 192 on its six-warp variant, two LPs per SM; 100 < n <= 150 on 151-column variants: same statuses, labels and pivot counts as plan 6 on
     the same Philox batch, x and objective within 1e-9."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
@@ -281,7 +282,8 @@ def test_cluster_kernel_agrees_with_the_streamed_plan(cuda_device, m, n, N):
     x and objective within 1e-9."""
     from deep_dantzig_b200 import solver, _lib
     ctx = _lib.context(0)
-    assert ctx.solve_plan(m, n) == (0 if (n <= 100 and m - n <= 384) else 6)   # (400,100): the 12-warp row-per-thread variant
+    wide = (n <= 100 and m - n <= 384) or (n <= 150 and max(n, m - n) <= 256)      # wide row-per-thread variants of plan 0
+    assert ctx.solve_plan(m, n) == (0 if wide else 6)
     dA, db, dc = solver.generate(4711, 0, N, m, n)
     try:
         ctx.set_solve_plan(6)
