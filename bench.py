@@ -372,7 +372,7 @@ def run_ours(args):
         from deep_dantzig_b200 import phase_transitions
         from deep_dantzig_b200.ml.models.s2v import Model as _Model
         from deep_dantzig_b200.ml import train as _train
-        phase_transitions.sweep_ratio_density(per_cell=512, device=local)                 # warm-up (all shapes' kernels)
+        phase_transitions.warm_up_sweep(device=local)                                     # warm-up (all shapes' kernels, on every rank)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()

@@ -47,6 +47,15 @@ def compute_phaseTransitions(save_path, dataset, benchmark_params, cuda=False, t
     return records
 
 
+def warm_up_sweep(n=100, ratios=(1.25, 1.5, 2.0, 3.0, 4.0), densities=(1.0, 0.5, 0.1), chunk=2048, device=0):
+    """One untimed chunk of EVERY cell on this rank (kernels loaded, scratch sized for the chunk), whatever cells the timed
+    sweep will deal to it."""
+    for r in ratios:
+        for d in densities:
+            solver.generate_solve_label(0, 0, chunk, int(round(r * n)), n, density=d, device=device)
+    torch.cuda.synchronize(device)
+
+
 def sweep_ratio_density(n=100, ratios=(1.25, 1.5, 2.0, 3.0, 4.0), densities=(1.0, 0.5, 0.1), per_cell=10000, chunk=2048,
                         key=0, device=0):
     """BASELINE.json config 3: grid over m/n and density of A; the (cell, chunk) list is dealt round-robin to the ranks

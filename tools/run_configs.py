@@ -20,7 +20,8 @@ if world > 1:
 
 # ---- config 3 ----------------------------------------------------------------------------------------------------------
 per_cell = int(os.environ.get('DDB_PER_CELL', '10000'))
-sweep_ratio_density(n=100, per_cell=256, chunk=256, key=299, device=local)          # warm-up: every cell's kernels loaded, scratch allocated
+from deep_dantzig_b200.phase_transitions import warm_up_sweep
+warm_up_sweep(n=100, device=local)                                                  # warm-up: every cell's kernels loaded, scratch allocated, on every rank
 torch.cuda.synchronize(); t0 = time.perf_counter()
 sw = sweep_ratio_density(n=100, per_cell=per_cell, chunk=2048, key=300, device=local)
 torch.cuda.synchronize(); dt = time.perf_counter() - t0
