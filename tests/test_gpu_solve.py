@@ -675,6 +675,27 @@ def test_register_resident_and_generic_kernels_agree(cuda_device, m, n, N, plan0
     assert np.abs(r0['obj'][ok] - r1['obj'][ok]).max() <= 1e-9 * np.abs(r1['obj'][ok]).max()
 
 
+@pytest.mark.parametrize('m,n,B,dens', [(400, 100, 300, 1.0), (250, 100, 400, 1.0), (300, 150, 300, 1.0), (400, 150, 200, 0.1),
+                                        (484, 100, 200, 0.5)])
+def test_in_kernel_generator_on_the_wide_row_variants(cuda_device, m, n, B, dens):
+    """Fused mode 1 (the instance drawn inside the solver CTA) on the six- / twelve-warp and 151-column row variants: the
+    same instance bits as the generator entry point and the same results as solving the materialised instances
+    (tools/check_gen_variants.py is the same check as a script)."""
+    from deep_dantzig_b200 import solver, _lib
+    ctx = _lib.context(0)
+    A, b, c = solver.generate(61, 7, B, m, n, density=dens)
+    want = solver.solve_label(A, b, c)
+    ctx.set_fused_mode(1)
+    try:
+        got = solver.generate_solve_label(61, 7, B, m, n, density=dens)
+        keep = solver.generate_solve_label(61, 7, B, m, n, density=dens, keep_instances=True)
+    finally:
+        ctx.set_fused_mode(0)
+    assert (keep['A'] == A).all() and (keep['b'] == b).all() and (keep['c'] == c).all()
+    for k in ('status', 'labels', 'pivots', 'n_active', 'ties', 'x'):
+        assert (got[k] == want[k]).all() and (keep[k] == want[k]).all(), k
+
+
 def test_fused_in_kernel_generator_is_bit_identical(cuda_device):
     """The fused call draws each instance inside the solver CTA.  Same (key, index) -> the same instance bits as the
     generator entry point, and -- same kernel arithmetic on the same bits -- the same results bit for bit as solving the
