@@ -48,6 +48,18 @@ def test_sass_is_sm100a_with_bulk_tma(built):
     assert 'DFMA' in out
 
 
+def test_row_variants_are_in_the_shipped_cubin(built):
+    """Every instantiation of the row-per-thread kernel the dispatch table names (rowreg_kernel.cuh: row_variants) is in the
+    library, with and without the in-solver generator -- including the wide variants (six / twelve warps, 151 columns)."""
+    out = subprocess.run(['cuobjdump', '-elf', built], capture_output=True, text=True, check=True).stdout
+    src = open(os.path.join(os.path.dirname(built), 'csrc', 'rowreg_kernel.cuh')).read()
+    table = re.findall(r'DDB_ROW_VARIANT\((\d+), (\d+), (\d+), (\d+), GEN\)', src)
+    assert len(table) >= 13 and ('101', '46', '12', '1') in table and ('151', '74', '5', '1') in table
+    for nc, ts, w, minb in table:
+        for gen in '01':
+            assert 'simplex_rowreg_kernelILi%sELi%sELi%sELi%sELb%s' % (nc, ts, w, minb, gen) in out, (nc, ts, w, minb, gen)
+
+
 def test_no_cpu_fallback_without_device(built):
     import torch
     if torch.cuda.is_available():
